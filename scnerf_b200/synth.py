@@ -1,0 +1,118 @@
+"""Deterministic synthetic inputs for the SCNeRF hot path.
+
+Pure numpy (PCG64 streams are stable across machines), so the golden-vector
+generator (run next to the reference), the CPU oracle tests, the GPU parity
+tests and ``bench.py`` all see byte-identical inputs without shipping weights.
+
+Nothing here is on the product path: it only manufactures inputs.
+"""
+from __future__ import annotations
+
+import types
+import numpy as np
+
+# LLFF fern at factor=8: H=378, W=504, 20 images -> 17 train views.
+FERN_H, FERN_W, FERN_NCAM, FERN_FOCAL = 378, 504, 17, 407.5
+
+
+def camera_args(camera_model="pinhole_rot_noise_10k_rayo_rayd", ray_o_noise_scale=1e-3,
+                ray_d_noise_scale=1e-3, extrinsics_noise_scale=1.0,
+                intrinsics_noise_scale=1.0, grid_size=10, multiplicative_noise=True,
+                distortion_noise_scale=1e-2):
+    """Flag namespace the camera classes read (NeRF/config_argparse.py:166,270-304)."""
+    return types.SimpleNamespace(
+        camera_model=camera_model, ray_o_noise_scale=ray_o_noise_scale,
+        ray_d_noise_scale=ray_d_noise_scale, extrinsics_noise_scale=extrinsics_noise_scale,
+        intrinsics_noise_scale=intrinsics_noise_scale, grid_size=grid_size,
+        multiplicative_noise=multiplicative_noise,
+        distortion_noise_scale=distortion_noise_scale)
+
+
+def _axis_angle_matrix(axis, angle):
+    axis = axis / np.linalg.norm(axis)
+    x, y, z = axis
+    c, s = np.cos(angle), np.sin(angle)
+    C = 1.0 - c
+    return np.array([[c + x * x * C, x * y * C - z * s, x * z * C + y * s],
+                     [y * x * C + z * s, c + y * y * C, y * z * C - x * s],
+                     [z * x * C - y * s, z * y * C + x * s, c + z * z * C]])
+
+
+def camera_poses(seed=0, n_cams=FERN_NCAM, max_deg=10.0, t_range=0.3):
+    """[n,4,4] float32 camera-to-world poses: small rotations about identity,
+    translations U(-t_range, t_range)^3 (post-recenter LLFF scale)."""
+    rng = np.random.default_rng(seed)
+    out = np.tile(np.eye(4), (n_cams, 1, 1))
+    for i in range(n_cams):
+        axis = rng.standard_normal(3)
+        ang = np.deg2rad(rng.uniform(-max_deg, max_deg))
+        out[i, :3, :3] = _axis_angle_matrix(axis, ang)
+        out[i, :3, 3] = rng.uniform(-t_range, t_range, 3)
+    return out.astype(np.float32)
+
+
+def intrinsic_init(H=FERN_H, W=FERN_W, focal=FERN_FOCAL):
+    """4x4 K as NeRF/create_nerf.py:101-108 builds it (fx=fy=focal, principal point at centre)."""
+    return np.array([[focal, 0, W / 2, 0], [0, focal, H / 2, 0],
+                     [0, 0, 1, 0], [0, 0, 0, 1]], dtype=np.float32)
+
+
+def camera_noise_state(seed, n_cams=FERN_NCAM, H=FERN_H, W=FERN_W, grid_size=10,
+                       sigma_ie=1e-3, sigma_od=1.0, with_distortion=False):
+    """Non-trivial values for the learnable camera parameters so every gradient is exercised."""
+    rng = np.random.default_rng(seed + 1000)
+    st = {
+        "intrinsics_noise": rng.standard_normal(4) * sigma_ie,
+        "extrinsics_noise": rng.standard_normal((n_cams, 9)) * sigma_ie,
+        "ray_o_noise": rng.standard_normal((H // grid_size, W // grid_size, 3)) * sigma_od,
+        "ray_d_noise": rng.standard_normal((H // grid_size, W // grid_size, 3)) * sigma_od,
+    }
+    if with_distortion:
+        st["distortion_noise"] = rng.standard_normal(2) * 1e-2
+    return {k: v.astype(np.float32) for k, v in st.items()}
+
+
+def mlp_layer_shapes(D=8, W=256, input_ch=63, input_ch_views=27, output_ch=5,
+                     skips=(4,), use_viewdirs=True):
+    """(name, out, in, activation) in ``NeRF.parameters()`` order."""
+    layers = [("pts_linears.0", W, input_ch, "relu")]
+    for i in range(D - 1):
+        fan_in = W + input_ch if i in skips else W
+        layers.append((f"pts_linears.{i + 1}", W, fan_in, "relu"))
+    layers.append(("views_linears.0", W // 2, input_ch_views + W, "relu"))
+    if use_viewdirs:
+        layers += [("feature_linear", W, W, "linear"), ("alpha_linear", 1, W, "linear"),
+                   ("rgb_linear", 3, W // 2, "linear")]
+    else:
+        layers.append(("output_linear", output_ch, W, "linear"))
+    return layers
+
+
+def mlp_state(seed, bias_sigma=0.05, **kw):
+    """Xavier-uniform weights (gain sqrt2 for relu layers, 1 for linear heads —
+    NeRF/run_nerf_helpers.py:18-21) and small NON-zero biases (the reference
+    zero-inits them; non-zero exercises the bias path)."""
+    rng = np.random.default_rng(seed + 2000)
+    st = {}
+    for name, fo, fi, act in mlp_layer_shapes(**kw):
+        gain = np.sqrt(2.0) if act == "relu" else 1.0
+        a = gain * np.sqrt(6.0 / (fi + fo))
+        st[name + ".weight"] = rng.uniform(-a, a, (fo, fi)).astype(np.float32)
+        st[name + ".bias"] = (rng.standard_normal(fo) * bias_sigma).astype(np.float32)
+    return st
+
+
+def pixel_batch(seed, N, H=FERN_H, W=FERN_W, n_cams=FERN_NCAM):
+    """kps[N,2] int64 as (x, y), per-ray camera index idx[N] int64, target rgb[N,3] f32."""
+    rng = np.random.default_rng(seed + 3000)
+    kps = np.stack([rng.integers(0, W, N), rng.integers(0, H, N)], -1).astype(np.int64)
+    idx = rng.integers(0, n_cams, N).astype(np.int64)
+    target = rng.uniform(0, 1, (N, 3)).astype(np.float32)
+    return kps, idx, target
+
+
+def reference_pytest_rand(shape):
+    """What the reference draws when ``pytest=True``: ``np.random.seed(0); np.random.rand(*shape)``
+    cast to float32 (NeRF/render.py:252-255, 333-336, 432-440)."""
+    np.random.seed(0)
+    return np.random.rand(*shape).astype(np.float32)

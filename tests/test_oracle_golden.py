@@ -1,0 +1,193 @@
+"""Pin the CPU oracle against outputs of the reference itself (tests/golden/*.npz, produced by
+tests/golden/make_golden.py importing /root/reference).  CPU only."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import scnerf_oracle as O
+from scnerf_b200 import synth
+
+H, W, FOCAL = synth.FERN_H, synth.FERN_W, synth.FERN_FOCAL
+T = torch.from_numpy
+
+
+def close(a, b, rtol=1e-5, atol=1e-6):
+    a = a.detach().numpy() if isinstance(a, torch.Tensor) else np.asarray(a)
+    np.testing.assert_allclose(a, b, rtol=rtol, atol=atol)
+
+
+def make_cam(seed, mult=True, requires_grad=False):
+    cam = O.Camera(synth.intrinsic_init(), synth.camera_poses(seed),
+                   synth.camera_args(multiplicative_noise=mult), H, W)
+    return cam.load(synth.camera_noise_state(seed), requires_grad)
+
+
+def test_camera(golden):
+    g = golden("camera")
+    for mult, tag in ((True, "mult"), (False, "add")):
+        cam = make_cam(1, mult)
+        close(cam.intrinsic(), g[f"K_{tag}"], 1e-6, 0)
+        close(cam.extrinsic(), g[f"E_{tag}"], 1e-6, 1e-7)
+    cam = make_cam(1)
+    sel = T(g["field_sel"])
+    close(cam.ray_o_field()[sel], g["ray_o_field"], 1e-6, 1e-9)
+    close(cam.ray_d_field()[sel], g["ray_d_field"], 1e-6, 1e-9)
+    # closed-form bilinear lookup (what the CUDA kernel implements) == F.interpolate path
+    ys, xs = sel // W, sel % W
+    close(O.bilinear_grid_lookup(cam.ray_o_noise, ys, xs, H, W, cam.args.ray_o_noise_scale),
+          g["ray_o_field"], 1e-4, 2e-9)
+    close(cam.extrinsic()[5], g["fwd5_E"], 1e-6, 1e-7)
+
+
+def test_raygen(golden):
+    g = golden("raygen")
+    cam = make_cam(2)
+    kps, idx, _ = synth.pixel_batch(2, 256)
+    kps, idx = T(kps), T(idx)
+    o, d = O.rays_pixels_camera(H, W, cam, kps, idx=idx)
+    close(o, g["kps_idx_o"]); close(d, g["kps_idx_d"])
+    o, d = O.rays_pixels_camera(H, W, cam, kps, idx=3)
+    close(o, g["kps_int_o"]); close(d, g["kps_int_d"])
+    ext = T(synth.camera_poses(7)[4])
+    o, d = O.rays_pixels_camera(H, W, cam, kps, extrinsic=ext)
+    close(o, g["kps_ext_o"]); close(d, g["kps_ext_d"])
+    o, d = O.rays_pixels_camera(H, W, cam, kps, extrinsic=T(synth.camera_poses(8, n_cams=256)))
+    close(o, g["kps_extN_o"]); close(d, g["kps_extN_d"])
+    sel = T(g["full_sel"])
+    o, d = O.rays_full_image_camera(H, W, cam, ext)
+    close(o[sel], g["full_cam_o"]); close(d[sel], g["full_cam_d"])
+    o, d = O.rays_full_image_pinhole(H, W, FOCAL, ext)
+    close(o.reshape(-1, 3)[sel], g["full_pin_o"]); close(d.reshape(-1, 3)[sel], g["full_pin_d"])
+    o, d = O.rays_pixels_pinhole(H, W, FOCAL, ext, kps)
+    close(o, g["kps_pin_o"]); close(d, g["kps_pin_d"])
+    no, nd = O.ndc_project(H, W, FOCAL, FOCAL, 1., o, d)
+    close(no, g["ndc_pin_o"], 1e-5, 1e-6); close(nd, g["ndc_pin_d"], 1e-5, 1e-6)
+    o, d = O.rays_pixels_camera(H, W, cam, kps, idx=idx)
+    K = cam.intrinsic()
+    no, nd = O.ndc_project(H, W, K[0, 0], K[1, 1], 1., o, d)
+    close(no, g["ndc_cam_o"], 1e-5, 1e-6); close(nd, g["ndc_cam_d"], 1e-5, 1e-6)
+
+
+def test_field(golden):
+    g = golden("field")
+    x, v = O.posenc(T(g["pts"]), 10), O.posenc(T(g["dirs"]), 4)
+    close(x, g["pe_pts"], 0, 0); close(v, g["pe_dirs"], 0, 0)
+    P = O.state_to_tensors(synth.mlp_state(3))
+    close(O.mlp_forward(P, x, v), g["raw"], 1e-5, 1e-6)
+    P = O.state_to_tensors(synth.mlp_state(4, use_viewdirs=False, input_ch_views=0))
+    close(O.mlp_forward(P, x, None), g["raw_noview"], 1e-5, 1e-6)
+
+
+def test_composite(golden):
+    g = golden("composite")
+    raw, z, d = T(g["raw"]), T(g["z"]), T(g["d"])
+    for std, wb, tag in ((0., False, "plain"), (1., False, "noise"), (0., True, "white"), (0.5, True, "noise_white")):
+        noise = T(synth.reference_pytest_rand(z.shape)) * std if std > 0 else None
+        r = O.composite(raw, z, d, noise, wb)
+        for name, val in zip(("rgb", "disp", "acc", "weights", "depth"), r):
+            close(val, g[f"{tag}_{name}"], 1e-6, 1e-7)
+
+
+def test_sample_pdf(golden):
+    g = golden("sample_pdf")
+    bins, w = T(g["bins"]), T(g["weights"])
+    # pytest=True + det draws u from float64 np.linspace cast to f32 (NeRF/render.py:436-437)
+    u = T(np.linspace(0., 1., 128).astype(np.float32)).expand(64, 128)
+    s, inds = O.inverse_cdf_sample(bins, w, u, return_inds=True)
+    assert np.array_equal(inds.numpy(), g["det_inds"])
+    close(s, g["det_samples"], 0, 0)
+    u = T(synth.reference_pytest_rand((64, 128)))
+    s, inds = O.inverse_cdf_sample(bins, w, u, return_inds=True)
+    assert np.array_equal(inds.numpy(), g["rand_inds"])
+    close(s, g["rand_samples"], 0, 0)
+
+
+def test_render_c1(golden):
+    """BASELINE.json configs[0]."""
+    g = golden("render_c1")
+    kps = T(g["kps"])
+    c2w = T(synth.camera_poses(5)[0])
+    P = O.state_to_tensors(synth.mlp_state(5))
+    o, d = O.rays_pixels_pinhole(H, W, FOCAL, c2w, kps)
+    rays = O.pack_rays(H, W, o, d, 0., 1., True, True, FOCAL, FOCAL)
+    for tag in ("det", "rand"):
+        rnd = T(synth.reference_pytest_rand((256, 64))) if tag == "rand" else None
+        with torch.no_grad():
+            r = O.clamp_rgb_(O.render_rays(rays, P, None, 64, 0, t_rand=rnd, noise0=rnd, retraw=True))
+        close(r["rgb_map"], g[f"{tag}_rgb"], 1e-5, 1e-6)
+        close(r["disp_map"], g[f"{tag}_disp"], 1e-5, 1e-6)
+        close(r["acc_map"], g[f"{tag}_acc"], 1e-5, 1e-6)
+        close(r["raw"][:16], g[f"{tag}_raw"], 1e-4, 1e-5)
+
+
+def test_render_c2mini(golden):
+    g = golden("render_c2mini")
+    N = 64
+    cam = make_cam(6)
+    kps, idx, _ = synth.pixel_batch(6, N)
+    Pc, Pf = O.state_to_tensors(synth.mlp_state(6)), O.state_to_tensors(synth.mlp_state(7))
+    for perturb, std, wb, tag in ((0, 0., False, "det"), (1, 1., False, "rand"), (1, 0., True, "white")):
+        t_rand = T(synth.reference_pytest_rand((N, 64))) if perturb else None
+        u = T(synth.reference_pytest_rand((N, 128))) if perturb else None
+        n0 = T(synth.reference_pytest_rand((N, 64))) * std if std > 0 else None
+        n1 = T(synth.reference_pytest_rand((N, 192))) * std if std > 0 else None
+        with torch.no_grad():
+            o, d = O.rays_pixels_camera(H, W, cam, T(kps), idx=T(idx))
+            K = cam.intrinsic()
+            rays = O.pack_rays(H, W, o, d, 0., 1., True, True, K[0, 0], K[1, 1])
+            r = O.clamp_rgb_(O.render_rays(rays, Pc, Pf, 64, 128, white_bkgd=wb, t_rand=t_rand, u=u,
+                                           noise0=n0, noise1=n1, retraw=True))
+        for k, gk in (("rgb_map", "rgb"), ("disp_map", "disp"), ("acc_map", "acc"), ("rgb0", "rgb0"),
+                      ("disp0", "disp0"), ("acc0", "acc0"), ("z_std", "z_std")):
+            close(r[k], g[f"{tag}_{gk}"], 2e-5, 2e-6)
+        close(r["raw"][:8], g[f"{tag}_raw"], 1e-4, 1e-5)
+
+
+def test_train_step_gradients(golden):
+    g = golden("train_step")
+    N = 96
+    cam = make_cam(8, requires_grad=True)
+    kps, idx, target = synth.pixel_batch(8, N)
+    Pc = O.state_to_tensors(synth.mlp_state(8), requires_grad=True)
+    Pf = O.state_to_tensors(synth.mlp_state(9), requires_grad=True)
+    loss, ret, _ = O.train_step(
+        cam, Pc, Pf, T(kps), T(idx), T(target), H, W, 64, 128,
+        t_rand=T(synth.reference_pytest_rand((N, 64))), u=T(synth.reference_pytest_rand((N, 128))),
+        noise0=T(synth.reference_pytest_rand((N, 64))), noise1=T(synth.reference_pytest_rand((N, 192))))
+    loss.backward()
+    close(loss, g["loss"], 1e-5, 0)
+    close(ret["rgb_map"], g["rgb"], 2e-5, 2e-6)
+    for k in O.Camera.LEARNABLE:
+        ref = g["g_cam_" + k]
+        # fp32 noise floor: the reference's own fp32 camera gradients sit 3e-3..9e-3 (of max|g|)
+        # from an fp64 evaluation (PE frequencies up to 2^9 amplify round-off), and two fp32
+        # evaluations with different accumulation order differ by up to ~2e-3.
+        close(getattr(cam, k).grad, ref, 0, 5e-3 * np.abs(ref).max())
+    rng = np.random.default_rng(99)
+    for tag, P in (("coarse", Pc), ("fine", Pf)):
+        for name, _fo, _fi, _a in synth.mlp_layer_shapes():
+            for suffix in (".weight", ".bias"):
+                key = name + suffix
+                gr = P[key].grad.double().reshape(-1)
+                probe = T(rng.standard_normal(gr.numel()))
+                pin = g[f"gpin_{tag}_{key}"]
+                got = np.array([gr.norm().item(), (gr * probe).sum().item(), gr.abs().max().item()])
+                np.testing.assert_allclose(got, pin, rtol=5e-3, atol=5e-3 * pin[0])
+                if f"g_{tag}_{key}" in g:
+                    ref = g[f"g_{tag}_{key}"]
+                    close(P[key].grad, ref, 0, 5e-3 * np.abs(ref).max())
+
+
+@pytest.mark.parametrize("right", [False, True])
+def test_searchsorted_rows_matches_torch(right):
+    """Same grid as NeRF/torchsearchsorted/test/test_searchsorted.py:27-44 (subset of repeats)."""
+    rng = np.random.default_rng(5)
+    for Ba, Bv in ((1, 100), (100, 1), (100, 100)):
+        for A in (1, 50, 500):
+            for V in (1, 12, 120):
+                a = np.sort(rng.random((Ba, A)).astype(np.float32), -1)
+                v = rng.random((Bv, V)).astype(np.float32)
+                got = O.searchsorted_rows(a, v, right)
+                nrow = max(Ba, Bv)
+                ref = torch.searchsorted(T(a).expand(nrow, A).contiguous(), T(v).expand(nrow, V).contiguous(), right=right)
+                assert np.array_equal(got, ref.numpy())
