@@ -1,0 +1,135 @@
+"""CPU-side checks: the C-ABI library loads and exports every symbol the header declares; host
+logic (flat gradient buffer, all-reduce over gloo with world_size 2, ray sharding) works; the
+product path refuses CPU tensors instead of falling back."""
+import os
+import re
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _ensure_built():
+    from scnerf_b200 import _lib
+    if not os.path.exists(_lib.LIB_PATH):
+        import __graft_entry__ as g
+        g.build()
+    return _lib
+
+
+def test_header_symbols_exported():
+    _lib = _ensure_built()
+    lib = _lib.load()
+    header = open(os.path.join(ROOT, "include", "scnerf_b200.h")).read()
+    declared = set(re.findall(r"\b(scnerf_[a-z0-9_]+)\s*\(", header))
+    assert declared, "no declarations parsed"
+    for name in sorted(declared):
+        assert hasattr(lib, name), f"{name} declared in the header but not exported"
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    assert lib.scnerf_abi_version() == 1
+    assert lib.scnerf_built_for_sm() == 100
+
+
+def test_struct_sizes_match_header():
+    """ctypes mirrors must have the C layout (pointer-heavy structs: cheap sanity on sizes)."""
+    import ctypes as C
+    _lib = _ensure_built()
+    assert C.sizeof(_lib.Camera) == 6 * 8 + 4 * 4 + 6 * 4
+    assert C.sizeof(_lib.Mlp) == 9 * 4 + 4 + (2 * 16 + 10) * 8          # 9 ints + pad + pointers
+    assert C.sizeof(_lib.RenderCfg) == 48
+    assert C.sizeof(_lib.RaygenArgs) == 8 + 4 * 3 + 4 + 8 * 4 + 8 + 8
+
+
+def test_no_cpu_fallback():
+    _lib = _ensure_built()
+    with pytest.raises(RuntimeError, match="CUDA"):
+        _lib.ptr(torch.zeros(3))
+    from scnerf_b200.render import searchsorted
+    with pytest.raises(RuntimeError):
+        searchsorted(torch.zeros(1, 4), torch.zeros(1, 2))
+
+
+def test_missing_library_is_loud(monkeypatch, tmp_path):
+    from scnerf_b200 import _lib
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "LIB_PATH", str(tmp_path / "nope.so"))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        _lib.load()
+
+
+def test_modules_have_reference_state_dict_keys():
+    """checkpoint compatibility."""
+    from tests.util import build_modules
+    from scnerf_b200.run_nerf_helpers import SingleDeviceParallel
+    m = build_modules(0, "cpu")
+    keys = list(m["coarse"].state_dict())
+    assert keys[:4] == ["pts_linears.0.weight", "pts_linears.0.bias", "pts_linears.1.weight", "pts_linears.1.bias"]
+    assert m["coarse"].state_dict()["pts_linears.5.weight"].shape == (256, 319)
+    assert m["coarse"].state_dict()["views_linears.0.weight"].shape == (128, 283)
+    assert sum(p.numel() for p in m["coarse"].parameters()) == 595844
+    assert list(SingleDeviceParallel(m["coarse"]).state_dict())[0] == "module.pts_linears.0.weight"
+    cam = m["cam"]
+    assert [n for n, _ in cam.named_parameters()] == [
+        "intrinsics_initial", "extrinsics_initial", "intrinsics_noise", "extrinsics_noise",
+        "ray_o_noise", "ray_d_noise"]
+    assert cam.ray_o_noise.shape == (37, 50, 3) and not cam.intrinsics_initial.requires_grad
+    # API-parity getters agree with the oracle
+    from oracle import scnerf_oracle as O
+    from scnerf_b200 import synth
+    oc = O.Camera(synth.intrinsic_init(), synth.camera_poses(0), synth.camera_args(), 378, 504)
+    oc.load(synth.camera_noise_state(0))
+    np.testing.assert_allclose(cam.get_intrinsic().detach().numpy(), oc.intrinsic().numpy(), rtol=1e-6)
+    np.testing.assert_allclose(cam.get_extrinsic().detach().numpy(), oc.extrinsic().numpy(), rtol=1e-5, atol=1e-7)
+    K5, E5 = cam(5)
+    np.testing.assert_allclose(E5.detach().numpy(), oc.extrinsic()[5].numpy(), rtol=1e-5, atol=1e-7)
+
+
+def test_shard_rays_partition():
+    from scnerf_b200.parallel import shard_rays
+    for n, ws in ((190512, 8), (4096, 3), (7, 4)):
+        spans = [shard_rays(n, r, ws) for r in range(ws)]
+        assert spans[0][0] == 0 and spans[-1][1] == n
+        assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+        assert max(h - l for l, h in spans) - min(h - l for l, h in spans) <= 1
+
+
+def _gloo_worker(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from scnerf_b200.parallel import FlatGrads
+    named = [("a", torch.zeros(3, 4)), ("b", torch.zeros(5))]
+    fg = FlatGrads(named, "cpu")
+    fg.views["a"].fill_(float(rank + 1))
+    fg.views["b"].copy_(torch.arange(5.) * (rank + 1))
+    fg.all_reduce_mean()
+    q.put((rank, fg.flat.clone().numpy()))
+    dist.destroy_process_group()
+
+
+def test_flat_grad_allreduce_gloo_world2():
+    """The N>1 path on CPU: world_size-2 gloo, one collective over the flat buffer, mean."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, q)) for r in range(2)]
+    [p.start() for p in procs]
+    res = dict(q.get(timeout=120) for _ in range(2))
+    [p.join(60) for p in procs]
+    want = np.concatenate([np.full(12, 1.5), np.arange(5.) * 1.5]).astype(np.float32)
+    for r in range(2):
+        np.testing.assert_allclose(res[r], want)
+
+
+def test_synth_is_deterministic():
+    from scnerf_b200 import synth
+    a, b = synth.mlp_state(3), synth.mlp_state(3)
+    assert all(np.array_equal(a[k], b[k]) for k in a)
+    k1, i1, t1 = synth.pixel_batch(9, 64)
+    k2, i2, t2 = synth.pixel_batch(9, 64)
+    assert np.array_equal(k1, k2) and np.array_equal(i1, i2) and np.array_equal(t1, t2)
+    assert k1[:, 0].max() < synth.FERN_W and k1[:, 1].max() < synth.FERN_H
