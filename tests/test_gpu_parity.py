@@ -321,4 +321,3 @@ def test_render_no_grad_full_image_chunks(lib):
         b = batchify_rays(rays, 3000, **kw)
     for k in a:
         assert torch.equal(a[k], b[k]), k
-EOF
