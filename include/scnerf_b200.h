@@ -240,6 +240,12 @@ int scnerf_train_step(const scnerf_camera* cam, const scnerf_camera_grads* g_cam
                       const scnerf_step_io* io, int32_t inputs_on_host, int64_t N, void* workspace,
                       size_t workspace_bytes, void* stream);
 
+/* Hardware self-test of the tcgen05 building blocks (descriptor encodings, TMEM, bulk copy):
+ * D[128,N] = bf16(A[128,K]) * bf16(B[N,K])^T with fp32 accumulation, one CTA.
+ * variant bit0 swaps the LBO/SBO descriptor fields (diagnostic), bit1 stages through cp.async.bulk. */
+int scnerf_tc_selftest(const float* A, const float* B, float* D, int32_t N, int32_t K, int32_t variant,
+                       void* workspace, size_t workspace_bytes, void* stream);
+
 /* Kernel-launch counter (bench.py's gpu_launches): number of kernels this library has launched
  * in this process since the last reset. */
 int64_t scnerf_launch_count(int32_t reset);

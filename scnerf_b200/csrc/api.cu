@@ -32,6 +32,12 @@ int64_t scnerf_launch_count(int32_t reset) {
   return v;
 }
 
+int scnerf_tc_selftest(const float* A, const float* B, float* D, int32_t N, int32_t K, int32_t variant,
+                       void* workspace, size_t workspace_bytes, void* stream) {
+  SCNERF_CHECK_ARG(A && B && D, "selftest: null pointer");
+  return tc_selftest(A, B, D, N, K, variant, workspace, workspace_bytes, stream);
+}
+
 int scnerf_searchsorted_f32(const float* a, const float* v, int64_t* out, int64_t nrow_a,
                             int64_t nrow_v, int64_t ncol_a, int64_t ncol_v, int right, void* stream) {
   SCNERF_CHECK_ARG(a && v && out, "searchsorted: null pointer");

@@ -1,10 +1,138 @@
-// Fused tcgen05 field forward (placeholder until the kernel lands in this file).
+// Tensor-core (tcgen05) field path.
+//  - pack_canon_kernel: fp32 nn.Linear weights -> bf16 (hi[,lo]) images in the UMMA canonical
+//    no-swizzle K-major layout, so a weight K-slab is ONE contiguous byte range that a 1-D bulk
+//    async copy (TMA, cp.async.bulk) can drop into shared memory with no tensor map.
+//  - tc_selftest_kernel: single-tile GEMM that pins the descriptor encodings on hardware.
+//  - field_tc_fwd: fused PE + MLP forward (see field_tc_fused.cuh).
 #pragma once
 #include "common.cuh"
 #include "field_simt.cuh"
+#include "tc_prims.cuh"
+
 namespace scnerf {
+
+// W[rows, cols] fp32 (row stride ld, first source column col0) -> canonical image with rows_pad
+// rows and k_pad columns (zero padded).  lo = bf16(W - float(hi)) for the split-bf16 path.
+__global__ void __launch_bounds__(256) pack_canon_kernel(const float* __restrict__ W, int64_t ld,
+                                                         int rows, int cols, int col0, int rows_pad,
+                                                         int k_pad, uint8_t* __restrict__ hi,
+                                                         uint8_t* __restrict__ lo) {
+  int g = blockIdx.x * blockDim.x + threadIdx.x;
+  int nchunk = k_pad >> 3;
+  if (g >= rows_pad * nchunk) return;
+  int row = g % rows_pad, kc = g / rows_pad;
+  float v[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    int k = kc * 8 + j;
+    v[j] = (row < rows && k < cols) ? W[(int64_t)row * ld + col0 + k] : 0.f;
+  }
+  uint32_t h[4], l[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    __nv_bfloat16 h0 = __float2bfloat16_rn(v[2 * j]), h1 = __float2bfloat16_rn(v[2 * j + 1]);
+    h[j] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+    l[j] = tc::pack_bf16(v[2 * j] - __bfloat162float(h0), v[2 * j + 1] - __bfloat162float(h1));
+  }
+  uint32_t off = tc::canon_off(row, kc * 8, rows_pad);
+  *reinterpret_cast<uint4*>(hi + off) = make_uint4(h[0], h[1], h[2], h[3]);
+  if (lo) *reinterpret_cast<uint4*>(lo + off) = make_uint4(l[0], l[1], l[2], l[3]);
+}
+
+// D[128,N] = A[128,K] * B[N,K]^T from canonical bf16 images in global memory.
+// variant bit0: swap the LBO/SBO descriptor fields (diagnostic); bit1: stage with cp.async.bulk.
+__global__ void __launch_bounds__(128) tc_selftest_kernel(const uint8_t* __restrict__ A_img,
+                                                          const uint8_t* __restrict__ B_img,
+                                                          float* __restrict__ D, int N, int K,
+                                                          int variant) {
+  extern __shared__ __align__(1024) uint8_t tc_smem[];
+  __shared__ __align__(8) uint64_t bar_mma, bar_tma;
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t a_bytes = 128u * K * 2u, b_bytes = (uint32_t)N * K * 2u;
+  uint8_t* sA = tc_smem;
+  uint8_t* sB = tc_smem + a_bytes;
+  uint32_t ncols = 32;
+  while (ncols < (uint32_t)N) ncols <<= 1;
+  if (tid == 0) {
+    tc::mbar_init(&bar_mma, 1);
+    tc::mbar_init(&bar_tma, 1);
+    tc::fence_mbar_init();
+  }
+  __syncthreads();
+  if (warp == 0) tc::tmem_alloc(&tmem_base_s, ncols);
+  if (variant & 2) {
+    if (tid == 0) {
+      tc::mbar_arrive_expect_tx(&bar_tma, a_bytes + b_bytes);
+      for (uint32_t o = 0; o < a_bytes; o += 16384) tc::bulk_g2s(sA + o, A_img + o, min(16384u, a_bytes - o), &bar_tma);
+      for (uint32_t o = 0; o < b_bytes; o += 16384) tc::bulk_g2s(sB + o, B_img + o, min(16384u, b_bytes - o), &bar_tma);
+    }
+    tc::mbar_wait(&bar_tma, 0);
+  } else {
+    for (uint32_t o = tid * 16; o < a_bytes; o += 128 * 16)
+      *reinterpret_cast<uint4*>(sA + o) = *reinterpret_cast<const uint4*>(A_img + o);
+    for (uint32_t o = tid * 16; o < b_bytes; o += 128 * 16)
+      *reinterpret_cast<uint4*>(sB + o) = *reinterpret_cast<const uint4*>(B_img + o);
+    tc::fence_proxy_async();
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem = tmem_base_s;
+  if (tid == 0) {
+    uint32_t lboA = 128 * 16, lboB = (uint32_t)N * 16, sboA = 128, sboB = 128;
+    const uint32_t stepA = 2 * lboA, stepB = 2 * lboB;   // one K=16 step = two 8-element chunks
+    if (variant & 1) { uint32_t t = lboA; lboA = sboA; sboA = t; t = lboB; lboB = sboB; sboB = t; }
+    const uint32_t idesc = tc::idesc_bf16_f32(128, (uint32_t)N);
+    for (int k = 0; k < K / 16; ++k) {
+      uint64_t ad = tc::smem_desc(tc::smem_u32(sA) + k * stepA, lboA, sboA);
+      uint64_t bd = tc::smem_desc(tc::smem_u32(sB) + k * stepB, lboB, sboB);
+      tc::mma_ss(tmem, ad, bd, idesc, k > 0);
+    }
+    tc::tc_commit(&bar_mma);
+  }
+  tc::mbar_wait(&bar_mma, 0);
+  tc::tc_fence_after();
+  for (int c0 = 0; c0 < N; c0 += 32) {
+    uint32_t v[32];
+    tc::tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + c0, v);
+    tc::tmem_ld_wait();
+    float* drow = D + (int64_t)(warp * 32 + lane) * N + c0;
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+      if (c0 + j < N) drow[j] = __uint_as_float(v[j]);
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tc::tmem_dealloc(tmem, ncols);
+}
+
+// host side of the self-test: A[128,K], B[N,K] fp32 row-major -> D[128,N] fp32
+inline int tc_selftest(const float* A, const float* B, float* D, int N, int K, int variant,
+                       void* workspace, size_t workspace_bytes, void* stream) {
+  SCNERF_CHECK_ARG(N % 16 == 0 && N >= 16 && N <= 256 && K % 16 == 0 && K >= 16, "selftest: bad N/K");
+  size_t a_bytes = (size_t)128 * K * 2, b_bytes = (size_t)N * K * 2;
+  SCNERF_CHECK_ARG(a_bytes + b_bytes <= 220 * 1024, "selftest: tile does not fit shared memory");
+  Arena ar(workspace, workspace_bytes);
+  uint8_t* Ai = ar.get<uint8_t>(a_bytes);
+  uint8_t* Bi = ar.get<uint8_t>(b_bytes);
+  if (!workspace || !ar.ok()) return fail(SCNERF_ERR_WORKSPACE, "selftest: workspace too small");
+  SCNERF_LAUNCH(pack_canon_kernel, (unsigned)cdiv(128 * (K / 8), 256), 256, 0, stream, A, (int64_t)K, 128, K,
+                0, 128, K, Ai, (uint8_t*)nullptr);
+  SCNERF_LAUNCH(pack_canon_kernel, (unsigned)cdiv(N * (K / 8), 256), 256, 0, stream, B, (int64_t)K, N, K, 0, N,
+                K, Bi, (uint8_t*)nullptr);
+  static bool attr_set = false;
+  if (!attr_set) {
+    SCNERF_CUDA(cudaFuncSetAttribute(tc_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_set = true;
+  }
+  SCNERF_LAUNCH(tc_selftest_kernel, 1, 128, a_bytes + b_bytes, stream, Ai, Bi, D, N, K, variant);
+  return 0;
+}
+
 inline int field_tc_fwd(const scnerf_mlp&, int, const float*, int, const float*, const float*,
                         const float*, int64_t, int, const FieldBufs&, float*, void*) {
   return fail(SCNERF_ERR_UNSUPPORTED, "tensor-core field path not built into this library yet");
 }
+
 }  // namespace scnerf

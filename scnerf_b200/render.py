@@ -99,7 +99,7 @@ class _RenderRays(torch.autograd.Function):
         dev = rays.device
         nc = len(net_c.field_tensors())
         p_c, p_f = params[:nc], params[nc:]
-        training = torch.is_grad_enabled() and any(ctx.needs_input_grad)
+        training = any(ctx.needs_input_grad)   # (grad mode is always off inside forward)
         cfg = _lib.RenderCfg()
         cfg.N_samples, cfg.N_importance, cfg.ray_cols = opt["N_samples"], opt["N_importance"], cols
         cfg.lindisp, cfg.white_bkgd = int(opt["lindisp"]), int(opt["white_bkgd"])

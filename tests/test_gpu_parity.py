@@ -163,10 +163,11 @@ def test_raw2outputs_golden(lib, golden):
 
 def _check_inds(inds, ref_inds, cdf, u, what):
     bad = np.argwhere(inds != ref_inds)
-    for r, c in bad:   # only exact-tie flips are tolerated: u within 1 ulp of the knot in dispute
+    for r, c in bad:   # only tie flips are tolerated: u within the round-off of the disputed CDF
+        # knot (a 62-term fp32 running sum: a few ulp; the sampled value is continuous across it)
         k = min(inds[r, c], ref_inds[r, c])
         assert abs(int(inds[r, c]) - int(ref_inds[r, c])) == 1, what
-        assert abs(u[r, c] - cdf[r, k]) <= 2 * np.spacing(np.float32(cdf[r, k])), (what, r, c)
+        assert abs(u[r, c] - cdf[r, k]) <= 8 * np.spacing(np.float32(cdf[r, k])), (what, r, c)
     return len(bad)
 
 
@@ -321,3 +322,22 @@ def test_render_no_grad_full_image_chunks(lib):
         b = batchify_rays(rays, 3000, **kw)
     for k in a:
         assert torch.equal(a[k], b[k]), k
+
+
+@pytest.mark.parametrize("N,K", [(256, 256), (128, 64), (16, 16), (256, 288)])
+def test_tcgen05_selftest(lib, N, K):
+    """Single-tile tcgen05 GEMM (bf16 in, fp32 accumulate) vs torch on bf16-rounded inputs:
+    pins the smem/instruction descriptor encodings, TMEM alloc/ld and the bulk-copy staging."""
+    from scnerf_b200 import _lib
+    g = torch.Generator(device="cpu").manual_seed(N * 1000 + K)
+    A = torch.randn(128, K, generator=g).to(DEV)
+    B = torch.randn(N, K, generator=g).to(DEV)
+    ref = (A.bfloat16().float() @ B.bfloat16().float().T)
+    ws = torch.empty(1 << 20, dtype=torch.uint8, device=DEV)
+    for variant in (0, 2):
+        D = torch.full((128, N), float("nan"), device=DEV)
+        _lib.check(lib.scnerf_tc_selftest(_lib.ptr(A), _lib.ptr(B), _lib.ptr(D), N, K, variant, _lib.ptr(ws),
+                                          ws.numel(), _lib.stream()), "tc_selftest")
+        torch.cuda.synchronize()
+        err = (D - ref).abs().max().item() / ref.abs().max().item()
+        assert err < 1e-5, f"variant {variant}: rel err {err:.3e}"
