@@ -32,9 +32,10 @@ inline std::atomic<int64_t>& launch_counter() {
 // Every kernel launch in the library goes through this macro: counts it and checks the launch.
 #define SCNERF_LAUNCH(kernel, grid, block, smem, stream, ...)                                   \
   do {                                                                                          \
+    (void)cudaGetLastError(); /* drop stale non-sticky errors left by other libraries */        \
     kernel<<<(grid), (block), (smem), (cudaStream_t)(stream)>>>(__VA_ARGS__);                   \
     scnerf::launch_counter().fetch_add(1, std::memory_order_relaxed);                           \
-    cudaError_t e__ = cudaPeekAtLastError();                                                    \
+    cudaError_t e__ = cudaGetLastError();                                                       \
     if (e__ != cudaSuccess)                                                                     \
       return scnerf::fail(SCNERF_ERR_CUDA, "%s launch failed: %s", #kernel,                     \
                           cudaGetErrorString(e__));                                             \

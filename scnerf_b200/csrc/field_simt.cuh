@@ -220,7 +220,12 @@ struct FieldBufs {
   float* F = nullptr;                  // [P, W + icv] = [feature | PE(dir)]
   float* HV = nullptr;                 // [P, W/2]
   int64_t ldx5 = 0, ldf = 0;
+  bool keep_all = false;               // training layout (every H[i] distinct)
+  uint8_t* tc_img = nullptr;           // packed bf16 weight image for the tcgen05 path
+  float* tc_cbuf = nullptr;            // packed biases / head weights
 };
+constexpr size_t TC_IMG_BYTES = 2400 * 1024;   // >= fused::weight_image_bytes<3>() (checked there)
+constexpr size_t TC_CBUF_FLOATS = 4096;
 struct FieldGradBufs {
   float *Ga = nullptr, *Gb = nullptr;  // [P, W] ping-pong
   float* Gx5 = nullptr;                // [P, ldx5]
@@ -231,6 +236,9 @@ struct FieldGradBufs {
 inline void field_bufs_alloc(Arena& ar, const scnerf_mlp& m, int64_t P, bool keep_all, FieldBufs& B) {
   B.ldx5 = m.input_ch + m.W;
   B.ldf = m.W + m.input_ch_views;
+  B.keep_all = keep_all;
+  B.tc_img = ar.get<uint8_t>(TC_IMG_BYTES);
+  B.tc_cbuf = ar.get<float>(TC_CBUF_FLOATS);
   B.X5 = ar.get<float>(P * B.ldx5);
   if (keep_all) {
     for (int i = 0; i < m.D; ++i)

@@ -8,6 +8,7 @@
 #include "common.cuh"
 #include "field_simt.cuh"
 #include "tc_prims.cuh"
+#include "field_tc_fused.cuh"
 
 namespace scnerf {
 
@@ -40,7 +41,8 @@ __global__ void __launch_bounds__(256) pack_canon_kernel(const float* __restrict
 }
 
 // D[128,N] = A[128,K] * B[N,K]^T from canonical bf16 images in global memory.
-// variant bit0: swap the LBO/SBO descriptor fields (diagnostic); bit1: stage with cp.async.bulk.
+// variant bit0: swap the LBO/SBO descriptor fields (diagnostic); bit1: stage with cp.async.bulk;
+// bit2: A operand from TMEM (TS-mode MMA), written there with tcgen05.st from registers.
 __global__ void __launch_bounds__(128) tc_selftest_kernel(const uint8_t* __restrict__ A_img,
                                                           const uint8_t* __restrict__ B_img,
                                                           float* __restrict__ D, int N, int K,
@@ -54,6 +56,7 @@ __global__ void __launch_bounds__(128) tc_selftest_kernel(const uint8_t* __restr
   uint8_t* sB = tc_smem + a_bytes;
   uint32_t ncols = 32;
   while (ncols < (uint32_t)N) ncols <<= 1;
+  if (variant & 4) ncols = 512;   // D in [0,256), A in [256, 256+K/2)
   if (tid == 0) {
     tc::mbar_init(&bar_mma, 1);
     tc::mbar_init(&bar_tma, 1);
@@ -79,6 +82,25 @@ __global__ void __launch_bounds__(128) tc_selftest_kernel(const uint8_t* __restr
   __syncthreads();
   tc::tc_fence_after();
   const uint32_t tmem = tmem_base_s;
+  if (variant & 4) {
+    // row (= TMEM lane) r of A as packed bf16 pairs -> TMEM columns [256, 256+K/2)
+    const int r = warp * 32 + lane;
+    for (int c0 = 0; c0 < K / 2; c0 += 16) {
+      uint32_t v[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        int k = 2 * (c0 + j);
+        uint32_t lo16 = *reinterpret_cast<const uint16_t*>(sA + tc::canon_off(r, k, 128));
+        uint32_t hi16 = *reinterpret_cast<const uint16_t*>(sA + tc::canon_off(r, k + 1, 128));
+        v[j] = lo16 | (hi16 << 16);
+      }
+      tc::tmem_st16(tmem + ((uint32_t)(warp * 32) << 16) + 256 + c0, v);
+    }
+    tc::tmem_st_wait();
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+  }
   if (tid == 0) {
     uint32_t lboA = 128 * 16, lboB = (uint32_t)N * 16, sboA = 128, sboB = 128;
     const uint32_t stepA = 2 * lboA, stepB = 2 * lboB;   // one K=16 step = two 8-element chunks
@@ -87,7 +109,8 @@ __global__ void __launch_bounds__(128) tc_selftest_kernel(const uint8_t* __restr
     for (int k = 0; k < K / 16; ++k) {
       uint64_t ad = tc::smem_desc(tc::smem_u32(sA) + k * stepA, lboA, sboA);
       uint64_t bd = tc::smem_desc(tc::smem_u32(sB) + k * stepB, lboB, sboB);
-      tc::mma_ss(tmem, ad, bd, idesc, k > 0);
+      if (variant & 4) tc::mma_ts(tmem, tmem + 256 + k * 8, bd, idesc, k > 0);
+      else tc::mma_ss(tmem, ad, bd, idesc, k > 0);
     }
     tc::tc_commit(&bar_mma);
   }
@@ -113,6 +136,7 @@ inline int tc_selftest(const float* A, const float* B, float* D, int N, int K, i
   SCNERF_CHECK_ARG(N % 16 == 0 && N >= 16 && N <= 256 && K % 16 == 0 && K >= 16, "selftest: bad N/K");
   size_t a_bytes = (size_t)128 * K * 2, b_bytes = (size_t)N * K * 2;
   SCNERF_CHECK_ARG(a_bytes + b_bytes <= 220 * 1024, "selftest: tile does not fit shared memory");
+  SCNERF_CHECK_ARG(!(variant & 4) || (K <= 512 && K % 32 == 0), "selftest: TS variant needs K%%32==0, K<=512");
   Arena ar(workspace, workspace_bytes);
   uint8_t* Ai = ar.get<uint8_t>(a_bytes);
   uint8_t* Bi = ar.get<uint8_t>(b_bytes);
@@ -130,9 +154,66 @@ inline int tc_selftest(const float* A, const float* B, float* D, int N, int K, i
   return 0;
 }
 
-inline int field_tc_fwd(const scnerf_mlp&, int, const float*, int, const float*, const float*,
-                        const float*, int64_t, int, const FieldBufs&, float*, void*) {
-  return fail(SCNERF_ERR_UNSUPPORTED, "tensor-core field path not built into this library yet");
+inline int device_sm_count() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+  }
+  return n;
+}
+
+template <int NSPLIT>
+inline int field_tc_fwd_impl(const scnerf_mlp& m, const float* rays, int ray_cols, const float* z,
+                             const float* pts, const float* viewdirs, int64_t N, int S,
+                             const FieldBufs& B, float* raw, void* stream) {
+  using namespace fused;
+  static_assert(weight_image_bytes<3>() <= TC_IMG_BYTES, "TC_IMG_BYTES too small");
+  static_assert(C_TOTAL <= (int)TC_CBUF_FLOATS, "TC_CBUF_FLOATS too small");
+  PackSrc src{};
+  for (int i = 0; i < 8; ++i) { src.w[i] = m.pts_w[i]; src.b[i] = m.pts_b[i]; src.ld[i] = (i == 0) ? 63 : (i == 5 ? 319 : 256); }
+  src.w[8] = m.feature_w; src.b[8] = m.feature_b; src.ld[8] = 256;
+  src.w[9] = m.views_w; src.b[9] = m.views_b; src.ld[9] = 283;
+  src.alpha_w = m.alpha_w; src.alpha_b = m.alpha_b; src.rgb_w = m.rgb_w; src.rgb_b = m.rgb_b;
+  SCNERF_LAUNCH((pack_weights_kernel<NSPLIT>), (unsigned)cdiv(pack_total_threads(), 256), 256, 0, stream, src,
+                B.tc_img, B.tc_cbuf);
+  Args a{};
+  a.rays = rays; a.ray_cols = ray_cols; a.z = z; a.pts = pts; a.viewdirs = viewdirs;
+  a.P = N * S; a.S = S; a.wimg = B.tc_img; a.cbuf = B.tc_cbuf; a.raw = raw;
+  a.num_tiles = (int)cdiv(a.P, TILE_M);
+  if (B.keep_all) {   // training: leave the fp32 layer inputs where the backward expects them
+    for (int s = 0; s < 8; ++s) {
+      a.dump[s] = (s == 4) ? B.X5 + 63 : B.H[s];
+      a.dump_ld[s] = (s == 4) ? (int)B.ldx5 : 256;
+    }
+    a.dump[8] = B.F; a.dump_ld[8] = (int)B.ldf;
+    a.dump[9] = B.HV; a.dump_ld[9] = 128;
+    a.dump_pe = B.X5; a.dump_pe_ld = (int)B.ldx5;
+    a.dump_ped = B.F + 256; a.dump_ped_ld = (int)B.ldf;
+  }
+  static bool attr_set = false;
+  if (!attr_set) {
+    SCNERF_CUDA(cudaFuncSetAttribute(field_fused_fwd_kernel<NSPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     Cfg<NSPLIT>::SMEM_BYTES));
+    attr_set = true;
+  }
+  int grid = std::min(device_sm_count(), a.num_tiles);
+  SCNERF_LAUNCH((field_fused_fwd_kernel<NSPLIT>), grid, 192, Cfg<NSPLIT>::SMEM_BYTES, stream, a);
+  return 0;
+}
+
+inline int field_tc_fwd(const scnerf_mlp& m, int precision, const float* rays, int ray_cols,
+                        const float* z, const float* pts, const float* viewdirs, int64_t N, int S,
+                        const FieldBufs& B, float* raw, void* stream) {
+  if (!(m.D == 8 && m.W == 256 && m.skip == 4 && m.use_viewdirs && m.L_pos == 10 && m.L_dir == 4))
+    return fail(SCNERF_ERR_UNSUPPORTED,
+                "tensor-core field path is specialised for the 8x256, skip-4, use_viewdirs network "
+                "(multires 10/4); use precision fp32 for other shapes");
+  if (rays && ray_cols != 11) return fail(SCNERF_ERR_ARG, "tensor-core field path needs 11-column rays");
+  if (precision == SCNERF_PRECISION_BF16X3)
+    return field_tc_fwd_impl<3>(m, rays, ray_cols, z, pts, viewdirs, N, S, B, raw, stream);
+  return field_tc_fwd_impl<1>(m, rays, ray_cols, z, pts, viewdirs, N, S, B, raw, stream);
 }
 
 }  // namespace scnerf

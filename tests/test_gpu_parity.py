@@ -334,10 +334,51 @@ def test_tcgen05_selftest(lib, N, K):
     B = torch.randn(N, K, generator=g).to(DEV)
     ref = (A.bfloat16().float() @ B.bfloat16().float().T)
     ws = torch.empty(1 << 20, dtype=torch.uint8, device=DEV)
-    for variant in (0, 2):
+    for variant in (0, 2) + ((4, 6) if K % 32 == 0 else ()):
         D = torch.full((128, N), float("nan"), device=DEV)
         _lib.check(lib.scnerf_tc_selftest(_lib.ptr(A), _lib.ptr(B), _lib.ptr(D), N, K, variant, _lib.ptr(ws),
                                           ws.numel(), _lib.stream()), "tc_selftest")
         torch.cuda.synchronize()
         err = (D - ref).abs().max().item() / ref.abs().max().item()
         assert err < 1e-5, f"variant {variant}: rel err {err:.3e}"
+
+
+def _field_inputs(N, S, seed):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    pts = (torch.rand(N, S, 3, generator=g) * 3 - 1.5).to(DEV)
+    dirs = torch.nn.functional.normalize(torch.randn(N, 3, generator=g), dim=-1).to(DEV)
+    return pts, dirs
+
+
+@pytest.mark.parametrize("precision,tol", [("bf16x3", 3e-5), ("bf16", 3e-2)])
+def test_field_tc_forward_vs_fp32(lib, golden, precision, tol):
+    """Fused tcgen05 field forward vs the fp32 CUDA-core path (and the reference golden):
+    P = 300*77 samples is not a multiple of the 128-row tile (ragged tail), then 1 sample."""
+    from scnerf_b200.create_nerf import run_network
+    net = build_modules(3, DEV)["coarse"]
+    for N, S in ((300, 77), (1, 1), (2, 128)):
+        pts, dirs = _field_inputs(N, S, 100 + N)
+        ref = run_network(pts, dirs, net, None, None, precision="fp32")
+        got = run_network(pts, dirs, net, None, None, precision=precision)
+        torch.cuda.synchronize()
+        assert torch.isfinite(got).all()
+        e = rel(got.cpu().numpy(), ref.cpu().numpy())
+        print(f"field {precision} N={N} S={S}: rel-to-max err {e:.3e}")
+        assert e <= tol, f"{precision} N={N},S={S}: {e:.3e}"
+    g = golden("field")
+    raw = run_network(T(g["pts"]).to(DEV)[:, None, :], T(g["dirs"]).to(DEV), net, None, None, precision=precision)
+    close(raw[:, 0, :], g["raw"], tol, "golden raw")
+
+
+def test_render_c2mini_golden_bf16x3(lib, golden):
+    """configs[1] shape through the tensor-core (split-bf16) forward: still within 1e-4."""
+    from scnerf_b200.get_rays import get_rays_kps_use_camera
+    g = golden("render_c2mini")
+    mods = build_modules(6, DEV)
+    kps, idx, _ = synth.pixel_batch(6, 64)
+    with torch.no_grad():
+        o, d = get_rays_kps_use_camera(H, W, mods["cam"], T(kps).to(DEV), idx_in_camera_param=T(idx).to(DEV))
+    for perturb, std, wb, tag in ((0., 0., False, "det"), (1., 1., False, "rand")):
+        rgb, disp, acc, ex = _render_golden(mods, o, d, mods["cam"], None, 64, 128, perturb, std, wb, "bf16x3")
+        close(rgb, g[f"{tag}_rgb"], 1e-4, f"{tag} rgb"); close(acc, g[f"{tag}_acc"], 1e-4, f"{tag} acc")
+        close(ex["rgb0"], g[f"{tag}_rgb0"], 1e-4, f"{tag} rgb0")
