@@ -324,10 +324,29 @@ def pdf_to_cdf(weights):
     return torch.cat([torch.zeros_like(cdf[:, :1]), cdf], -1)
 
 
-def inverse_cdf_sample(bins, weights, u, return_inds=False):
+def pdf_to_cdf_sequential(weights):
+    """Same as pdf_to_cdf but with a strictly sequential fp32 sum and running sum in index order
+    (numpy, one add at a time).  torch.sum's vectorised order is build/ISA dependent (its CDF
+    differs from this one by up to ~2e-6 on 62 bins, and the reference's CUDA run differs again),
+    so this is the order the CUDA kernel fixes; tests use it to bit-match the kernel's logic."""
+    import numpy as np
+    w = (np.asarray(weights, dtype=np.float32) + np.float32(1e-5)).astype(np.float32)
+    tot = np.zeros(w.shape[0], np.float32)
+    for i in range(w.shape[1]):
+        tot = (tot + w[:, i]).astype(np.float32)
+    run = np.zeros(w.shape[0], np.float32)
+    cols = [run.copy()]
+    for i in range(w.shape[1]):
+        run = (run + (w[:, i] / tot).astype(np.float32)).astype(np.float32)
+        cols.append(run.copy())
+    return torch.from_numpy(np.stack(cols, 1))
+
+
+def inverse_cdf_sample(bins, weights, u, return_inds=False, cdf=None):
     """sample_pdf, NeRF/render.py:417-460, with the uniforms ``u`` [N,Nf] supplied
-    (linspace(0,1,Nf) when det, rand otherwise)."""
-    cdf = pdf_to_cdf(weights)
+    (linspace(0,1,Nf) when det, rand otherwise).  ``cdf`` overrides the CDF (summation-order
+    studies)."""
+    cdf = pdf_to_cdf(weights) if cdf is None else cdf
     u = u.contiguous()
     inds = torch.searchsorted(cdf, u, right=True)
     below = (inds - 1).clamp(min=0)

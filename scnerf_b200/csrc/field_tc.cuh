@@ -147,7 +147,7 @@ inline int tc_selftest(const float* A, const float* B, float* D, int N, int K, i
                 K, Bi, (uint8_t*)nullptr);
   static bool attr_set = false;
   if (!attr_set) {
-    SCNERF_CUDA(cudaFuncSetAttribute(tc_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    SCNERF_CUDA(cudaFuncSetAttribute(tc_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
     attr_set = true;
   }
   SCNERF_LAUNCH(tc_selftest_kernel, 1, 128, a_bytes + b_bytes, stream, Ai, Bi, D, N, K, variant);
