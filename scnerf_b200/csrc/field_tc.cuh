@@ -164,25 +164,59 @@ inline int device_sm_count() {
   return n;
 }
 
+// one-time (per device) upload of the slab plans into __constant__ / __device__ symbols
+inline int fwd_plan_init() {
+  static bool done[64] = {};
+  int dev = 0;
+  SCNERF_CUDA(cudaGetDevice(&dev));
+  if (dev < 64 && done[dev]) return 0;
+  static eng::Plan P;
+  static fused::PlanSrc S;
+  fused::build_fwd_plan(P, S);
+  if (fused::plan_image_bytes(P, 3) > TC_IMG_BYTES) return fail(SCNERF_ERR_WORKSPACE, "TC_IMG_BYTES too small");
+  SCNERF_CUDA(cudaMemcpyToSymbol(fused::c_plan_fwd, &P, sizeof(P)));
+  SCNERF_CUDA(cudaMemcpyToSymbol(fused::d_plansrc_fwd, &S, sizeof(S)));
+  SCNERF_CUDA(cudaFuncSetAttribute(fused::field_fused_fwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   fused::Cfg<1>::SMEM_BYTES));
+  SCNERF_CUDA(cudaFuncSetAttribute(fused::field_fused_fwd_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   fused::Cfg<3>::SMEM_BYTES));
+  if (dev < 64) done[dev] = true;
+  return 0;
+}
+inline const eng::Plan& fwd_plan_host() {
+  static eng::Plan P;
+  static fused::PlanSrc S;
+  static bool built = false;
+  if (!built) { fused::build_fwd_plan(P, S); built = true; }
+  return P;
+}
+
+inline fused::PackSrc make_pack_src(const scnerf_mlp& m) {
+  fused::PackSrc src{};
+  for (int i = 0; i < 8; ++i) { src.w[i] = m.pts_w[i]; src.b[i] = m.pts_b[i]; src.ld[i] = (i == 0) ? 63 : (i == 5 ? 319 : 256); }
+  src.w[8] = m.feature_w; src.b[8] = m.feature_b; src.ld[8] = 256;
+  src.w[9] = m.views_w; src.b[9] = m.views_b; src.ld[9] = 283;
+  src.alpha_w = m.alpha_w; src.alpha_b = m.alpha_b; src.rgb_w = m.rgb_w; src.rgb_b = m.rgb_b;
+  return src;
+}
+
 template <int NSPLIT>
 inline int field_tc_fwd_impl(const scnerf_mlp& m, const float* rays, int ray_cols, const float* z,
                              const float* pts, const float* viewdirs, int64_t N, int S,
                              const FieldBufs& B, float* raw, void* stream) {
   using namespace fused;
-  static_assert(weight_image_bytes<3>() <= TC_IMG_BYTES, "TC_IMG_BYTES too small");
   static_assert(C_TOTAL <= (int)TC_CBUF_FLOATS, "TC_CBUF_FLOATS too small");
-  PackSrc src{};
-  for (int i = 0; i < 8; ++i) { src.w[i] = m.pts_w[i]; src.b[i] = m.pts_b[i]; src.ld[i] = (i == 0) ? 63 : (i == 5 ? 319 : 256); }
-  src.w[8] = m.feature_w; src.b[8] = m.feature_b; src.ld[8] = 256;
-  src.w[9] = m.views_w; src.b[9] = m.views_b; src.ld[9] = 283;
-  src.alpha_w = m.alpha_w; src.alpha_b = m.alpha_b; src.rgb_w = m.rgb_w; src.rgb_b = m.rgb_b;
-  SCNERF_LAUNCH((pack_weights_kernel<NSPLIT>), (unsigned)cdiv(pack_total_threads(), 256), 256, 0, stream, src,
-                B.tc_img, B.tc_cbuf);
+  int rc = fwd_plan_init();
+  if (rc) return rc;
+  const eng::Plan& P = fwd_plan_host();
+  PackSrc src = make_pack_src(m);
+  SCNERF_LAUNCH((pack_fwd_kernel<NSPLIT>), dim3(2, (unsigned)P.n_slabs), 256, 0, stream, src, B.tc_img);
+  SCNERF_LAUNCH(pack_consts_kernel, (unsigned)cdiv(C_TOTAL, 256), 256, 0, stream, src, B.tc_cbuf);
   Args a{};
   a.rays = rays; a.ray_cols = ray_cols; a.z = z; a.pts = pts; a.viewdirs = viewdirs;
   a.P = N * S; a.S = S; a.wimg = B.tc_img; a.cbuf = B.tc_cbuf; a.raw = raw;
   a.num_tiles = (int)cdiv(a.P, TILE_M);
-  if (B.keep_all) {   // training: leave the fp32 layer inputs where the backward expects them
+  if (B.keep_all && B.X5) {   // training with the fp32 CUDA-core backward: fp32 row-major layer inputs
     for (int s = 0; s < 8; ++s) {
       a.dump[s] = (s == 4) ? B.X5 + 63 : B.H[s];
       a.dump_ld[s] = (s == 4) ? (int)B.ldx5 : 256;
@@ -192,14 +226,8 @@ inline int field_tc_fwd_impl(const scnerf_mlp& m, const float* rays, int ray_col
     a.dump_pe = B.X5; a.dump_pe_ld = (int)B.ldx5;
     a.dump_ped = B.F + 256; a.dump_ped_ld = (int)B.ldf;
   }
-  static bool attr_set = false;
-  if (!attr_set) {
-    SCNERF_CUDA(cudaFuncSetAttribute(field_fused_fwd_kernel<NSPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     Cfg<NSPLIT>::SMEM_BYTES));
-    attr_set = true;
-  }
   int grid = std::min(device_sm_count(), a.num_tiles);
-  SCNERF_LAUNCH((field_fused_fwd_kernel<NSPLIT>), grid, 192, Cfg<NSPLIT>::SMEM_BYTES, stream, a);
+  SCNERF_LAUNCH((field_fused_fwd_kernel<NSPLIT>), grid, 320, Cfg<NSPLIT>::SMEM_BYTES, stream, a);
   return 0;
 }
 

@@ -3,30 +3,35 @@
 // NO intermediate activation ever leaving the SM:
 //
 //   HBM in : 44 B/ray-sample of geometry (rays, z; L2-resident) ; HBM out: raw[4] = 16 B/sample
-//   weights: bf16 (hi[,lo]) slabs streamed L2 -> smem by 1-D bulk TMA through an mbarrier ring
+//   weights: bf16 (hi[,lo]) K=16 slabs streamed L2 -> smem by 1-D bulk TMA through an mbarrier ring
 //   A operand (activations): TMEM (TS-mode MMA) for the 256-wide hidden state, smem for the
-//                            PE(pts) (K=64) and PE(dir) (K=32) slabs
-//   accumulator: TMEM, 128 lanes x 256 fp32 columns
+//                            PE(pts) (K=64) and PE(dir) (K=32) slabs and the constant ONES slab
+//   accumulator: TMEM, 128 lanes x 256 fp32 columns; biases are folded into the GEMM as one extra
+//                K=16 slab (A = ONES, B = [bias | 0]) so the epilogue has no bias traffic
 //
-// Warp roles (192 threads):  warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM alloc),
-// warps 2..5 = epilogue (TMEM lane quadrant = warp & 3): bias, ReLU, bf16 (hi/lo) split, tcgen05.st
-// back into TMEM as the next layer's A operand; alpha / rgb heads are fp32 dot products in the
-// epilogue registers.
+// Warp roles (320 threads):  warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM alloc),
+// warps 2..9 = epilogue, two per TMEM lane quadrant (warp & 3), each owning half of the output
+// columns: ReLU + bf16 (hi/lo) split with cvt.rn.relu.bf16x2, tcgen05.st back into TMEM as the next
+// layer's A operand; alpha / rgb heads are fp32 dot products in the epilogue registers.
 //
 // NSPLIT = 1: single-pass bf16 (fp32 accumulate).   NSPLIT = 3: split-bf16, A_hi*B_hi + A_lo*B_hi +
 // A_hi*B_lo — ~16 mantissa bits per operand, which is what the 1e-4 parity gate needs.
 //
-// Algorithmic work: 593,408 MAC/sample; tensor pipe executes 593,920 MAC/sample
-// (K padded 63->64, 27->32) x NSPLIT.   Reference: NeRF/run_nerf_helpers.py:24-72,105-128 and
+// Training mode additionally writes every layer input as bf16 (hi[,lo]) TILE IMAGES in the operand
+// layout of the wgrad kernel (tc_engine.cuh: ImgDump), 16-byte coalesced stores.
+//
+// Algorithmic work: 593,408 MAC/sample; tensor pipe executes
+// (593,920 + 10 bias slabs) MAC/sample x NSPLIT.   Reference: NeRF/run_nerf_helpers.py:24-72,105-128,
 // NeRF/create_nerf.py:18-32.
 #pragma once
 #include "common.cuh"
 #include "tc_prims.cuh"
+#include "tc_engine.cuh"
 
 namespace scnerf {
 namespace fused {
 
-constexpr int TILE_M = 128;
+using eng::TILE_M;
 constexpr int NSTAGE = 10;
 // per stage: output width N, k16 slabs taken from X (PE pts, smem), H (hidden, TMEM), V (PE dir, smem)
 struct StageDef { int N, kx, kh, kv, relu; };
@@ -37,48 +42,119 @@ __host__ __device__ constexpr StageDef stage_def(int s) {
        : s == 9 ? StageDef{128, 0, 16, 2, 1}      // views_linears[0]
                 : StageDef{256, 0, 16, 0, 1};
 }
-__host__ __device__ constexpr int stage_k16(int s) {
-  return stage_def(s).kx + stage_def(s).kh + stage_def(s).kv;
-}
-__host__ __device__ constexpr int slab_bytes(int s) { return stage_def(s).N * 32; }  // one k16 slab, one half
 
-// A ring slot carries 16 KB (N=256) / 8 KB (N=128): NSPLIT==1 -> two consecutive k16 slabs (K=32),
-// NSPLIT==3 -> the hi and lo slab of one k16.
-template <int NSPLIT> __host__ __device__ constexpr int slots_in_stage(int s) {
-  return NSPLIT == 1 ? stage_k16(s) / 2 : stage_k16(s);
-}
-template <int NSPLIT> __host__ __device__ constexpr int slots_per_tile() {
+// smem A area (byte offsets from its base)
+constexpr int A_XHI = 0, A_XLO = 16384, A_VHI = 32768, A_VLO = 40960, A_ONES = 49152, A_BYTES = 53248;
+
+// source of each slab for the pack kernel (parallel to the plan)
+struct SrcDef {
+  uint8_t wsel;      // index into PackSrc.w / .b
+  uint8_t kind;      // 0: B[n][k] = W[n][col0+k]   1: B[n][k] = W[row0+k][col0+n]   2: B[n][0] = b[n]
+  uint16_t row0, col0, valid_k, valid_n;
+  uint16_t pad;
+  uint32_t img_off;  // byte offset of the slab in the NSPLIT==1 image (x2 for NSPLIT==3)
+};
+struct PlanSrc { SrcDef s[eng::MAX_SLABS]; };
+struct PackSrc {
+  const float* w[12]; int ld[12];
+  const float* b[12];
+  const float *alpha_w, *alpha_b, *rgb_w, *rgb_b;
+};
+
+inline void build_fwd_plan(eng::Plan& P, PlanSrc& S) {
   int n = 0;
-  for (int s = 0; s < NSTAGE; ++s) n += slots_in_stage<NSPLIT>(s);
-  return n;
+  uint32_t off = 0;
+  for (int s = 0; s < NSTAGE; ++s) {
+    const StageDef d = stage_def(s);
+    const int nk = d.kx + d.kh + d.kv;
+    for (int j = 0; j <= nk; ++j, ++n) {
+      eng::SlabDef& e = P.slab[n];
+      SrcDef& q = S.s[n];
+      e = eng::SlabDef{};
+      q = SrcDef{};
+      e.n = (uint16_t)d.N; e.acc_col = 0;
+      e.flags = (j == 0 ? eng::F_ZERO_ACC : 0) | (j == nk ? eng::F_STAGE_END : 0);
+      q.wsel = (uint8_t)s; q.valid_n = (uint16_t)d.N; q.img_off = off;
+      if (j == nk) {                       // bias slab
+        e.a_kind = eng::A_SMEM; e.a_off = A_ONES / 16; e.flags |= eng::F_HI_ONLY_A;
+        q.kind = 2;
+      } else if (j < d.kx) {               // PE(pts) columns
+        e.a_kind = eng::A_SMEM; e.a_off = (uint16_t)((A_XHI + j * 4096) / 16); e.a_lo_delta = (A_XLO - A_XHI) / 16;
+        q.col0 = (uint16_t)(16 * j); q.valid_k = (uint16_t)std::min(16, 63 - 16 * j);
+      } else if (j < d.kx + d.kh) {        // hidden state
+        e.a_kind = eng::A_TMEM; e.a_off = (uint16_t)((j - d.kx) * 8);
+        q.col0 = (uint16_t)((d.kx ? 63 : 0) + 16 * (j - d.kx)); q.valid_k = 16;
+      } else {                             // PE(dir) columns
+        const int jv = j - d.kx - d.kh;
+        e.a_kind = eng::A_SMEM; e.a_off = (uint16_t)((A_VHI + jv * 4096) / 16); e.a_lo_delta = (A_VLO - A_VHI) / 16;
+        q.col0 = (uint16_t)(256 + 16 * jv); q.valid_k = (uint16_t)std::min(16, 27 - 16 * jv);
+      }
+      off += (uint32_t)d.N * 32u;
+    }
+  }
+  P.n_slabs = n; P.n_stages = NSTAGE;
 }
-template <int NSPLIT> __host__ __device__ constexpr size_t weight_image_bytes() {
-  size_t n = 0;
-  for (int s = 0; s < NSTAGE; ++s) n += (size_t)slots_in_stage<NSPLIT>(s) * slab_bytes(s) * 2;
-  return n;
+inline size_t plan_image_bytes(const eng::Plan& P, int nsplit) {
+  size_t b = 0;
+  for (int i = 0; i < P.n_slabs; ++i) b += (size_t)P.slab[i].n * 32u * (nsplit == 3 ? 2 : 1);
+  return b;
+}
+
+// one thread per 16-byte chunk of a slab: blockIdx.y = slab, thread -> (row n, k-chunk)
+template <int NSPLIT>
+__device__ __forceinline__ void pack_slab_impl(const eng::SlabDef& d, const SrcDef& q, const PackSrc& src,
+                                               uint8_t* __restrict__ img) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= d.n * 2) return;
+  const int chunk = t / d.n, row = t % d.n;
+  float v[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const int k = chunk * 8 + e;
+    float x = 0.f;
+    if (q.kind == 0) { if (k < q.valid_k && row < q.valid_n) x = src.w[q.wsel][(int64_t)row * src.ld[q.wsel] + q.col0 + k]; }
+    else if (q.kind == 1) { if (k < q.valid_k && row < q.valid_n) x = src.w[q.wsel][(int64_t)(q.row0 + k) * src.ld[q.wsel] + q.col0 + row]; }
+    else { if (k == 0 && row < q.valid_n) x = src.b[q.wsel][row]; }
+    v[e] = x;
+  }
+  uint32_t h[4], l[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    h[e] = eng::cvt_bf16x2(v[2 * e], v[2 * e + 1]);
+    l[e] = eng::cvt_bf16x2(v[2 * e] - eng::bf16lo_f(h[e]), v[2 * e + 1] - eng::bf16hi_f(h[e]));
+  }
+  const size_t sb = (size_t)d.n * 32;
+  const size_t in_slab = (size_t)chunk * d.n * 16 + (row >> 3) * 128 + (row & 7) * 16;
+  uint8_t* dst = img + (size_t)q.img_off * (NSPLIT == 3 ? 2 : 1);
+  *reinterpret_cast<uint4*>(dst + in_slab) = make_uint4(h[0], h[1], h[2], h[3]);
+  if (NSPLIT == 3) *reinterpret_cast<uint4*>(dst + sb + in_slab) = make_uint4(l[0], l[1], l[2], l[3]);
 }
 
 // constants block (fp32) kept in shared memory
-constexpr int C_BIAS = 0;                 // 8 x 256 trunk biases
-constexpr int C_BFEAT = 8 * 256;          // 256
-constexpr int C_BVIEW = C_BFEAT + 256;    // 128
-constexpr int C_WALPHA = C_BVIEW + 128;   // 256
-constexpr int C_WRGB = C_WALPHA + 256;    // 3 x 128
-constexpr int C_SCAL = C_WRGB + 384;      // b_alpha, b_rgb[3]
-constexpr int C_TOTAL = C_SCAL + 8;       // 3080 floats
+constexpr int C_WALPHA = 0;               // 256
+constexpr int C_WRGB = 256;               // 3 x 128
+constexpr int C_SCAL = 640;               // b_alpha, b_rgb[3]
+constexpr int C_TOTAL = 648;
+__global__ void pack_consts_kernel(PackSrc src, float* __restrict__ cbuf) {
+  int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= C_TOTAL) return;
+  float v = 0.f;
+  if (g < C_WRGB) v = src.alpha_w[g];
+  else if (g < C_SCAL) v = src.rgb_w[g - C_WRGB];
+  else if (g == C_SCAL) v = src.alpha_b[0];
+  else if (g < C_SCAL + 4) v = src.rgb_b[g - C_SCAL - 1];
+  cbuf[g] = v;
+}
 
 template <int NSPLIT> struct Cfg {
-  static constexpr int NSLOT = NSPLIT == 1 ? 10 : 9;
-  static constexpr int SLOT_BYTES = 16384;
-  static constexpr int X_BYTES = 16384;   // 128 rows x 64 k bf16
-  static constexpr int V_BYTES = 8192;    // 128 rows x 32 k bf16
-  static constexpr int NHALF = NSPLIT == 1 ? 1 : 2;
+  static constexpr int NSLOT = NSPLIT == 1 ? 16 : 9;
+  static constexpr int SLOT_BYTES = NSPLIT == 1 ? 8192 : 16384;
   static constexpr int OFF_RING = 0;
-  static constexpr int OFF_X = NSLOT * SLOT_BYTES;
-  static constexpr int OFF_V = OFF_X + X_BYTES * NHALF;
-  static constexpr int OFF_C = OFF_V + V_BYTES * NHALF;
-  static constexpr int OFF_BAR = OFF_C + ((C_TOTAL * 4 + 127) / 128) * 128;
-  static constexpr int SMEM_BYTES = OFF_BAR + (2 * NSLOT + 2) * 8 + 16 + 1024;  // + alignment slack
+  static constexpr int OFF_A = NSLOT * SLOT_BYTES;
+  static constexpr int OFF_C = OFF_A + A_BYTES;
+  static constexpr int OFF_OUT = OFF_C + ((C_TOTAL * 4 + 127) / 128) * 128;   // [128][4] head partial sums
+  static constexpr int OFF_BAR = OFF_OUT + 128 * 4 * 4;
+  static constexpr int SMEM_BYTES = OFF_BAR + (2 * NSLOT + 2) * 8 + 16;
 };
 
 struct Args {
@@ -87,147 +163,74 @@ struct Args {
   const float* pts;                    // [N, S, 3] explicit points (rays == NULL)
   const float* viewdirs;               // [N, 3]    explicit directions (rays == NULL)
   int64_t P; int S;
-  const uint8_t* wimg;                 // packed weight image (see pack_weights_kernel)
-  const float* cbuf;                   // packed constants, C_TOTAL floats
+  const uint8_t* wimg;                 // packed weight image
+  const float* cbuf;                   // packed head constants, C_TOTAL floats
   float* raw;                          // [P, 4]
   int num_tiles;
-  // training mode: fp32 copies of every layer input for the backward (NULL = inference)
-  float* dump[NSTAGE]; int dump_ld[NSTAGE];   // post-activation output of stage s
-  float* dump_pe; int dump_pe_ld;             // PE(pts)  [P, 63]
-  float* dump_ped; int dump_ped_ld;           // PE(dir)  [P, 27]
+  // training (tensor-core backward): bf16 tile images of every layer input
+  eng::ImgDump img_x, img_v, img_out[NSTAGE];
+  // training (fp32 CUDA-core backward): fp32 row-major copies
+  float* dump[NSTAGE]; int dump_ld[NSTAGE];
+  float* dump_pe; int dump_pe_ld;
+  float* dump_ped; int dump_ped_ld;
 };
 
-// ---- weight packing: fp32 nn.Linear tensors -> slab image in MMA-issue order ----------------------
-struct PackSrc {
-  const float* w[NSTAGE]; int ld[NSTAGE];   // weight of each stage ([N, ld] row-major)
-  const float* b[NSTAGE];
-  const float *alpha_w, *alpha_b, *rgb_w, *rgb_b;
-};
-
+__constant__ eng::Plan c_plan_fwd;
+__device__ PlanSrc d_plansrc_fwd;
 template <int NSPLIT>
-__global__ void __launch_bounds__(256) pack_weights_kernel(PackSrc src, uint8_t* __restrict__ img,
-                                                           float* __restrict__ cbuf) {
-  // one thread per (stage, k16 slab, row, k-chunk of 8)
-  int g = blockIdx.x * blockDim.x + threadIdx.x;
-  size_t base = 0;
-  for (int s = 0; s < NSTAGE; ++s) {
-    const StageDef d = stage_def(s);
-    const int nk16 = d.kx + d.kh + d.kv;
-    const int work = nk16 * d.N * 2;
-    if (g < work) {
-      int j = g / (d.N * 2), rem = g % (d.N * 2), chunk = rem / d.N, row = rem % d.N;
-      // source columns of this k16 slab
-      int col0, valid;
-      if (j < d.kx) { col0 = 16 * j; valid = min(16, 63 - 16 * j); }
-      else if (j < d.kx + d.kh) { col0 = (d.kx ? 63 : 0) + 16 * (j - d.kx); valid = 16; }
-      else { col0 = 256 + 16 * (j - d.kx - d.kh); valid = min(16, 27 - 16 * (j - d.kx - d.kh)); }
-      float v[8];
-#pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        int k = chunk * 8 + e;
-        v[e] = (k < valid) ? src.w[s][(int64_t)row * src.ld[s] + col0 + k] : 0.f;
-      }
-      uint32_t h[4], l[4];
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        __nv_bfloat16 h0 = __float2bfloat16_rn(v[2 * e]), h1 = __float2bfloat16_rn(v[2 * e + 1]);
-        h[e] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-        l[e] = tc::pack_bf16(v[2 * e] - __bfloat162float(h0), v[2 * e + 1] - __bfloat162float(h1));
-      }
-      const size_t sb = (size_t)d.N * 32;             // bytes of one k16 slab (one half)
-      const size_t in_slab = (size_t)chunk * d.N * 16 + (row >> 3) * 128 + (row & 7) * 16;
-      if (NSPLIT == 1) {
-        *reinterpret_cast<uint4*>(img + base + (size_t)j * sb + in_slab) = make_uint4(h[0], h[1], h[2], h[3]);
-      } else {
-        *reinterpret_cast<uint4*>(img + base + (size_t)j * 2 * sb + in_slab) = make_uint4(h[0], h[1], h[2], h[3]);
-        *reinterpret_cast<uint4*>(img + base + (size_t)j * 2 * sb + sb + in_slab) = make_uint4(l[0], l[1], l[2], l[3]);
-      }
-      return;
-    }
-    g -= work;
-    base += (size_t)nk16 * d.N * 32 * (NSPLIT == 1 ? 1 : 2);
-  }
-  // remaining threads: constants
-  if (g < C_TOTAL) {
-    float v = 0.f;
-    if (g < C_BFEAT) v = src.b[g / 256][g % 256];
-    else if (g < C_BVIEW) v = src.b[8][g - C_BFEAT];
-    else if (g < C_WALPHA) v = src.b[9][g - C_BVIEW];
-    else if (g < C_WRGB) v = src.alpha_w[g - C_WALPHA];
-    else if (g < C_SCAL) v = src.rgb_w[g - C_WRGB];
-    else if (g == C_SCAL) v = src.alpha_b[0];
-    else if (g < C_SCAL + 4) v = src.rgb_b[g - C_SCAL - 1];
-    cbuf[g] = v;
-  }
-}
-inline int pack_total_threads() {
-  int n = 0;
-  for (int s = 0; s < NSTAGE; ++s) n += stage_k16(s) * stage_def(s).N * 2;
-  return n + C_TOTAL;
+__global__ void __launch_bounds__(256) pack_fwd_kernel(PackSrc src, uint8_t* __restrict__ img) {
+  const int i = blockIdx.y;
+  if (i < c_plan_fwd.n_slabs) pack_slab_impl<NSPLIT>(c_plan_fwd.slab[i], d_plansrc_fwd.s[i], src, img);
 }
 
-// ---- the fused kernel --------------------------------------------------------------------------------
-__device__ __forceinline__ void pe_store(uint8_t* img_hi, uint8_t* img_lo, int row, int k0,
-                                         const float (&v)[8], bool split) {
+// value of PE column i for a 3-vector (L frequencies): [x, sin(2^0 x), cos(2^0 x), ...]
+template <int L>
+__device__ __forceinline__ float pe_col(const float (&x)[3], int i) {
+  if (i < 3) return x[i];
+  if (i >= 3 + 6 * L) return 0.f;
+  const int f = (i - 3) / 6, r = (i - 3) % 6;
+  const float arg = x[r % 3] * (float)(1 << f);
+  return r < 3 ? sinf(arg) : cosf(arg);
+}
+// write PE columns [8*ch, 8*ch+8) of row `row` into the canonical K-major smem image (+ dumps)
+template <int L, bool SPLIT>
+__device__ __forceinline__ void pe_chunk(const float (&x)[3], bool valid, int ch, uint8_t* hi_img,
+                                         uint8_t* lo_img, int row, const eng::ImgDump& img, int tile,
+                                         float* dump) {
+  float v[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = valid ? pe_col<L>(x, ch * 8 + i) : 0.f;
   uint32_t h[4], l[4];
 #pragma unroll
   for (int e = 0; e < 4; ++e) {
-    __nv_bfloat16 h0 = __float2bfloat16_rn(v[2 * e]), h1 = __float2bfloat16_rn(v[2 * e + 1]);
-    h[e] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-    l[e] = tc::pack_bf16(v[2 * e] - __bfloat162float(h0), v[2 * e + 1] - __bfloat162float(h1));
+    h[e] = eng::cvt_bf16x2(v[2 * e], v[2 * e + 1]);
+    l[e] = eng::cvt_bf16x2(v[2 * e] - eng::bf16lo_f(h[e]), v[2 * e + 1] - eng::bf16hi_f(h[e]));
   }
-  uint32_t off = tc::canon_off(row, k0, TILE_M);
-  *reinterpret_cast<uint4*>(img_hi + off) = make_uint4(h[0], h[1], h[2], h[3]);
-  if (split) *reinterpret_cast<uint4*>(img_lo + off) = make_uint4(l[0], l[1], l[2], l[3]);
-}
-
-// PE of a 3-vector into `ncols_pad` columns (63 -> 64, 27 -> 32), canonical K-major smem image
-template <int L, int NCHUNK>
-__device__ __forceinline__ void pe_write(const float (&x)[3], bool valid, uint8_t* hi, uint8_t* lo,
-                                         int row, bool split, float* dump) {
-  float e[NCHUNK * 8];
-#pragma unroll
-  for (int i = 0; i < NCHUNK * 8; ++i) e[i] = 0.f;
-  if (valid) {
-    e[0] = x[0]; e[1] = x[1]; e[2] = x[2];
-#pragma unroll
-    for (int f = 0; f < L; ++f) {
-      float fr = (float)(1 << f);
-#pragma unroll
-      for (int c = 0; c < 3; ++c) {
-        float s, cs;
-        sincosf(x[c] * fr, &s, &cs);
-        e[3 + 6 * f + c] = s;
-        e[3 + 6 * f + 3 + c] = cs;
-      }
-    }
+  const uint32_t off = tc::canon_off(row, ch * 8, TILE_M);
+  *reinterpret_cast<uint4*>(hi_img + off) = make_uint4(h[0], h[1], h[2], h[3]);
+  if (SPLIT) *reinterpret_cast<uint4*>(lo_img + off) = make_uint4(l[0], l[1], l[2], l[3]);
+  if (img.base) {
+    *reinterpret_cast<uint4*>(img.chunk(tile, row, ch * 8, 0)) = make_uint4(h[0], h[1], h[2], h[3]);
+    if (SPLIT && img.nhalf == 2)
+      *reinterpret_cast<uint4*>(img.chunk(tile, row, ch * 8, 1)) = make_uint4(l[0], l[1], l[2], l[3]);
   }
   if (dump && valid) {
 #pragma unroll
-    for (int i = 0; i < 3 + 6 * L; ++i) dump[i] = e[i];
-  }
-#pragma unroll
-  for (int ch = 0; ch < NCHUNK; ++ch) {
-    float v[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) v[i] = e[ch * 8 + i];
-    pe_store(hi, lo, row, ch * 8, v, split);
+    for (int i = 0; i < 8; ++i)
+      if (ch * 8 + i < 3 + 6 * L) dump[ch * 8 + i] = v[i];
   }
 }
 
 template <int NSPLIT>
-__global__ void __launch_bounds__(192, 1) field_fused_fwd_kernel(Args a) {
+__global__ void __launch_bounds__(320, 1) field_fused_fwd_kernel(Args a) {
   using C = Cfg<NSPLIT>;
   constexpr bool SPLIT = NSPLIT == 3;
-  extern __shared__ uint8_t fused_smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(fused_smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* ring = smem + C::OFF_RING;
-  uint8_t* Xhi = smem + C::OFF_X;
-  uint8_t* Xlo = Xhi + C::X_BYTES;
-  uint8_t* Vhi = smem + C::OFF_V;
-  uint8_t* Vlo = Vhi + C::V_BYTES;
-  float* cst = reinterpret_cast<float*>(smem + C::OFF_C);
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem + C::OFF_BAR);
+  extern __shared__ __align__(128) uint8_t fsm[];
+  uint8_t* ringp = fsm + C::OFF_RING;
+  uint8_t* areg = fsm + C::OFF_A;
+  float* cst = reinterpret_cast<float*>(fsm + C::OFF_C);
+  float* out_s = reinterpret_cast<float*>(fsm + C::OFF_OUT);
+  uint64_t* full = reinterpret_cast<uint64_t*>(fsm + C::OFF_BAR);
   uint64_t* empty = full + C::NSLOT;
   uint64_t* acc_full = empty + C::NSLOT;
   uint64_t* a_ready = acc_full + 1;
@@ -237,10 +240,16 @@ __global__ void __launch_bounds__(192, 1) field_fused_fwd_kernel(Args a) {
   if (tid == 0) {
     for (int i = 0; i < C::NSLOT; ++i) { tc::mbar_init(&full[i], 1); tc::mbar_init(&empty[i], 1); }
     tc::mbar_init(acc_full, 1);
-    tc::mbar_init(a_ready, 128);
+    tc::mbar_init(a_ready, 256);
     tc::fence_mbar_init();
   }
   for (int i = tid; i < C_TOTAL; i += blockDim.x) cst[i] = a.cbuf[i];
+  // constant ONES slab: [128 rows x 16 k], k == 0 -> 1.0 (bf16 0x3F80), else 0
+  for (int i = tid; i < 4096 / 16; i += blockDim.x) {
+    const bool k0chunk = i < 128;          // first k-chunk (k 0..7): 128 rows x 16 B
+    *reinterpret_cast<uint4*>(areg + A_ONES + i * 16) = make_uint4(k0chunk ? 0x00003F80u : 0u, 0u, 0u, 0u);
+  }
+  tc::fence_proxy_async();
   __syncthreads();
   if (warp == 1) tc::tmem_alloc(tmem_slot, 512);
   tc::tc_fence_before();
@@ -248,93 +257,25 @@ __global__ void __launch_bounds__(192, 1) field_fused_fwd_kernel(Args a) {
   tc::tc_fence_after();
   const uint32_t tmem = *tmem_slot;
   const uint32_t T_ACC = tmem, T_AHI = tmem + 256, T_ALO = tmem + 384;
+  eng::Ring ring{ringp, full, empty};
 
   if (warp == 0) {
-    // ===================== TMA producer: stream the weight image, once per tile ====================
-    if (lane == 0) {
-      uint32_t n = 0;
-      for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
-        const uint8_t* src = a.wimg;
-#pragma unroll 1
-        for (int s = 0; s < NSTAGE; ++s) {
-          const uint32_t bytes = (uint32_t)slab_bytes(s) * 2;
-          const int ns = slots_in_stage<NSPLIT>(s);
-#pragma unroll 1
-          for (int i = 0; i < ns; ++i, ++n) {
-            const uint32_t idx = n % C::NSLOT, ph = (n / C::NSLOT) & 1;
-            tc::mbar_wait(&empty[idx], ph ^ 1);
-            tc::mbar_arrive_expect_tx(&full[idx], bytes);
-            tc::bulk_g2s(ring + idx * C::SLOT_BYTES, src, bytes, &full[idx]);
-            src += bytes;
-          }
-        }
-      }
-    }
+    if (lane == 0)
+      eng::producer_loop<NSPLIT, C::NSLOT, C::SLOT_BYTES>(c_plan_fwd, a.wimg, ring, a.num_tiles);
   } else if (warp == 1) {
-    // ===================== MMA issuer (one thread) ==================================================
-    if (lane == 0) {
-      uint32_t n = 0, q = 0;
-      const uint32_t x_addr = tc::smem_u32(Xhi), v_addr = tc::smem_u32(Vhi), ring_addr = tc::smem_u32(ring);
-      for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
-#pragma unroll 1
-        for (int s = 0; s < NSTAGE; ++s, ++q) {
-          const StageDef d = stage_def(s);
-          const uint32_t idesc = tc::idesc_bf16_f32(TILE_M, (uint32_t)d.N);
-          const uint32_t sb = (uint32_t)d.N * 32, lbo_b = (uint32_t)d.N * 16;
-          tc::mbar_wait(a_ready, q & 1);     // this stage's A operand is in place, ACC is free
-          tc::tc_fence_after();
-          const int nk16 = d.kx + d.kh + d.kv;
-          uint32_t acc_flag = 0;
-#pragma unroll 1
-          for (int j = 0; j < nk16; j += (SPLIT ? 1 : 2), ++n) {
-            const uint32_t idx = n % C::NSLOT, ph = (n / C::NSLOT) & 1;
-            tc::mbar_wait(&full[idx], ph);
-            tc::tc_fence_after();
-            const uint32_t slot = ring_addr + idx * C::SLOT_BYTES;
-#pragma unroll
-            for (int u = 0; u < (SPLIT ? 1 : 2); ++u) {
-              const int jj = j + u;
-              const uint64_t b_hi = tc::smem_desc(slot + (SPLIT ? 0u : (uint32_t)u * sb), lbo_b, 128);
-              const uint64_t b_lo = tc::smem_desc(slot + sb, lbo_b, 128);
-              if (jj < d.kx || jj >= d.kx + d.kh) {
-                // A slab from shared memory (PE of points / PE of the view direction)
-                const bool isx = jj < d.kx;
-                const uint32_t abase = (isx ? x_addr : v_addr) + (uint32_t)(isx ? jj : jj - d.kx - d.kh) * 4096u;
-                const uint32_t lo_off = isx ? (uint32_t)C::X_BYTES : (uint32_t)C::V_BYTES;
-                const uint64_t a_hi = tc::smem_desc(abase, 2048, 128);
-                tc::mma_ss(T_ACC, a_hi, b_hi, idesc, acc_flag);
-                acc_flag = 1;
-                if (SPLIT) {
-                  const uint64_t a_lo = tc::smem_desc(abase + lo_off, 2048, 128);
-                  tc::mma_ss(T_ACC, a_lo, b_hi, idesc, 1);
-                  tc::mma_ss(T_ACC, a_hi, b_lo, idesc, 1);
-                }
-              } else {
-                const uint32_t col = (uint32_t)(jj - d.kx) * 8u;
-                tc::mma_ts(T_ACC, T_AHI + col, b_hi, idesc, acc_flag);
-                acc_flag = 1;
-                if (SPLIT) {
-                  tc::mma_ts(T_ACC, T_ALO + col, b_hi, idesc, 1);
-                  tc::mma_ts(T_ACC, T_AHI + col, b_lo, idesc, 1);
-                }
-              }
-            }
-            tc::tc_commit(&empty[idx]);     // slot reusable once these MMAs retire
-          }
-          tc::tc_commit(acc_full);          // accumulator of this stage complete
-        }
-      }
-    }
+    if (lane == 0)
+      eng::mma_loop<NSPLIT, C::NSLOT, C::SLOT_BYTES>(c_plan_fwd, ring, a_ready, acc_full, T_ACC, T_AHI, T_ALO,
+                                                     tc::smem_u32(areg), a.num_tiles);
   } else {
-    // ===================== epilogue warps (128 threads, thread <-> tile row) ======================
-    const int quad = warp & 3;
+    // ===================== epilogue: 8 warps, 2 per TMEM lane quadrant =============================
+    const int quad = warp & 3, half = (warp - 2) >> 2;
     const int row = quad * 32 + lane;
     const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
     uint32_t m = 0;
     for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
       const int64_t p = (int64_t)tile * TILE_M + row;
       const bool valid = p < a.P;
-      // ---- positional encodings of this row's point and view direction -> smem A slabs ----------
+      // ---- positional encodings -> smem A slabs (half 0: X chunks 0-3; half 1: X 4-7 and V 0-3)
       {
         float x[3] = {0.f, 0.f, 0.f}, vd[3] = {0.f, 0.f, 0.f};
         if (valid) {
@@ -352,8 +293,21 @@ __global__ void __launch_bounds__(192, 1) field_fused_fwd_kernel(Args a) {
             for (int c = 0; c < 3; ++c) { x[c] = a.pts[p * 3 + c]; vd[c] = a.viewdirs[r * 3 + c]; }
           }
         }
-        pe_write<10, 8>(x, valid, Xhi, Xlo, row, SPLIT, a.dump_pe ? a.dump_pe + p * a.dump_pe_ld : nullptr);
-        pe_write<4, 4>(vd, valid, Vhi, Vlo, row, SPLIT, a.dump_ped ? a.dump_ped + p * a.dump_ped_ld : nullptr);
+        float* dpe = a.dump_pe ? a.dump_pe + p * a.dump_pe_ld : nullptr;
+        float* dped = a.dump_ped ? a.dump_ped + p * a.dump_ped_ld : nullptr;
+        if (half == 0) {          // compile-time chunk indices keep the PE column maths constant-folded
+#pragma unroll
+          for (int c = 0; c < 4; ++c)
+            pe_chunk<10, SPLIT>(x, valid, c, areg + A_XHI, areg + A_XLO, row, a.img_x, tile, dpe);
+          *reinterpret_cast<float4*>(out_s + row * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+        } else {
+#pragma unroll
+          for (int c = 4; c < 8; ++c)
+            pe_chunk<10, SPLIT>(x, valid, c, areg + A_XHI, areg + A_XLO, row, a.img_x, tile, dpe);
+#pragma unroll
+          for (int c = 0; c < 4; ++c)
+            pe_chunk<4, SPLIT>(vd, valid, c, areg + A_VHI, areg + A_VLO, row, a.img_v, tile, dped);
+        }
         tc::fence_proxy_async();
         tc::mbar_arrive(a_ready);
       }
@@ -361,46 +315,53 @@ __global__ void __launch_bounds__(192, 1) field_fused_fwd_kernel(Args a) {
 #pragma unroll 1
       for (int s = 0; s < NSTAGE; ++s, ++m) {
         const StageDef d = stage_def(s);
-        const float* bias = cst + (s < 8 ? C_BIAS + s * 256 : (s == 8 ? C_BFEAT : C_BVIEW));
+        const int nchunk = d.N / 64;          // 32-column chunks per warp (this warp's half)
+        const int cbase = half * (d.N / 2);
         tc::mbar_wait(acc_full, m & 1);
         tc::tc_fence_after();
 #pragma unroll 1
-        for (int c0 = 0; c0 < d.N; c0 += 32) {
-          uint32_t v[32];
-          tc::tmem_ld32(T_ACC + lane_base + c0, v);
+        for (int cc = 0; cc < nchunk; cc += 2) {
+          uint32_t v0[32], v1[32];
+          const int c0 = cbase + cc * 32, c1 = c0 + 32;
+          tc::tmem_ld32(T_ACC + lane_base + c0, v0);
+          tc::tmem_ld32(T_ACC + lane_base + c1, v1);
           tc::tmem_ld_wait();
-          float f[32];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            float t = __uint_as_float(v[j]) + bias[c0 + j];
-            f[j] = d.relu ? fmaxf(t, 0.f) : t;
-          }
-          if (a.dump[s] && valid) {
-            float* dp = a.dump[s] + p * a.dump_ld[s] + c0;
-#pragma unroll
-            for (int j = 0; j < 32; ++j) dp[j] = f[j];
-          }
-          if (s == 7) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) alpha = fmaf(f[j], cst[C_WALPHA + c0 + j], alpha);
-          }
-          if (s == 9) {
+          for (int u = 0; u < 2; ++u) {
+            const uint32_t (&v)[32] = u ? v1 : v0;
+            const int cu = u ? c1 : c0;
+            float f[32];
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
-              rgb[0] = fmaf(f[j], cst[C_WRGB + c0 + j], rgb[0]);
-              rgb[1] = fmaf(f[j], cst[C_WRGB + 128 + c0 + j], rgb[1]);
-              rgb[2] = fmaf(f[j], cst[C_WRGB + 256 + c0 + j], rgb[2]);
+              const float t = __uint_as_float(v[j]);
+              f[j] = d.relu ? fmaxf(t, 0.f) : t;
             }
-          } else {
-            uint32_t hi[16], lo[16];
+            if (a.dump[s] && valid) {
+              float* dp = a.dump[s] + p * a.dump_ld[s] + cu;
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              __nv_bfloat16 h0 = __float2bfloat16_rn(f[2 * j]), h1 = __float2bfloat16_rn(f[2 * j + 1]);
-              hi[j] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-              if (SPLIT) lo[j] = tc::pack_bf16(f[2 * j] - __bfloat162float(h0), f[2 * j + 1] - __bfloat162float(h1));
+              for (int j = 0; j < 32; ++j) dp[j] = f[j];
             }
-            tc::tmem_st16(T_AHI + lane_base + (uint32_t)(c0 >> 1), hi);
-            if (SPLIT) tc::tmem_st16(T_ALO + lane_base + (uint32_t)(c0 >> 1), lo);
+            if (s == 7) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) alpha = fmaf(f[j], cst[C_WALPHA + cu + j], alpha);
+            }
+            if (s == 9) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                rgb[0] = fmaf(f[j], cst[C_WRGB + cu + j], rgb[0]);
+                rgb[1] = fmaf(f[j], cst[C_WRGB + 128 + cu + j], rgb[1]);
+                rgb[2] = fmaf(f[j], cst[C_WRGB + 256 + cu + j], rgb[2]);
+              }
+            }
+            if (s != 9 || a.img_out[9].base) {
+              uint32_t hi[16], lo[16];
+              eng::split32<SPLIT>(f, hi, lo);
+              if (s != 9) {
+                tc::tmem_st16(T_AHI + lane_base + (uint32_t)(cu >> 1), hi);
+                if (SPLIT) tc::tmem_st16(T_ALO + lane_base + (uint32_t)(cu >> 1), lo);
+              }
+              if (a.img_out[s].base) eng::dump32<SPLIT>(a.img_out[s], tile, row, cu, hi, lo);
+            }
           }
         }
         if (s < 9) {
@@ -409,13 +370,19 @@ __global__ void __launch_bounds__(192, 1) field_fused_fwd_kernel(Args a) {
           tc::mbar_arrive(a_ready);
         }
       }
-      if (valid) {
-        float4 o = make_float4(rgb[0] + cst[C_SCAL + 1], rgb[1] + cst[C_SCAL + 2], rgb[2] + cst[C_SCAL + 3],
-                               alpha + cst[C_SCAL]);
-        *reinterpret_cast<float4*>(a.raw + p * 4) = o;
-      }
-      // order this tile's last TMEM reads before the next tile's first MMA (issued after a_ready)
+      // combine the two column-halves of each row: half 1 adds into smem, half 0 finishes
+      atomicAdd(out_s + row * 4 + 0, rgb[0]);
+      atomicAdd(out_s + row * 4 + 1, rgb[1]);
+      atomicAdd(out_s + row * 4 + 2, rgb[2]);
+      atomicAdd(out_s + row * 4 + 3, alpha);
       tc::tc_fence_before();
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (half == 0 && valid) {
+        const float4 o = *reinterpret_cast<const float4*>(out_s + row * 4);
+        *reinterpret_cast<float4*>(a.raw + p * 4) =
+            make_float4(o.x + cst[C_SCAL + 1], o.y + cst[C_SCAL + 2], o.z + cst[C_SCAL + 3], o.w + cst[C_SCAL]);
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");   // out_s is re-zeroed by the next tile's prologue
     }
   }
   tc::tc_fence_before();
