@@ -361,7 +361,7 @@ def inverse_cdf_sample(bins, weights, u, return_inds=False, cdf=None):
 
 def render_rays(rays, P_coarse, P_fine, N_samples, N_importance=0, lindisp=False,
                 white_bkgd=False, t_rand=None, u=None, noise0=None, noise1=None,
-                retraw=False, L_pos=10, L_dir=4):
+                retraw=False, L_pos=10, L_dir=4, sequential_cdf=False):
     """NeRF/render.py:186-300 with all randomness injected:
     t_rand [N,Nc] (None = perturb 0), u [N,Nf] (None = deterministic linspace),
     noise0 [N,Nc] / noise1 [N,Nc+Nf] already multiplied by raw_noise_std."""
@@ -378,7 +378,8 @@ def render_rays(rays, P_coarse, P_fine, N_samples, N_importance=0, lindisp=False
         z_mid = .5 * (z[:, 1:] + z[:, :-1])
         if u is None:
             u = torch.linspace(0., 1., steps=N_importance, dtype=z.dtype).expand(z.shape[0], N_importance)
-        z_samples = inverse_cdf_sample(z_mid, weights[:, 1:-1], u).detach()
+        cdf = pdf_to_cdf_sequential(weights[:, 1:-1].detach().float().numpy()).to(z.dtype) if sequential_cdf else None
+        z_samples = inverse_cdf_sample(z_mid, weights[:, 1:-1], u, cdf=cdf).detach()
         z, _ = torch.sort(torch.cat([z, z_samples], -1), -1)
         pts = rays_o[:, None, :] + rays_d[:, None, :] * z[:, :, None]
         raw = query_field(P_fine if P_fine is not None else P_coarse, pts, viewdirs, L_pos, L_dir)
@@ -406,7 +407,8 @@ def img2mse(x, y):
 
 
 def train_step(cam: Camera, P_coarse, P_fine, kps, idx, target, H, W, N_samples, N_importance,
-               near=0., far=1., t_rand=None, u=None, noise0=None, noise1=None, white_bkgd=False):
+               near=0., far=1., t_rand=None, u=None, noise0=None, noise1=None, white_bkgd=False,
+               sequential_cdf=False):
     """One optimisation step's forward, NeRF/run_nerf.py:385-506 (camera branch, NDC,
     use_viewdirs): pixels -> rays -> render -> loss = mse(rgb) + mse(rgb0).  Caller runs
     ``loss.backward()``; gradients land on every tensor that requires grad."""
@@ -415,7 +417,7 @@ def train_step(cam: Camera, P_coarse, P_fine, kps, idx, target, H, W, N_samples,
     rays = pack_rays(H, W, rays_o, rays_d, near, far, True, True, K[0, 0], K[1, 1])
     ret = clamp_rgb_(render_rays(rays, P_coarse, P_fine, N_samples, N_importance,
                                  white_bkgd=white_bkgd, t_rand=t_rand, u=u,
-                                 noise0=noise0, noise1=noise1))
+                                 noise0=noise0, noise1=noise1, sequential_cdf=sequential_cdf))
     loss = img2mse(ret["rgb_map"], target)
     if "rgb0" in ret:
         loss = loss + img2mse(ret["rgb0"], target)

@@ -154,10 +154,11 @@ size_t scnerf_field_workspace_bytes(const scnerf_mlp* m, int64_t P, int32_t trai
 
 static int field_fwd_dispatch(const scnerf_mlp& m, int precision, const float* rays, int ray_cols,
                               const float* z, const float* pts, const float* viewdirs, int64_t N,
-                              int S, const FieldBufs& B, float* raw, void* stream) {
+                              int S, const FieldBufs& B, float* raw, void* stream,
+                              const TcFwdImages* imgs = nullptr) {
   if (precision == SCNERF_PRECISION_FP32)
     return field_simt_fwd(m, rays, ray_cols, z, pts, viewdirs, N, S, B, raw, stream);
-  return field_tc_fwd(m, precision, rays, ray_cols, z, pts, viewdirs, N, S, B, raw, stream);
+  return field_tc_fwd(m, precision, rays, ray_cols, z, pts, viewdirs, N, S, B, raw, stream, imgs);
 }
 
 int scnerf_field_fwd(const scnerf_mlp* m, const float* pts, const float* viewdirs, int64_t N, int64_t S,
@@ -226,6 +227,9 @@ struct RenderWS {
   float* g_raw;
   FieldBufs fb_c, fb_f;
   FieldGradBufs gb;
+  bool tc_train;            // tensor-core training path: bf16 tile images instead of fp32 activations
+  TcFwdImages im_c, im_f;
+  TcBwdBufs tb;
 };
 
 static void render_ws_layout(Arena& ar, const scnerf_render_cfg& cfg, const scnerf_mlp& m, int64_t N,
@@ -244,7 +248,18 @@ static void render_ws_layout(Arena& ar, const scnerf_render_cfg& cfg, const scne
     w.acc_f = ar.get<float>(N);
     w.depth_f = ar.get<float>(N);
   }
-  if (cfg.training) {
+  w.tc_train = cfg.training && cfg.precision != SCNERF_PRECISION_FP32;
+  if (w.tc_train) {
+    const int ns = cfg.precision == SCNERF_PRECISION_BF16X3 ? 3 : 1;
+    w.g_raw = ar.get<float>(N * std::max(Nc, St) * 4);
+    field_bufs_alloc(ar, m, N * Nc, true, w.fb_c, true);
+    tc_fwd_images_alloc(ar, N * Nc, ns, w.im_c);
+    if (Nf > 0) {
+      field_bufs_alloc(ar, m, N * St, true, w.fb_f, true);
+      tc_fwd_images_alloc(ar, N * St, ns, w.im_f);
+    }
+    tc_bwd_bufs_alloc(ar, N * std::max(Nc, St), ns, w.tb);
+  } else if (cfg.training) {
     w.g_raw = ar.get<float>(N * std::max(Nc, St) * 4);
     field_bufs_alloc(ar, m, N * Nc, true, w.fb_c);
     if (Nf > 0) field_bufs_alloc(ar, m, N * St, true, w.fb_f);
@@ -321,7 +336,7 @@ int scnerf_render_rays_fwd(const scnerf_render_cfg* cfg, const float* rays, int6
   SCNERF_LAUNCH(stratified_kernel, (unsigned)cdiv(N * Nc, 256), 256, 0, stream, rays, cfg->ray_cols, N, Nc,
                 cfg->lindisp, cfg->perturb > 0, rnd->t_rand, cfg->seed, w.z_c);
   rc = field_fwd_dispatch(mc, cfg->precision, rays, cfg->ray_cols, w.z_c, nullptr, nullptr, N, Nc, w.fb_c,
-                          w.raw_c, stream);
+                          w.raw_c, stream, w.tc_train ? &w.im_c : nullptr);
   if (rc) return rc;
   const bool two = Nf > 0;
   rc = composite_launch(*cfg, w.raw_c, rcn, w.z_c, rays, rnd->noise0, RNG_NOISE0, N, Nc,
@@ -342,7 +357,7 @@ int scnerf_render_rays_fwd(const scnerf_render_cfg* cfg, const float* rays, int6
     size_t smem = sizeof(float) * (2 * (Nc - 1) + a.sort_n);
     SCNERF_LAUNCH(sample_pdf_kernel, (unsigned)N, 128, smem, stream, a);
     rc = field_fwd_dispatch(mf, cfg->precision, rays, cfg->ray_cols, w.z_f, nullptr, nullptr, N, St, w.fb_f,
-                            w.raw_f, stream);
+                            w.raw_f, stream, w.tc_train ? &w.im_f : nullptr);
     if (rc) return rc;
     rc = composite_launch(*cfg, w.raw_f, rcn, w.z_f, rays, rnd->noise1, RNG_NOISE1, N, St, out->rgb_map,
                           out->disp_map, out->acc_map, w.w_f, w.depth_f, stream);
@@ -412,7 +427,9 @@ int scnerf_render_rays_bwd(const scnerf_render_cfg* cfg, const float* rays, int6
     rc = composite_bwd_launch(*cfg, w.raw_f, rcn, w.z_f, rays, rnd->noise1, RNG_NOISE1, N, St, gin->rgb_map,
                               gin->disp_map, gin->acc_map, w.acc_f, w.depth_f, w.g_raw, d_rays, stream);
     if (rc) return rc;
-    rc = field_simt_bwd(mf, gf, rays, cfg->ray_cols, w.z_f, N, St, w.fb_f, w.gb, w.g_raw, d_rays, stream);
+    rc = w.tc_train ? field_tc_bwd(mf, gf, cfg->precision, rays, cfg->ray_cols, w.z_f, N, St, w.fb_f, w.im_f, w.tb,
+                                   w.g_raw, d_rays, stream)
+                    : field_simt_bwd(mf, gf, rays, cfg->ray_cols, w.z_f, N, St, w.fb_f, w.gb, w.g_raw, d_rays, stream);
     if (rc) return rc;
   }
   const float* g_rgb = two ? gin->rgb0 : gin->rgb_map;
@@ -422,7 +439,9 @@ int scnerf_render_rays_bwd(const scnerf_render_cfg* cfg, const float* rays, int6
     rc = composite_bwd_launch(*cfg, w.raw_c, rcn, w.z_c, rays, rnd->noise0, RNG_NOISE0, N, Nc, g_rgb, g_disp,
                               g_acc, w.acc_c, w.depth_c, w.g_raw, d_rays, stream);
     if (rc) return rc;
-    rc = field_simt_bwd(mc, gc, rays, cfg->ray_cols, w.z_c, N, Nc, w.fb_c, w.gb, w.g_raw, d_rays, stream);
+    rc = w.tc_train ? field_tc_bwd(mc, gc, cfg->precision, rays, cfg->ray_cols, w.z_c, N, Nc, w.fb_c, w.im_c, w.tb,
+                                   w.g_raw, d_rays, stream)
+                    : field_simt_bwd(mc, gc, rays, cfg->ray_cols, w.z_c, N, Nc, w.fb_c, w.gb, w.g_raw, d_rays, stream);
     if (rc) return rc;
   }
   return 0;

@@ -224,7 +224,7 @@ struct FieldBufs {
   uint8_t* tc_img = nullptr;           // packed bf16 weight image for the tcgen05 path
   float* tc_cbuf = nullptr;            // packed biases / head weights
 };
-constexpr size_t TC_IMG_BYTES = 2400 * 1024;   // >= fused::weight_image_bytes<3>() (checked there)
+constexpr size_t TC_IMG_BYTES = 2560 * 1024;   // >= fused::weight_image_bytes<3>() (checked there)
 constexpr size_t TC_CBUF_FLOATS = 4096;
 struct FieldGradBufs {
   float *Ga = nullptr, *Gb = nullptr;  // [P, W] ping-pong
@@ -233,12 +233,14 @@ struct FieldGradBufs {
   float* Ghv = nullptr;                // [P, W/2]
 };
 
-inline void field_bufs_alloc(Arena& ar, const scnerf_mlp& m, int64_t P, bool keep_all, FieldBufs& B) {
+inline void field_bufs_alloc(Arena& ar, const scnerf_mlp& m, int64_t P, bool keep_all, FieldBufs& B,
+                             bool tc_only = false) {
   B.ldx5 = m.input_ch + m.W;
   B.ldf = m.W + m.input_ch_views;
   B.keep_all = keep_all;
   B.tc_img = ar.get<uint8_t>(TC_IMG_BYTES);
   B.tc_cbuf = ar.get<float>(TC_CBUF_FLOATS);
+  if (tc_only) return;     // tensor-core training path keeps bf16 tile images instead (TcTrainBufs)
   B.X5 = ar.get<float>(P * B.ldx5);
   if (keep_all) {
     for (int i = 0; i < m.D; ++i)

@@ -9,6 +9,8 @@
 #include "field_simt.cuh"
 #include "tc_prims.cuh"
 #include "field_tc_fused.cuh"
+#include "field_tc_dgrad.cuh"
+#include "field_tc_wgrad.cuh"
 
 namespace scnerf {
 
@@ -200,10 +202,40 @@ inline fused::PackSrc make_pack_src(const scnerf_mlp& m) {
   return src;
 }
 
+// bf16 tile images kept by the tensor-core training path (one set of forward images per pass;
+// the dgrad images and per-sample geometry gradients are shared between passes)
+struct TcFwdImages { eng::ImgDump x, v, h[8], feat, hv; };
+struct TcBwdBufs {
+  eng::ImgDump dz[8], dfeat, dzv;
+  float *g_pts = nullptr, *g_vd = nullptr;
+  uint8_t* wimg = nullptr;      // transposed weight slabs for the dgrad kernel
+};
+inline eng::ImgDump img_alloc(Arena& ar, int64_t tiles, uint32_t F, uint32_t nh) {
+  eng::ImgDump d;
+  d.F = F; d.nhalf = nh;
+  d.base = ar.get<uint8_t>((size_t)tiles * F * 256u * nh);
+  return d;
+}
+inline void tc_fwd_images_alloc(Arena& ar, int64_t P, int nsplit, TcFwdImages& I) {
+  const int64_t T = cdiv(P, 128);
+  const uint32_t nh = nsplit == 3 ? 2 : 1;
+  I.x = img_alloc(ar, T, 64, nh); I.v = img_alloc(ar, T, 32, nh);
+  for (int i = 0; i < 8; ++i) I.h[i] = img_alloc(ar, T, 256, nh);
+  I.feat = img_alloc(ar, T, 256, nh); I.hv = img_alloc(ar, T, 128, nh);
+}
+inline void tc_bwd_bufs_alloc(Arena& ar, int64_t P, int nsplit, TcBwdBufs& G) {
+  const int64_t T = cdiv(P, 128);
+  const uint32_t nh = nsplit == 3 ? 2 : 1;
+  for (int i = 0; i < 8; ++i) G.dz[i] = img_alloc(ar, T, 256, nh);
+  G.dfeat = img_alloc(ar, T, 256, nh); G.dzv = img_alloc(ar, T, 128, nh);
+  G.g_pts = ar.get<float>(P * 3); G.g_vd = ar.get<float>(P * 3);
+  G.wimg = ar.get<uint8_t>(TC_IMG_BYTES);
+}
+
 template <int NSPLIT>
 inline int field_tc_fwd_impl(const scnerf_mlp& m, const float* rays, int ray_cols, const float* z,
                              const float* pts, const float* viewdirs, int64_t N, int S,
-                             const FieldBufs& B, float* raw, void* stream) {
+                             const FieldBufs& B, float* raw, void* stream, const TcFwdImages* imgs = nullptr) {
   using namespace fused;
   static_assert(C_TOTAL <= (int)TC_CBUF_FLOATS, "TC_CBUF_FLOATS too small");
   int rc = fwd_plan_init();
@@ -216,6 +248,11 @@ inline int field_tc_fwd_impl(const scnerf_mlp& m, const float* rays, int ray_col
   a.rays = rays; a.ray_cols = ray_cols; a.z = z; a.pts = pts; a.viewdirs = viewdirs;
   a.P = N * S; a.S = S; a.wimg = B.tc_img; a.cbuf = B.tc_cbuf; a.raw = raw;
   a.num_tiles = (int)cdiv(a.P, TILE_M);
+  if (imgs) {                 // training with the tensor-core backward: bf16 tile images
+    a.img_x = imgs->x; a.img_v = imgs->v;
+    for (int s = 0; s < 8; ++s) a.img_out[s] = imgs->h[s];
+    a.img_out[8] = imgs->feat; a.img_out[9] = imgs->hv;
+  }
   if (B.keep_all && B.X5) {   // training with the fp32 CUDA-core backward: fp32 row-major layer inputs
     for (int s = 0; s < 8; ++s) {
       a.dump[s] = (s == 4) ? B.X5 + 63 : B.H[s];
@@ -233,15 +270,115 @@ inline int field_tc_fwd_impl(const scnerf_mlp& m, const float* rays, int ray_col
 
 inline int field_tc_fwd(const scnerf_mlp& m, int precision, const float* rays, int ray_cols,
                         const float* z, const float* pts, const float* viewdirs, int64_t N, int S,
-                        const FieldBufs& B, float* raw, void* stream) {
+                        const FieldBufs& B, float* raw, void* stream, const TcFwdImages* imgs = nullptr) {
   if (!(m.D == 8 && m.W == 256 && m.skip == 4 && m.use_viewdirs && m.L_pos == 10 && m.L_dir == 4))
     return fail(SCNERF_ERR_UNSUPPORTED,
                 "tensor-core field path is specialised for the 8x256, skip-4, use_viewdirs network "
                 "(multires 10/4); use precision fp32 for other shapes");
   if (rays && ray_cols != 11) return fail(SCNERF_ERR_ARG, "tensor-core field path needs 11-column rays");
   if (precision == SCNERF_PRECISION_BF16X3)
-    return field_tc_fwd_impl<3>(m, rays, ray_cols, z, pts, viewdirs, N, S, B, raw, stream);
-  return field_tc_fwd_impl<1>(m, rays, ray_cols, z, pts, viewdirs, N, S, B, raw, stream);
+    return field_tc_fwd_impl<3>(m, rays, ray_cols, z, pts, viewdirs, N, S, B, raw, stream, imgs);
+  return field_tc_fwd_impl<1>(m, rays, ray_cols, z, pts, viewdirs, N, S, B, raw, stream, imgs);
+}
+
+// ---- tensor-core backward: dgrad chain -> per-ray reduce -> wgrad pass -> head gradients -----------
+inline int bwd_plan_init() {
+  static bool done[64] = {};
+  int dev = 0;
+  SCNERF_CUDA(cudaGetDevice(&dev));
+  if (dev < 64 && done[dev]) return 0;
+  static eng::Plan P;
+  static fused::PlanSrc S;
+  dgrad::build_plan(P, S);
+  if (fused::plan_image_bytes(P, 3) > TC_IMG_BYTES) return fail(SCNERF_ERR_WORKSPACE, "TC_IMG_BYTES too small (dgrad)");
+  SCNERF_CUDA(cudaMemcpyToSymbol(dgrad::c_plan_dgrad, &P, sizeof(P)));
+  SCNERF_CUDA(cudaMemcpyToSymbol(dgrad::d_plansrc_dgrad, &S, sizeof(S)));
+  SCNERF_CUDA(cudaFuncSetAttribute(dgrad::field_fused_dgrad_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   dgrad::Cfg<1>::SMEM_BYTES));
+  SCNERF_CUDA(cudaFuncSetAttribute(dgrad::field_fused_dgrad_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   dgrad::Cfg<3>::SMEM_BYTES));
+  SCNERF_CUDA(cudaFuncSetAttribute(wgrad::field_wgrad_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   wgrad::Cfg<1>::SMEM_BYTES));
+  SCNERF_CUDA(cudaFuncSetAttribute(wgrad::field_wgrad_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   wgrad::Cfg<3>::SMEM_BYTES));
+  if (dev < 64) done[dev] = true;
+  return 0;
+}
+inline int dgrad_n_slabs() {
+  static int n = -1;
+  if (n < 0) { static eng::Plan P; static fused::PlanSrc S; dgrad::build_plan(P, S); n = P.n_slabs; }
+  return n;
+}
+
+inline void wgrad_unit(wgrad::Unit& u, int a_img, int a_half, int b_img, int n, int acc_col, float* out, int ld,
+                       int rows_valid, int cols_valid) {
+  u.a_img = a_img; u.a_half = a_half; u.b_img = b_img; u.n = n; u.acc_col = acc_col; u.out = out; u.ld = ld;
+  u.rows_valid = rows_valid; u.cols_valid = cols_valid;
+}
+
+template <int NSPLIT>
+inline int field_tc_bwd_impl(const scnerf_mlp& m, const scnerf_mlp& g, const float* rays, int ray_cols,
+                             const float* z, int64_t N, int S, const FieldBufs& B, const TcFwdImages& I,
+                             const TcBwdBufs& G, const float* g_raw, float* d_rays, void* stream) {
+  int rc = bwd_plan_init();
+  if (rc) return rc;
+  const int64_t P = N * S;
+  const int T = (int)cdiv(P, 128);
+  fused::PackSrc src = make_pack_src(m);
+  SCNERF_LAUNCH((dgrad::pack_dgrad_kernel<NSPLIT>), dim3(2, (unsigned)dgrad_n_slabs()), 256, 0, stream, src, G.wimg);
+  SCNERF_LAUNCH(fused::pack_consts_kernel, (unsigned)cdiv(fused::C_TOTAL, 256), 256, 0, stream, src, B.tc_cbuf);
+  dgrad::Args a{};
+  a.rays = rays; a.ray_cols = ray_cols; a.z = z; a.P = P; a.S = S; a.num_tiles = T;
+  a.g_raw = g_raw; a.wimg = G.wimg; a.cbuf = B.tc_cbuf;
+  for (int i = 0; i < 8; ++i) { a.img_h[i] = I.h[i]; a.out_dz[i] = G.dz[i]; }
+  a.img_hv = I.hv; a.out_dfeat = G.dfeat; a.out_dzv = G.dzv; a.g_pts = G.g_pts; a.g_vd = G.g_vd;
+  SCNERF_LAUNCH((dgrad::field_fused_dgrad_kernel<NSPLIT>), std::min(device_sm_count(), T), 320,
+                dgrad::Cfg<NSPLIT>::SMEM_BYTES, stream, a);
+  if (d_rays)
+    SCNERF_LAUNCH(dgrad::reduce_pts_grad_kernel, (unsigned)cdiv(N, 4), 128, 0, stream, G.g_pts, G.g_vd, z, N, S,
+                  ray_cols, d_rays);
+  // ---- wgrad jobs --------------------------------------------------------------------------------------
+  wgrad::Args w{};
+  w.num_tiles = T; w.P = P;
+  w.nslices = std::max(1, device_sm_count() / wgrad::NJOBS);
+  auto std_job = [&](wgrad::Job& J, const eng::ImgDump& A, const eng::ImgDump& Bi, float* dW, int ld, int col0,
+                     int cols_valid, float* db) {
+    J.a[0] = A; J.na = 1; J.b[0] = Bi; J.nb = 1; J.nu = 2; J.db = db;
+    wgrad_unit(J.u[0], 0, 0, 0, (int)Bi.F, 0, dW + col0, ld, 128, cols_valid);
+    wgrad_unit(J.u[1], 0, 1, 0, (int)Bi.F, 256, dW + (int64_t)128 * ld + col0, ld, 128, cols_valid);
+  };
+  {   // J0: layer 0 (dZ0 x X) and the skip columns of layer 5 (dZ5 x X)
+    wgrad::Job& J = w.job[0];
+    J.a[0] = G.dz[0]; J.a[1] = G.dz[5]; J.na = 2; J.b[0] = I.x; J.nb = 1; J.nu = 4; J.db = g.pts_b[0];
+    wgrad_unit(J.u[0], 0, 0, 0, 64, 0, g.pts_w[0], 63, 128, 63);
+    wgrad_unit(J.u[1], 0, 1, 0, 64, 64, g.pts_w[0] + 128 * 63, 63, 128, 63);
+    wgrad_unit(J.u[2], 1, 0, 0, 64, 128, g.pts_w[5], 319, 128, 63);
+    wgrad_unit(J.u[3], 1, 1, 0, 64, 192, g.pts_w[5] + 128 * 319, 319, 128, 63);
+  }
+  for (int l = 1; l <= 4; ++l) std_job(w.job[l], G.dz[l], I.h[l - 1], g.pts_w[l], 256, 0, 256, g.pts_b[l]);
+  std_job(w.job[5], G.dz[5], I.h[4], g.pts_w[5], 319, 63, 256, g.pts_b[5]);
+  std_job(w.job[6], G.dz[6], I.h[5], g.pts_w[6], 256, 0, 256, g.pts_b[6]);
+  std_job(w.job[7], G.dz[7], I.h[6], g.pts_w[7], 256, 0, 256, g.pts_b[7]);
+  std_job(w.job[8], G.dfeat, I.h[7], g.feature_w, 256, 0, 256, g.feature_b);
+  w.job[8].g_raw = g_raw; w.job[8].dw_alpha = g.alpha_w;
+  {   // J9: views layer: dZ_v (128 rows) x [feature | PE(dir)]
+    wgrad::Job& J = w.job[9];
+    J.a[0] = G.dzv; J.na = 1; J.b[0] = I.feat; J.b[1] = I.v; J.nb = 2; J.nu = 2; J.db = g.views_b;
+    wgrad_unit(J.u[0], 0, 0, 0, 256, 0, g.views_w, 283, 128, 256);
+    wgrad_unit(J.u[1], 0, 0, 1, 32, 256, g.views_w + 256, 283, 128, 27);
+  }
+  SCNERF_LAUNCH((wgrad::field_wgrad_kernel<NSPLIT>), (unsigned)(w.nslices * wgrad::NJOBS), 192,
+                wgrad::Cfg<NSPLIT>::SMEM_BYTES, stream, w);
+  SCNERF_LAUNCH((wgrad::head_wgrad_img_kernel<(NSPLIT == 3 ? 2 : 1)>), (unsigned)std::min(T, 2 * device_sm_count()), 128, 0,
+                stream, I.hv, g_raw, P, T, g.rgb_w, g.rgb_b, g.alpha_b);
+  return 0;
+}
+inline int field_tc_bwd(const scnerf_mlp& m, const scnerf_mlp& g, int precision, const float* rays, int ray_cols,
+                        const float* z, int64_t N, int S, const FieldBufs& B, const TcFwdImages& I,
+                        const TcBwdBufs& G, const float* g_raw, float* d_rays, void* stream) {
+  if (precision == SCNERF_PRECISION_BF16X3)
+    return field_tc_bwd_impl<3>(m, g, rays, ray_cols, z, N, S, B, I, G, g_raw, d_rays, stream);
+  return field_tc_bwd_impl<1>(m, g, rays, ray_cols, z, N, S, B, I, G, g_raw, d_rays, stream);
 }
 
 }  // namespace scnerf

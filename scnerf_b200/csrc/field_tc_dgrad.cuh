@@ -1,0 +1,330 @@
+// Fused field backward, data-gradient chain, on tcgen05 (sm_100a).
+//
+// For each 128-sample tile:  d(raw)[4] -> rgb/alpha heads (fp32 in registers) -> views layer ->
+// feature layer -> trunk 7..0, every  g_in = dZ * W  GEMM on the tensor cores with the SAME slab
+// engine as the forward (A = dZ in TMEM, B = transposed bf16 weight slabs streamed by bulk TMA),
+// ReLU masks taken from the forward's bf16 tile images, and every dZ written back as a bf16 (hi[,lo])
+// TILE IMAGE that the wgrad kernel consumes directly.  Also produces d(pts) and d(viewdirs) per
+// sample (PE backward in registers), reduced per ray by reduce_pts_grad_kernel.
+//
+// Graph = NeRF.forward's autograd graph (NeRF/run_nerf_helpers.py:105-128) + Embedder (:24-72).
+#pragma once
+#include "common.cuh"
+#include "tc_prims.cuh"
+#include "tc_engine.cuh"
+#include "field_tc_fused.cuh"
+
+namespace scnerf {
+namespace dgrad {
+
+using eng::TILE_M;
+using fused::PlanSrc;
+using fused::SrcDef;
+constexpr int NSTAGE = 11;   // S1, S2, S3, S4, S5a, S5b, S6, S7, S8, S9, S10
+constexpr int ACC2_COL = 320;
+
+inline void build_plan(eng::Plan& P, PlanSrc& S) {
+  int n = 0;
+  uint32_t off = 0;
+  auto add = [&](int N, int acc_col, int j, int K16, bool first, bool last, int wsel, int col0, int valid_n) {
+    eng::SlabDef& e = P.slab[n];
+    SrcDef& q = S.s[n];
+    e = eng::SlabDef{};
+    q = SrcDef{};
+    e.n = (uint16_t)N; e.acc_col = (uint16_t)acc_col; e.a_kind = eng::A_TMEM; e.a_off = (uint16_t)(j * 8);
+    e.flags = (first ? eng::F_ZERO_ACC : 0) | (last ? eng::F_STAGE_END : 0);
+    q.wsel = (uint8_t)wsel; q.kind = 1; q.row0 = (uint16_t)(16 * j); q.col0 = (uint16_t)col0;
+    q.valid_k = 16; q.valid_n = (uint16_t)valid_n; q.img_off = off;
+    off += (uint32_t)N * 32u;
+    ++n;
+    (void)K16;
+  };
+  // S1: [g_feat | g_V] = dZ_v (K=128) * W_views
+  for (int j = 0; j < 8; ++j) {
+    add(256, 0, j, 8, j == 0, false, 9, 0, 256);
+    add(32, ACC2_COL, j, 8, j == 0, j == 7, 9, 256, 27);
+  }
+  auto full = [&](int wsel, int N, int col0, int valid_n) {
+    for (int j = 0; j < 16; ++j) add(N, 0, j, 16, j == 0, j == 15, wsel, col0, valid_n);
+  };
+  full(8, 256, 0, 256);      // S2 : g_h7 = g_feat * W_feature
+  full(7, 256, 0, 256);      // S3 : g_h6 = dZ7 * W7
+  full(6, 256, 0, 256);      // S4 : g_h5 = dZ6 * W6
+  full(5, 64, 0, 63);        // S5a: g_X (skip branch) = dZ5 * W5[:, :63]
+  full(5, 256, 63, 256);     // S5b: g_h4 = dZ5 * W5[:, 63:]
+  full(4, 256, 0, 256);      // S6 : g_h3
+  full(3, 256, 0, 256);      // S7 : g_h2
+  full(2, 256, 0, 256);      // S8 : g_h1
+  full(1, 256, 0, 256);      // S9 : g_h0
+  full(0, 64, 0, 63);        // S10: g_X (layer 0) = dZ0 * W0
+  P.n_slabs = n; P.n_stages = NSTAGE;
+}
+
+__constant__ eng::Plan c_plan_dgrad;
+__device__ PlanSrc d_plansrc_dgrad;
+template <int NSPLIT>
+__global__ void __launch_bounds__(256) pack_dgrad_kernel(fused::PackSrc src, uint8_t* __restrict__ img) {
+  const int i = blockIdx.y;
+  if (i < c_plan_dgrad.n_slabs) fused::pack_slab_impl<NSPLIT>(c_plan_dgrad.slab[i], d_plansrc_dgrad.s[i], src, img);
+}
+
+template <int NSPLIT> struct Cfg {
+  static constexpr int NSLOT = NSPLIT == 1 ? 16 : 9;
+  static constexpr int SLOT_BYTES = NSPLIT == 1 ? 8192 : 16384;
+  static constexpr int OFF_RING = 0;
+  static constexpr int OFF_C = NSLOT * SLOT_BYTES;
+  static constexpr int OFF_GX = OFF_C + ((fused::C_TOTAL * 4 + 127) / 128) * 128;   // [64][128] fp32 skip-branch d(PE)
+  static constexpr int OFF_OUT = OFF_GX + 64 * 128 * 4;                               // [128][4]
+  static constexpr int OFF_BAR = OFF_OUT + 128 * 4 * 4;
+  static constexpr int SMEM_BYTES = OFF_BAR + (2 * NSLOT + 2) * 8 + 16;
+};
+
+struct Args {
+  const float* rays; int ray_cols; const float* z; int64_t P; int S; int num_tiles;
+  const float* g_raw;                  // [P,4]
+  const uint8_t* wimg; const float* cbuf;
+  eng::ImgDump img_h[8], img_hv;       // forward images (masks)          (read, hi half only)
+  eng::ImgDump out_dz[8], out_dfeat, out_dzv;   // produced for the wgrad kernel
+  float* g_pts;                        // [P,3] d(loss)/d(point)
+  float* g_vd;                         // [P,3] d(loss)/d(viewdir)
+};
+
+// mask 32 values with (h > 0) read from the forward image (hi half), features [c0, c0+32) of sample k
+__device__ __forceinline__ void relu_mask32(const eng::ImgDump& img, int tile, uint32_t k, uint32_t c0,
+                                            float (&f)[32]) {
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    const uint4 h = *reinterpret_cast<const uint4*>(img.chunk(tile, k, c0 + 8 * g, 0));
+    const uint32_t w[4] = {h.x, h.y, h.z, h.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      if ((w[e] & 0x0000ffffu) == 0u) f[8 * g + 2 * e] = 0.f;
+      if ((w[e] & 0xffff0000u) == 0u) f[8 * g + 2 * e + 1] = 0.f;
+    }
+  }
+}
+
+template <int NSPLIT>
+__global__ void __launch_bounds__(320, 1) field_fused_dgrad_kernel(Args a) {
+  using C = Cfg<NSPLIT>;
+  constexpr bool SPLIT = NSPLIT == 3;
+  extern __shared__ __align__(128) uint8_t dsm[];
+  uint8_t* ringp = dsm + C::OFF_RING;
+  float* cst = reinterpret_cast<float*>(dsm + C::OFF_C);
+  float* gx_s = reinterpret_cast<float*>(dsm + C::OFF_GX);
+  float* out_s = reinterpret_cast<float*>(dsm + C::OFF_OUT);
+  uint64_t* full = reinterpret_cast<uint64_t*>(dsm + C::OFF_BAR);
+  uint64_t* empty = full + C::NSLOT;
+  uint64_t* acc_full = empty + C::NSLOT;
+  uint64_t* a_ready = acc_full + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_ready + 1);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) {
+    for (int i = 0; i < C::NSLOT; ++i) { tc::mbar_init(&full[i], 1); tc::mbar_init(&empty[i], 1); }
+    tc::mbar_init(acc_full, 1);
+    tc::mbar_init(a_ready, 256);
+    tc::fence_mbar_init();
+  }
+  for (int i = tid; i < fused::C_TOTAL; i += blockDim.x) cst[i] = a.cbuf[i];
+  __syncthreads();
+  if (warp == 1) tc::tmem_alloc(tmem_slot, 512);
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t T_ACC = tmem, T_AHI = tmem + 256, T_ALO = tmem + 384;
+  eng::Ring ring{ringp, full, empty};
+
+  if (warp == 0) {
+    if (lane == 0)
+      eng::producer_loop<NSPLIT, C::NSLOT, C::SLOT_BYTES>(c_plan_dgrad, a.wimg, ring, a.num_tiles);
+  } else if (warp == 1) {
+    if (lane == 0)
+      eng::mma_loop<NSPLIT, C::NSLOT, C::SLOT_BYTES>(c_plan_dgrad, ring, a_ready, acc_full, T_ACC, T_AHI, T_ALO, 0u,
+                                                     a.num_tiles);
+  } else {
+    const int quad = warp & 3, half = (warp - 2) >> 2;
+    const int row = quad * 32 + lane;
+    const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
+    uint32_t m = 0;
+    for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
+      const int64_t p = (int64_t)tile * TILE_M + row;
+      const bool valid = p < a.P;
+      float4 gr = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (valid) gr = *reinterpret_cast<const float4*>(a.g_raw + p * 4);
+      // ---- E0: rgb head dgrad (fp32), ReLU mask of the view layer -> dZ_v (this warp's 64 columns)
+      {
+        if (half == 0) *reinterpret_cast<float4*>(out_s + row * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int cc = 0; cc < 2; ++cc) {
+          const int c0 = half * 64 + cc * 32;
+          float f[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            f[j] = gr.x * cst[fused::C_WRGB + c0 + j] + gr.y * cst[fused::C_WRGB + 128 + c0 + j] +
+                   gr.z * cst[fused::C_WRGB + 256 + c0 + j];
+          relu_mask32(a.img_hv, tile, row, c0, f);
+          uint32_t hi[16], lo[16];
+          eng::split32<SPLIT>(f, hi, lo);
+          tc::tmem_st16(T_AHI + lane_base + (uint32_t)(c0 >> 1), hi);
+          if (SPLIT) tc::tmem_st16(T_ALO + lane_base + (uint32_t)(c0 >> 1), lo);
+          eng::dump32<SPLIT>(a.out_dzv, tile, row, c0, hi, lo);
+        }
+        tc::tmem_st_wait();
+        tc::tc_fence_before();
+        tc::mbar_arrive(a_ready);
+      }
+#pragma unroll 1
+      for (int s = 0; s < NSTAGE; ++s, ++m) {
+        tc::mbar_wait(acc_full, m & 1);
+        tc::tc_fence_after();
+        if (s == 4 || s == 10) {
+          // ---- 64-wide d(PE) stages: this warp owns 32 columns
+          uint32_t v[32];
+          const int c0 = half * 32;
+          tc::tmem_ld32(T_ACC + lane_base + c0, v);
+          tc::tmem_ld_wait();
+          if (s == 4) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) gx_s[(c0 + j) * TILE_M + row] = __uint_as_float(v[j]);
+            tc::tc_fence_before();
+            tc::mbar_arrive(a_ready);
+          } else {
+            // total d(PE row) = layer-0 share + skip share; contract with dPE/dx (Embedder backward)
+            float x[3] = {0.f, 0.f, 0.f};
+            if (valid) {
+              const float* ry = a.rays + (p / a.S) * a.ray_cols;
+              const float zz = a.z[p];
+#pragma unroll
+              for (int c = 0; c < 3; ++c) x[c] = __fadd_rn(ry[c], __fmul_rn(ry[3 + c], zz));
+            }
+            float gx[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const int i = c0 + j;         // PE column (compile-time after unrolling for each half)
+              const float g = __uint_as_float(v[j]) + gx_s[i * TILE_M + row];
+              if (i < 3) gx[i] += g;
+              else if (i < 63) {
+                const int f = (i - 3) / 6, r = (i - 3) % 6, c = r % 3;
+                const float fr = (float)(1 << f), arg = x[c] * fr;
+                gx[c] += (r < 3) ? fr * cosf(arg) * g : -fr * sinf(arg) * g;
+              }
+            }
+            atomicAdd(out_s + row * 4 + 0, gx[0]);
+            atomicAdd(out_s + row * 4 + 1, gx[1]);
+            atomicAdd(out_s + row * 4 + 2, gx[2]);
+          }
+          continue;
+        }
+        // ---- 256-wide stages: this warp owns 128 columns = 4 chunks
+        // stage -> (mask image, output image)
+        // (by value: taking the address of a kernel parameter would spill the whole struct to local memory)
+        eng::ImgDump mask{}, outd{};
+        switch (s) {
+          case 0: outd = a.out_dfeat; break;                        // g_feat: feature_linear has no ReLU
+          case 1: mask = a.img_h[7]; outd = a.out_dz[7]; break;
+          case 2: mask = a.img_h[6]; outd = a.out_dz[6]; break;
+          case 3: mask = a.img_h[5]; outd = a.out_dz[5]; break;
+          case 5: mask = a.img_h[4]; outd = a.out_dz[4]; break;
+          case 6: mask = a.img_h[3]; outd = a.out_dz[3]; break;
+          case 7: mask = a.img_h[2]; outd = a.out_dz[2]; break;
+          case 8: mask = a.img_h[1]; outd = a.out_dz[1]; break;
+          default: mask = a.img_h[0]; outd = a.out_dz[0]; break;    // s == 9
+        }
+        if (s == 0 && half == 1) {
+          // d(PE(dir)) lives in ACC2: read it before this warp's stores overwrite those TMEM columns
+          uint32_t v[32];
+          tc::tmem_ld32(T_ACC + lane_base + ACC2_COL, v);
+          tc::tmem_ld_wait();
+          float vd[3] = {0.f, 0.f, 0.f}, gv[3] = {0.f, 0.f, 0.f};
+          if (valid) {
+            const float* ry = a.rays + (p / a.S) * a.ray_cols;
+            vd[0] = ry[8]; vd[1] = ry[9]; vd[2] = ry[10];
+          }
+#pragma unroll
+          for (int i = 0; i < 27; ++i) {
+            const float g = __uint_as_float(v[i]);
+            if (i < 3) gv[i] += g;
+            else {
+              const int f = (i - 3) / 6, r = (i - 3) % 6, c = r % 3;
+              const float fr = (float)(1 << f), arg = vd[c] * fr;
+              gv[c] += (r < 3) ? fr * cosf(arg) * g : -fr * sinf(arg) * g;
+            }
+          }
+          if (valid) { a.g_vd[p * 3] = gv[0]; a.g_vd[p * 3 + 1] = gv[1]; a.g_vd[p * 3 + 2] = gv[2]; }
+        }
+#pragma unroll 1
+        for (int cc = 0; cc < 4; cc += 2) {
+          uint32_t v0[32], v1[32];
+          const int c0 = half * 128 + cc * 32, c1 = c0 + 32;
+          tc::tmem_ld32(T_ACC + lane_base + c0, v0);
+          tc::tmem_ld32(T_ACC + lane_base + c1, v1);
+          tc::tmem_ld_wait();
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            const uint32_t (&v)[32] = u ? v1 : v0;
+            const int cu = u ? c1 : c0;
+            float f[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+            if (s == 1) {   // alpha head: g_h7 += g_alpha * w_alpha
+#pragma unroll
+              for (int j = 0; j < 32; ++j) f[j] = fmaf(gr.w, cst[fused::C_WALPHA + cu + j], f[j]);
+            }
+            if (mask.base) relu_mask32(mask, tile, row, cu, f);
+            uint32_t hi[16], lo[16];
+            eng::split32<SPLIT>(f, hi, lo);
+            tc::tmem_st16(T_AHI + lane_base + (uint32_t)(cu >> 1), hi);
+            if (SPLIT) tc::tmem_st16(T_ALO + lane_base + (uint32_t)(cu >> 1), lo);
+            eng::dump32<SPLIT>(outd, tile, row, cu, hi, lo);
+          }
+        }
+        tc::tmem_st_wait();
+        tc::tc_fence_before();
+        tc::mbar_arrive(a_ready);
+      }
+      tc::tc_fence_before();
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (half == 0 && valid) {
+        a.g_pts[p * 3] = out_s[row * 4]; a.g_pts[p * 3 + 1] = out_s[row * 4 + 1]; a.g_pts[p * 3 + 2] = out_s[row * 4 + 2];
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+    }
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tc::tmem_dealloc(tmem, 512);
+}
+
+// d_rays[r, 0:3] += sum_s g_pts ; d_rays[r, 3:6] += sum_s z*g_pts ; d_rays[r, 8:11] += sum_s g_vd
+__global__ void __launch_bounds__(128) reduce_pts_grad_kernel(const float* __restrict__ g_pts,
+                                                              const float* __restrict__ g_vd,
+                                                              const float* __restrict__ z, int64_t N, int S,
+                                                              int ray_cols, float* __restrict__ d_rays) {
+  const int lane = threadIdx.x & 31;
+  const int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (r >= N) return;
+  float acc[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  for (int s = lane; s < S; s += 32) {
+    const int64_t p = r * S + s;
+    const float zz = z[p];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float g = g_pts[p * 3 + c];
+      acc[c] += g; acc[3 + c] += zz * g; acc[6 + c] += g_vd[p * 3 + c];
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 9; ++k) acc[k] = warp_sum(acc[k]);
+  if (lane == 0) {
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+      const int col = k < 6 ? k : 8 + (k - 6);
+      if (col < ray_cols) d_rays[r * ray_cols + col] += acc[k];
+    }
+  }
+}
+
+}  // namespace dgrad
+}  // namespace scnerf

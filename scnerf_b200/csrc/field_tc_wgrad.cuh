@@ -1,0 +1,293 @@
+// Weight-gradient pass on tcgen05 (sm_100a):  dW_l[out,in] = sum_samples dZ_l[s,out] * X_l[s,in].
+//
+// Both operands are the bf16 (hi[,lo]) TILE IMAGES written by the fused forward (layer inputs) and the
+// fused dgrad (dZ): [tile][k16 slab][half][F*32 B], each slab in the UMMA canonical MN-major
+// no-swizzle layout, so one 1-D bulk TMA copy per image per K=16 step feeds the MMAs directly
+// (A = dZ^T: M = out features, K = samples; B = X^T: N = in features).  A CTA owns ONE job (a layer's
+// accumulator, both 128-row halves = 512 TMEM columns) over a contiguous slice of tiles, accumulates
+// across the whole slice in TMEM, then adds its partial dW into the fp32 gradient with atomics.
+// Helper warps reduce the bias gradients (column sums of dZ) — and d(alpha_linear.weight) — from the
+// very same shared-memory slabs while the tensor pipe works.
+//
+// HBM-bound by construction: per tile and job 2 images x 64 KB x NH in, 48 x NSPLIT/3 MMAs out;
+// algorithmic bytes per sample: sum over layers of (F_dZ + F_X) * 2 B * NH.
+#pragma once
+#include "common.cuh"
+#include "tc_prims.cuh"
+#include "tc_engine.cuh"
+
+namespace scnerf {
+namespace wgrad {
+
+constexpr int MAX_UNITS = 4;
+constexpr int NJOBS = 10;
+
+struct Unit {
+  int a_img, a_half;      // which A image of the job, which 128-feature half (M block)
+  int b_img;              // which B image of the job
+  int n;                  // GEMM N (multiple of 16)
+  int acc_col;            // TMEM column of this unit's accumulator
+  float* out;             // dW + row0*ld + col0
+  int ld, rows_valid, cols_valid;
+};
+struct Job {
+  eng::ImgDump a[2]; int na;
+  eng::ImgDump b[2]; int nb;
+  Unit u[MAX_UNITS]; int nu;
+  float* db;              // bias gradient of a[0] (F = a[0].F) or NULL
+  const float* g_raw;     // J8 only: d(raw)[P,4] for d(alpha_linear.weight)
+  float* dw_alpha;        //          [256]
+};
+struct Args {
+  Job job[NJOBS];
+  int num_tiles, nslices;
+  int64_t P;
+};
+
+template <int NSPLIT> struct Cfg {
+  static constexpr int NH = NSPLIT == 3 ? 2 : 1;
+  static constexpr int SLOT_BYTES = 36864 / (NSPLIT == 3 ? 1 : 2);   // worst job: 2 x 256 + 64 features
+  static constexpr int NSLOT = NSPLIT == 3 ? 5 : 10;
+  static constexpr int OFF_BAR = NSLOT * SLOT_BYTES;
+  static constexpr int SMEM_BYTES = OFF_BAR + (2 * NSLOT + 1) * 8 + 16;
+};
+
+// instruction descriptor: bf16 x bf16 -> f32, A and B both MN-major
+__host__ __device__ constexpr uint32_t idesc_mn(uint32_t M, uint32_t N) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((N >> 3) << 17) | ((M >> 4) << 24);
+}
+
+// sum of the 8 bf16 features of a 16-byte chunk (hi [+ lo]) into acc[8], optionally scaled
+__device__ __forceinline__ void add_chunk(const uint4& c, float s, float (&acc)[8]) {
+  const uint32_t w[4] = {c.x, c.y, c.z, c.w};
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    acc[2 * e] = fmaf(s, eng::bf16lo_f(w[e]), acc[2 * e]);
+    acc[2 * e + 1] = fmaf(s, eng::bf16hi_f(w[e]), acc[2 * e + 1]);
+  }
+}
+
+template <int NSPLIT>
+__global__ void __launch_bounds__(192, 1) field_wgrad_kernel(const __grid_constant__ Args a_) {
+  const Args* ap = &a_;
+  using C = Cfg<NSPLIT>;
+  constexpr int NH = C::NH;
+  constexpr bool SPLIT = NSPLIT == 3;
+  extern __shared__ __align__(128) uint8_t wsm[];
+  uint64_t* full = reinterpret_cast<uint64_t*>(wsm + C::OFF_BAR);
+  uint64_t* empty = full + C::NSLOT;
+  uint64_t* acc_done = empty + C::NSLOT;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_done + 1);
+  __shared__ Job job;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int jid = blockIdx.x % NJOBS, slice = blockIdx.x / NJOBS;
+  if (tid == 0) job = ap->job[jid];
+  if (tid == 32) {
+    for (int i = 0; i < C::NSLOT; ++i) { tc::mbar_init(&full[i], 1); tc::mbar_init(&empty[i], 5); }
+    tc::mbar_init(acc_done, 1);
+    tc::fence_mbar_init();
+  }
+  __syncthreads();
+  if (warp == 1) tc::tmem_alloc(tmem_slot, 512);
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const int nslices = ap->nslices;
+  const int per = (ap->num_tiles + nslices - 1) / nslices;
+  const int t0 = min(slice * per, ap->num_tiles), t1 = min(t0 + per, ap->num_tiles);
+  // byte offsets of each image's slab inside a slot
+  uint32_t offA[2], offB[2], bytesA[2], bytesB[2], slot_bytes = 0;
+  for (int i = 0; i < job.na; ++i) { offA[i] = slot_bytes; bytesA[i] = job.a[i].F * 32u * NH; slot_bytes += bytesA[i]; }
+  for (int i = 0; i < job.nb; ++i) { offB[i] = slot_bytes; bytesB[i] = job.b[i].F * 32u * NH; slot_bytes += bytesB[i]; }
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t n = 0;
+      for (int tile = t0; tile < t1; ++tile)
+#pragma unroll 1
+        for (int ks = 0; ks < 8; ++ks, ++n) {
+          const uint32_t idx = n % C::NSLOT, ph = (n / C::NSLOT) & 1;
+          tc::mbar_wait(&empty[idx], ph ^ 1);
+          tc::mbar_arrive_expect_tx(&full[idx], slot_bytes);
+          uint8_t* dst = wsm + idx * C::SLOT_BYTES;
+          for (int i = 0; i < job.na; ++i)
+            tc::bulk_g2s(dst + offA[i], job.a[i].base + (size_t)tile * job.a[i].tile_bytes() + (size_t)ks * bytesA[i],
+                         bytesA[i], &full[idx]);
+          for (int i = 0; i < job.nb; ++i)
+            tc::bulk_g2s(dst + offB[i], job.b[i].base + (size_t)tile * job.b[i].tile_bytes() + (size_t)ks * bytesB[i],
+                         bytesB[i], &full[idx]);
+        }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      uint32_t n = 0;
+      const uint32_t base = tc::smem_u32(wsm);
+      for (int tile = t0; tile < t1; ++tile)
+#pragma unroll 1
+        for (int ks = 0; ks < 8; ++ks, ++n) {
+          const uint32_t idx = n % C::NSLOT, ph = (n / C::NSLOT) & 1;
+          tc::mbar_wait(&full[idx], ph);
+          tc::tc_fence_after();
+          const uint32_t slot = base + idx * C::SLOT_BYTES;
+          for (int ui = 0; ui < job.nu; ++ui) {
+            const Unit& u = job.u[ui];
+            const uint32_t a_hi = slot + offA[u.a_img] + (uint32_t)u.a_half * 4096u;   // 16 mn-groups x 256 B
+            const uint32_t a_lo = a_hi + job.a[u.a_img].F * 32u;
+            const uint32_t b_hi = slot + offB[u.b_img];
+            const uint32_t b_lo = b_hi + job.b[u.b_img].F * 32u;
+            const uint32_t idesc = idesc_mn(128, (uint32_t)u.n);
+            const uint32_t acc = tmem + (uint32_t)u.acc_col;
+            const uint64_t dah = tc::smem_desc(a_hi, 128, 256), dbh = tc::smem_desc(b_hi, 128, 256);
+            tc::mma_ss(acc, dah, dbh, idesc, n > 0);
+            if (SPLIT) {
+              tc::mma_ss(acc, tc::smem_desc(a_lo, 128, 256), dbh, idesc, 1);
+              tc::mma_ss(acc, dah, tc::smem_desc(b_lo, 128, 256), idesc, 1);
+            }
+          }
+          tc::tc_commit(&empty[idx]);
+        }
+      tc::tc_commit(acc_done);
+    }
+  } else {
+    // ===================== helper warps 2..5: bias / alpha-weight gradients, then the dW epilogue ===
+    const int ht = tid - 64;                 // 0..127
+    const int FA = (int)job.a[0].F;          // 256 or 128 features
+    const int g = ht >> 2, q = ht & 3;       // mn-group, sample sub-slice (4 samples)
+    const bool do_bias = job.db != nullptr && g * 8 < FA;
+    const bool do_alpha = job.dw_alpha != nullptr;
+    float accb[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, acca[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    uint32_t n = 0;
+    for (int tile = t0; tile < t1; ++tile)
+#pragma unroll 1
+      for (int ks = 0; ks < 8; ++ks, ++n) {
+        const uint32_t idx = n % C::NSLOT, ph = (n / C::NSLOT) & 1;
+        tc::mbar_wait(&full[idx], ph);
+        const uint8_t* slot = wsm + idx * C::SLOT_BYTES;
+        if (do_bias || do_alpha) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int kk = q * 4 + i;        // sample within the slab (0..15)
+            const uint32_t coff = (uint32_t)g * 256u + (uint32_t)(kk >> 3) * 128u + (uint32_t)(kk & 7) * 16u;
+            if (do_bias) {
+              add_chunk(*reinterpret_cast<const uint4*>(slot + offA[0] + coff), 1.f, accb);
+              if (SPLIT) add_chunk(*reinterpret_cast<const uint4*>(slot + offA[0] + (uint32_t)FA * 32u + coff), 1.f, accb);
+            }
+            if (do_alpha) {
+              const int64_t p = (int64_t)tile * 128 + ks * 16 + kk;
+              const float ga = p < ap->P ? job.g_raw[p * 4 + 3] : 0.f;
+              add_chunk(*reinterpret_cast<const uint4*>(slot + offB[0] + coff), ga, acca);
+              if (SPLIT) add_chunk(*reinterpret_cast<const uint4*>(slot + offB[0] + job.b[0].F * 32u + coff), ga, acca);
+            }
+          }
+        }
+        __syncwarp();
+        if (lane == 0) tc::mbar_arrive(&empty[idx]);
+      }
+    // reduce the 4 sample sub-slices of each mn-group (lanes 4g..4g+3) and publish
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      accb[e] += __shfl_xor_sync(0xffffffffu, accb[e], 1); accb[e] += __shfl_xor_sync(0xffffffffu, accb[e], 2);
+      acca[e] += __shfl_xor_sync(0xffffffffu, acca[e], 1); acca[e] += __shfl_xor_sync(0xffffffffu, acca[e], 2);
+    }
+    if (q == 0 && t1 > t0) {
+      if (do_bias)
+#pragma unroll
+        for (int e = 0; e < 8; ++e) atomicAdd(job.db + g * 8 + e, accb[e]);
+      if (do_alpha)
+#pragma unroll
+        for (int e = 0; e < 8; ++e) atomicAdd(job.dw_alpha + g * 8 + e, acca[e]);
+    }
+    // ---- dW epilogue: TMEM -> atomicAdd into the fp32 gradient -------------------------------------
+    tc::mbar_wait(acc_done, 0);
+    tc::tc_fence_after();
+    if (t1 > t0) {
+      const int quad = warp & 3;
+      const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
+      const int r = quad * 32 + lane;
+      for (int ui = 0; ui < job.nu; ++ui) {
+        const Unit& u = job.u[ui];
+        for (int c0 = 0; c0 < u.n; c0 += 32) {
+          uint32_t v[32];
+          if (u.n - c0 >= 32) tc::tmem_ld32(tmem + lane_base + (uint32_t)(u.acc_col + c0), v);
+          else {
+            uint32_t w[16];
+            asm volatile(
+                "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7]),
+                  "=r"(w[8]), "=r"(w[9]), "=r"(w[10]), "=r"(w[11]), "=r"(w[12]), "=r"(w[13]), "=r"(w[14]), "=r"(w[15])
+                : "r"(tmem + lane_base + (uint32_t)(u.acc_col + c0)) : "memory");
+#pragma unroll
+            for (int j = 0; j < 16; ++j) { v[j] = w[j]; v[16 + j] = 0u; }
+          }
+          tc::tmem_ld_wait();
+          if (r < u.rows_valid) {
+            float* orow = u.out + (int64_t)r * u.ld + c0;
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (c0 + j < u.cols_valid) atomicAdd(orow + j, __uint_as_float(v[j]));
+          }
+        }
+      }
+    }
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tc::tmem_dealloc(tmem, 512);
+}
+
+// d(rgb_linear.weight)[3,128], d(rgb_linear.bias)[3], d(alpha_linear.bias)[1] from d(raw) and the HV image
+template <int NH>
+__global__ void __launch_bounds__(128) head_wgrad_img_kernel(eng::ImgDump hv, const float* __restrict__ g_raw,
+                                                             int64_t P, int num_tiles, float* __restrict__ dw_rgb,
+                                                             float* __restrict__ db_rgb, float* __restrict__ db_alpha) {
+  const int t = threadIdx.x, g = t >> 3, q = t & 7;     // 16 mn-groups x 8 sample sub-slices (2 samples)
+  float acc[3][8];
+#pragma unroll
+  for (int c = 0; c < 3; ++c)
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[c][e] = 0.f;
+  float sb[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    for (int ks = 0; ks < 8; ++ks)
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const int kk = ks * 16 + q * 2 + i;
+        const int64_t p = (int64_t)tile * 128 + kk;
+        if (p >= P) continue;
+        const float4 gr = *reinterpret_cast<const float4*>(g_raw + p * 4);
+        float h[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        add_chunk(*reinterpret_cast<const uint4*>(hv.chunk(tile, kk, g * 8, 0)), 1.f, h);
+        if (NH == 2) add_chunk(*reinterpret_cast<const uint4*>(hv.chunk(tile, kk, g * 8, 1)), 1.f, h);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          acc[0][e] = fmaf(gr.x, h[e], acc[0][e]);
+          acc[1][e] = fmaf(gr.y, h[e], acc[1][e]);
+          acc[2][e] = fmaf(gr.z, h[e], acc[2][e]);
+        }
+        if (g == 0) { sb[0] += gr.x; sb[1] += gr.y; sb[2] += gr.z; sb[3] += gr.w; }
+      }
+  }
+#pragma unroll
+  for (int c = 0; c < 3; ++c)
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      float v = acc[c][e];
+      v += __shfl_xor_sync(0xffffffffu, v, 1); v += __shfl_xor_sync(0xffffffffu, v, 2);
+      v += __shfl_xor_sync(0xffffffffu, v, 4);
+      if (q == 0) atomicAdd(dw_rgb + c * 128 + g * 8 + e, v);
+    }
+  if (g == 0) {
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      float v = sb[c];
+      v += __shfl_xor_sync(0x000000ffu, v, 1); v += __shfl_xor_sync(0x000000ffu, v, 2);
+      v += __shfl_xor_sync(0x000000ffu, v, 4);
+      if (q == 0) atomicAdd(c < 3 ? db_rgb + c : db_alpha, v);
+    }
+  }
+}
+
+}  // namespace wgrad
+}  // namespace scnerf

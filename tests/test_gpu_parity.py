@@ -191,7 +191,13 @@ def test_sample_pdf_golden(lib, golden):
             assert abs(u[r, c] - cdf_ref[r, k].item()) <= 4e-6, (tag, r, c)
         big = np.argwhere(np.abs(s - g[f"{tag}_samples"]) > 1e-5)
         flipset = {(int(r), int(c)) for r, c in flips}
-        assert all((int(r), int(c)) in flipset for r, c in big), f"{tag}: unexplained sample mismatch"
+        ref_i = g[f"{tag}_inds"]
+        for r, c in big:      # explained by a knot flip or by the denom<1e-5 branch sitting on its threshold
+            if (int(r), int(c)) in flipset:
+                continue
+            lo_, hi_ = max(ref_i[r, c] - 1, 0), min(ref_i[r, c], 62)
+            den = float(cdf_ref[r, hi_] - cdf_ref[r, lo_])
+            assert abs(den - 1e-5) <= 4e-6, f"{tag}: unexplained sample mismatch at {(r, c)} (denom {den:.3e})"
         print(f"sample_pdf {tag}: {len(flips)} knot flips, {len(big)} samples off by >1e-5 (of {64 * 128})")
         assert len(flips) <= 0.01 * 64 * 128
 
@@ -236,8 +242,33 @@ def test_render_c1_golden(lib, golden):
         assert set(ex) == {"raw"}
 
 
+def _rays_within(a, b, tol):
+    a = a.detach().cpu().numpy() if isinstance(a, torch.Tensor) else np.asarray(a)
+    d = np.abs(a.reshape(a.shape[0], -1) - np.asarray(b).reshape(a.shape[0], -1)).max(1)
+    return d <= tol * max(np.abs(b).max(), 1.0)
+
+
+def _oracle_c2mini(seed, kps, idx, perturb, std, wb, sequential_cdf):
+    from oracle import scnerf_oracle as O
+    N = kps.shape[0]
+    cam = O.Camera(synth.intrinsic_init(), synth.camera_poses(seed), synth.camera_args(), H, W)
+    cam.load(synth.camera_noise_state(seed))
+    Pc, Pf = O.state_to_tensors(synth.mlp_state(seed)), O.state_to_tensors(synth.mlp_state(seed + 1))
+    rnd = pytest_rand(N, 64, 128, perturb, std)
+    with torch.no_grad():
+        o, d = O.rays_pixels_camera(H, W, cam, T(kps), idx=T(idx))
+        K = cam.intrinsic()
+        rays = O.pack_rays(H, W, o, d, 0., 1., True, True, K[0, 0], K[1, 1])
+        return O.clamp_rgb_(O.render_rays(rays, Pc, Pf, 64, 128, white_bkgd=wb, retraw=True,
+                                          sequential_cdf=sequential_cdf, **rnd))
+
+
 def test_render_c2mini_golden(lib, golden):
-    """BASELINE.json configs[1] shape (64c + 128f, learnable camera, NDC) at 64 rays."""
+    """BASELINE.json configs[1] shape (64c + 128f, learnable camera, NDC) at 64 rays.
+    Two references: (a) the oracle with the kernel's CDF summation order — every ray within 1e-4;
+    (b) the reference's CPU golden — at most 2 of 64 rays may differ (a random u landing within
+    ~2e-6 of a CDF knot beside a `denom < 1e-5` bin moves one fine sample by a whole bin in the
+    reference itself; see test_sample_pdf_golden)."""
     from scnerf_b200.get_rays import get_rays_kps_use_camera
     g = golden("render_c2mini")
     mods = build_modules(6, DEV)
@@ -250,10 +281,16 @@ def test_render_c2mini_golden(lib, golden):
         # colours / opacities: absolute 1e-4 (scale 1).  With perturb=0 and no sigma noise this
         # scene is almost empty (max rgb ~3e-4): 1-exp(-x) at x~1e-6 is round-off dominated in the
         # reference itself, so relative-to-own-max would compare noise.
-        close(rgb, g[f"{tag}_rgb"], 1e-4, f"{tag} rgb", 1.0); close(acc, g[f"{tag}_acc"], 1e-4, f"{tag} acc", 1.0)
+        oseq = _oracle_c2mini(6, kps, idx, perturb, std, wb, True)
+        close(rgb, oseq["rgb_map"].numpy(), 1e-4, f"{tag} rgb vs sequential-CDF oracle", 1.0)
+        close(acc, oseq["acc_map"].numpy(), 1e-4, f"{tag} acc vs sequential-CDF oracle", 1.0)
+        close(ex["z_std"], oseq["z_std"].numpy(), 1e-4, f"{tag} z_std vs sequential-CDF oracle", 1.0)
+        ok = _rays_within(rgb, g[f"{tag}_rgb"], 1e-4) & _rays_within(acc, g[f"{tag}_acc"], 1e-4)
+        print(f"c2mini {tag}: {int((~ok).sum())} of 64 rays differ from the CPU golden by > 1e-4")
+        assert (~ok).sum() <= 2
         close(ex["rgb0"], g[f"{tag}_rgb0"], 1e-4, f"{tag} rgb0", 1.0)
         close(ex["acc0"], g[f"{tag}_acc0"], 1e-4, f"{tag} acc0", 1.0)
-        if tag != "det":
+        if tag != "det" and ok.all():
             # det draws u = linspace(0,1) whose end point u == 1.0 sits exactly on the last CDF knot:
             # which side it falls is summation-order dependent in the reference (see
             # test_sample_pdf_golden), moving one fine sample by up to a bin; skip the quantities
@@ -397,5 +434,55 @@ def test_render_c2mini_golden_bf16x3(lib, golden):
         o, d = get_rays_kps_use_camera(H, W, mods["cam"], T(kps).to(DEV), idx_in_camera_param=T(idx).to(DEV))
     for perturb, std, wb, tag in ((0., 0., False, "det"), (1., 1., False, "rand")):
         rgb, disp, acc, ex = _render_golden(mods, o, d, mods["cam"], None, 64, 128, perturb, std, wb, "bf16x3")
-        close(rgb, g[f"{tag}_rgb"], 1e-4, f"{tag} rgb", 1.0); close(acc, g[f"{tag}_acc"], 1e-4, f"{tag} acc", 1.0)
+        oseq = _oracle_c2mini(6, kps, idx, perturb, std, wb, True)
+        close(rgb, oseq["rgb_map"].numpy(), 1e-4, f"{tag} rgb vs sequential-CDF oracle", 1.0)
+        close(acc, oseq["acc_map"].numpy(), 1e-4, f"{tag} acc vs sequential-CDF oracle", 1.0)
+        ok = _rays_within(rgb, g[f"{tag}_rgb"], 1e-4)
+        assert (~ok).sum() <= 2
         close(ex["rgb0"], g[f"{tag}_rgb0"], 1e-4, f"{tag} rgb0", 1.0)
+
+
+def test_train_step_gradients_bf16x3(lib):
+    """Whole step with the tensor-core forward AND backward (fused dgrad + wgrad kernels, split-bf16):
+    same noise-floor criterion as the fp32 path (error vs fp64 oracle <= 3x the fp32 oracle's own
+    error, floor 1e-3)."""
+    N = 96
+    mods = build_modules(8, DEV)
+    kps, idx, target = synth.pixel_batch(8, N)
+    loss, rgb, grads = cuda_step(mods, kps, idx, target, 64, 128, precision="bf16x3")
+    l32, rgb32, g32 = oracle_step(8, kps, idx, target, 64, 128, torch.float32)
+    l64, _, g64 = oracle_step(8, kps, idx, target, 64, 128, torch.float64)
+    assert abs(loss - l32) <= 1e-4 * abs(l32)
+    close(rgb, rgb32, 1e-4, "rgb", 1.0)
+    worst = 0.0
+    for k in sorted(g64):
+        floor = rel(g32[k], g64[k])
+        mine = rel(grads[k], g64[k])
+        worst = max(worst, mine / max(floor, 1e-12))
+        print(f"  {k:40s} cuda-vs-f64 {mine:.2e}   fp32-oracle-vs-f64 {floor:.2e}")
+        assert mine <= max(3.0 * floor, 1e-3), f"{k}: cuda-vs-f64 {mine:.2e}, fp32 oracle floor {floor:.2e}"
+    print(f"train_step bf16x3: worst (cuda err)/(fp32 oracle err) ratio = {worst:.2f}")
+
+
+@pytest.mark.parametrize("precision,tol", [("bf16x3", 2e-3), ("bf16", 8e-2)])
+def test_engine_full_size_tc_backward(lib, precision, tol):
+    """configs[1] at full size through scnerf_train_step with the tensor-core backward: gradients
+    agree with the fp32 CUDA-core path (same deterministic sampling: perturb=0, no sigma noise)."""
+    from scnerf_b200.engine import TrainStep
+    N = 4096
+    mods = build_modules(41, DEV)
+    kps, idx, target = (T(x).to(DEV) for x in synth.pixel_batch(41, N))
+    ref = TrainStep(mods["cam"], mods["coarse"], mods["fine"], N, 64, 128, perturb=0., raw_noise_std=0., precision="fp32")
+    l_ref = float(ref.step_device(kps, idx, target))
+    g_ref = {k: v.clone() for k, v in ref.grads.views.items()}
+    del ref
+    eng = TrainStep(mods["cam"], mods["coarse"], mods["fine"], N, 64, 128, perturb=0., raw_noise_std=0., precision=precision)
+    l_tc = float(eng.step_device(kps, idx, target))
+    torch.cuda.synchronize()
+    assert abs(l_tc - l_ref) <= max(tol, 1e-4) * abs(l_ref)
+    worst = 0.0
+    for k, v in eng.grads.views.items():
+        e = rel(v.cpu().numpy(), g_ref[k].cpu().numpy())
+        worst = max(worst, e)
+        assert e <= tol * 5, f"{k}: {e:.3e}"
+    print(f"engine {precision}: loss {l_tc:.6f} vs {l_ref:.6f}; worst grad rel-to-max err {worst:.2e}")
