@@ -172,11 +172,11 @@ inline int fwd_plan_init() {
   int dev = 0;
   SCNERF_CUDA(cudaGetDevice(&dev));
   if (dev < 64 && done[dev]) return 0;
-  static eng::Plan P;
+  static eng::Plan P = fused::make_fwd_plan();
   static fused::PlanSrc S;
-  fused::build_fwd_plan(P, S);
+  fused::build_fwd_plansrc(S);
   if (fused::plan_image_bytes(P, 3) > TC_IMG_BYTES) return fail(SCNERF_ERR_WORKSPACE, "TC_IMG_BYTES too small");
-  SCNERF_CUDA(cudaMemcpyToSymbol(fused::c_plan_fwd, &P, sizeof(P)));
+  SCNERF_CUDA(cudaMemcpyToSymbol(fused::d_plan_fwd, &P, sizeof(P)));
   SCNERF_CUDA(cudaMemcpyToSymbol(fused::d_plansrc_fwd, &S, sizeof(S)));
   SCNERF_CUDA(cudaFuncSetAttribute(fused::field_fused_fwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    fused::Cfg<1>::SMEM_BYTES));
@@ -186,10 +186,7 @@ inline int fwd_plan_init() {
   return 0;
 }
 inline const eng::Plan& fwd_plan_host() {
-  static eng::Plan P;
-  static fused::PlanSrc S;
-  static bool built = false;
-  if (!built) { fused::build_fwd_plan(P, S); built = true; }
+  static eng::Plan P = fused::make_fwd_plan();
   return P;
 }
 
@@ -287,11 +284,11 @@ inline int bwd_plan_init() {
   int dev = 0;
   SCNERF_CUDA(cudaGetDevice(&dev));
   if (dev < 64 && done[dev]) return 0;
-  static eng::Plan P;
+  static eng::Plan P = dgrad::make_plan();
   static fused::PlanSrc S;
-  dgrad::build_plan(P, S);
+  dgrad::build_plansrc(S);
   if (fused::plan_image_bytes(P, 3) > TC_IMG_BYTES) return fail(SCNERF_ERR_WORKSPACE, "TC_IMG_BYTES too small (dgrad)");
-  SCNERF_CUDA(cudaMemcpyToSymbol(dgrad::c_plan_dgrad, &P, sizeof(P)));
+  SCNERF_CUDA(cudaMemcpyToSymbol(dgrad::d_plan_dgrad, &P, sizeof(P)));
   SCNERF_CUDA(cudaMemcpyToSymbol(dgrad::d_plansrc_dgrad, &S, sizeof(S)));
   SCNERF_CUDA(cudaFuncSetAttribute(dgrad::field_fused_dgrad_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    dgrad::Cfg<1>::SMEM_BYTES));
@@ -306,7 +303,7 @@ inline int bwd_plan_init() {
 }
 inline int dgrad_n_slabs() {
   static int n = -1;
-  if (n < 0) { static eng::Plan P; static fused::PlanSrc S; dgrad::build_plan(P, S); n = P.n_slabs; }
+  if (n < 0) { static eng::Plan P = dgrad::make_plan(); n = P.n_slabs; }
   return n;
 }
 

@@ -23,54 +23,75 @@ using fused::SrcDef;
 constexpr int NSTAGE = 11;   // S1, S2, S3, S4, S5a, S5b, S6, S7, S8, S9, S10
 constexpr int ACC2_COL = 320;
 
-inline void build_plan(eng::Plan& P, PlanSrc& S) {
+// one k16 slab of a transposed-weight GEMM stage
+struct SlabSpec { int N, acc_col, j, first, last, stage_begin, wsel, col0, valid_n, stage; };
+// enumerate the slab sequence (shared by the constexpr plan and the host-side pack table)
+template <class F>
+__host__ __device__ constexpr void for_each_slab(F&& f) {
+  // S1 (stage 0): [g_feat | g_V] = dZ_v (K=128) * W_views
+  for (int j = 0; j < 8; ++j) {
+    f(SlabSpec{256, 0, j, j == 0, 0, j == 0, 9, 0, 256, 0});
+    f(SlabSpec{32, ACC2_COL, j, j == 0, j == 7, 0, 9, 256, 27, 0});
+  }
+  // wsel, N, col0, valid_n for stages 1..10
+  const int spec[10][4] = {{8, 256, 0, 256},   // S2 : g_h7 = g_feat * W_feature
+                           {7, 256, 0, 256},   // S3 : g_h6 = dZ7 * W7
+                           {6, 256, 0, 256},   // S4 : g_h5 = dZ6 * W6
+                           {5, 64, 0, 63},     // S5a: g_X (skip branch) = dZ5 * W5[:, :63]
+                           {5, 256, 63, 256},  // S5b: g_h4 = dZ5 * W5[:, 63:]
+                           {4, 256, 0, 256},   // S6 : g_h3
+                           {3, 256, 0, 256},   // S7 : g_h2
+                           {2, 256, 0, 256},   // S8 : g_h1
+                           {1, 256, 0, 256},   // S9 : g_h0
+                           {0, 64, 0, 63}};    // S10: g_X (layer 0) = dZ0 * W0
+  for (int t = 0; t < 10; ++t)
+    for (int j = 0; j < 16; ++j)
+      f(SlabSpec{spec[t][1], 0, j, j == 0, j == 15, j == 0, spec[t][0], spec[t][2], spec[t][3], t + 1});
+}
+struct PlanFiller {
+  eng::Plan P{};
   int n = 0;
   uint32_t off = 0;
-  auto add = [&](int N, int acc_col, int j, int K16, bool first, bool last, int wsel, int col0, int valid_n) {
-    eng::SlabDef& e = P.slab[n];
-    SrcDef& q = S.s[n];
-    e = eng::SlabDef{};
-    q = SrcDef{};
-    e.n = (uint16_t)N; e.acc_col = (uint16_t)acc_col; e.a_kind = eng::A_TMEM; e.a_off = (uint16_t)(j * 8);
-    e.flags = (first ? eng::F_ZERO_ACC : 0) | (last ? eng::F_STAGE_END : 0);
-    q.wsel = (uint8_t)wsel; q.kind = 1; q.row0 = (uint16_t)(16 * j); q.col0 = (uint16_t)col0;
-    q.valid_k = 16; q.valid_n = (uint16_t)valid_n; q.img_off = off;
-    off += (uint32_t)N * 32u;
-    ++n;
-    (void)K16;
-  };
-  // S1: [g_feat | g_V] = dZ_v (K=128) * W_views
-  for (int j = 0; j < 8; ++j) {
-    add(256, 0, j, 8, j == 0, false, 9, 0, 256);
-    add(32, ACC2_COL, j, 8, j == 0, j == 7, 9, 256, 27);
+  __host__ __device__ constexpr void operator()(const SlabSpec& q) {
+    eng::SlabDef e{};
+    e.n = (uint16_t)q.N; e.acc_col = (uint16_t)q.acc_col; e.a_kind = eng::A_TMEM; e.a_off = (uint16_t)(q.j * 8);
+    e.stage = (uint8_t)q.stage; e.img_off = off;
+    e.flags = (uint8_t)((q.first ? eng::F_ZERO_ACC : 0) | (q.last ? eng::F_STAGE_END : 0) |
+                        (q.stage_begin ? eng::F_STAGE_BEGIN : 0));
+    P.slab[n++] = e;
+    off += (uint32_t)q.N * 32u;
   }
-  auto full = [&](int wsel, int N, int col0, int valid_n) {
-    for (int j = 0; j < 16; ++j) add(N, 0, j, 16, j == 0, j == 15, wsel, col0, valid_n);
-  };
-  full(8, 256, 0, 256);      // S2 : g_h7 = g_feat * W_feature
-  full(7, 256, 0, 256);      // S3 : g_h6 = dZ7 * W7
-  full(6, 256, 0, 256);      // S4 : g_h5 = dZ6 * W6
-  full(5, 64, 0, 63);        // S5a: g_X (skip branch) = dZ5 * W5[:, :63]
-  full(5, 256, 63, 256);     // S5b: g_h4 = dZ5 * W5[:, 63:]
-  full(4, 256, 0, 256);      // S6 : g_h3
-  full(3, 256, 0, 256);      // S7 : g_h2
-  full(2, 256, 0, 256);      // S8 : g_h1
-  full(1, 256, 0, 256);      // S9 : g_h0
-  full(0, 64, 0, 63);        // S10: g_X (layer 0) = dZ0 * W0
-  P.n_slabs = n; P.n_stages = NSTAGE;
+};
+__host__ __device__ constexpr eng::Plan make_plan() {
+  PlanFiller f{};
+  for_each_slab(f);
+  f.P.n_slabs = f.n; f.P.n_stages = NSTAGE;
+  return f.P;
+}
+inline void build_plansrc(PlanSrc& S) {
+  int n = 0;
+  for_each_slab([&](const SlabSpec& q) {
+    SrcDef d{};
+    d.wsel = (uint8_t)q.wsel; d.kind = 1; d.row0 = (uint16_t)(16 * q.j); d.col0 = (uint16_t)q.col0;
+    d.valid_k = 16; d.valid_n = (uint16_t)q.valid_n;
+    S.s[n++] = d;
+  });
 }
 
-__constant__ eng::Plan c_plan_dgrad;
+__device__ eng::Plan d_plan_dgrad;
 __device__ PlanSrc d_plansrc_dgrad;
 template <int NSPLIT>
 __global__ void __launch_bounds__(256) pack_dgrad_kernel(fused::PackSrc src, uint8_t* __restrict__ img) {
   const int i = blockIdx.y;
-  if (i < c_plan_dgrad.n_slabs) fused::pack_slab_impl<NSPLIT>(c_plan_dgrad.slab[i], d_plansrc_dgrad.s[i], src, img);
+  if (i < d_plan_dgrad.n_slabs) fused::pack_slab_impl<NSPLIT>(d_plan_dgrad.slab[i], d_plansrc_dgrad.s[i], src, img);
 }
 
-template <int NSPLIT> struct Cfg {
-  static constexpr int NSLOT = NSPLIT == 1 ? 16 : 9;
-  static constexpr int SLOT_BYTES = NSPLIT == 1 ? 8192 : 16384;
+template <int NSPLIT_> struct Cfg {
+  static constexpr int NSPLIT = NSPLIT_;
+  static constexpr eng::Plan PLAN = make_plan();
+  static constexpr int NSLOT = NSPLIT_ == 1 ? 22 : 11;        // 176 slabs per tile
+  static constexpr int SLOT_BYTES = NSPLIT_ == 1 ? 8192 : 16384;
+  static_assert(PLAN.n_slabs % NSLOT == 0, "ring size must divide the slab count");
   static constexpr int OFF_RING = 0;
   static constexpr int OFF_C = NSLOT * SLOT_BYTES;
   static constexpr int OFF_GX = OFF_C + ((fused::C_TOTAL * 4 + 127) / 128) * 128;   // [64][128] fp32 skip-branch d(PE)
@@ -105,7 +126,7 @@ __device__ __forceinline__ void relu_mask32(const eng::ImgDump& img, int tile, u
 }
 
 template <int NSPLIT>
-__global__ void __launch_bounds__(320, 1) field_fused_dgrad_kernel(Args a) {
+__global__ void __launch_bounds__(320, 1) field_fused_dgrad_kernel(const __grid_constant__ Args a) {
   using C = Cfg<NSPLIT>;
   constexpr bool SPLIT = NSPLIT == 3;
   extern __shared__ __align__(128) uint8_t dsm[];
@@ -134,15 +155,15 @@ __global__ void __launch_bounds__(320, 1) field_fused_dgrad_kernel(Args a) {
   tc::tc_fence_after();
   const uint32_t tmem = *tmem_slot;
   const uint32_t T_ACC = tmem, T_AHI = tmem + 256, T_ALO = tmem + 384;
-  eng::Ring ring{ringp, full, empty};
+  eng::Ctx ctx;
+  ctx.ring_addr = tc::smem_u32(ringp); ctx.full_addr = tc::smem_u32(full); ctx.empty_addr = tc::smem_u32(empty);
+  ctx.acc_full_addr = tc::smem_u32(acc_full); ctx.a_ready_addr = tc::smem_u32(a_ready);
+  ctx.tmem_acc = T_ACC; ctx.tmem_ahi = T_AHI; ctx.tmem_alo = T_ALO; ctx.smem_a = 0;
 
   if (warp == 0) {
-    if (lane == 0)
-      eng::producer_loop<NSPLIT, C::NSLOT, C::SLOT_BYTES>(c_plan_dgrad, a.wimg, ring, a.num_tiles);
+    if (lane == 0) eng::producer_loop<C>(ctx, a.wimg, a.num_tiles);
   } else if (warp == 1) {
-    if (lane == 0)
-      eng::mma_loop<NSPLIT, C::NSLOT, C::SLOT_BYTES>(c_plan_dgrad, ring, a_ready, acc_full, T_ACC, T_AHI, T_ALO, 0u,
-                                                     a.num_tiles);
+    if (lane == 0) eng::mma_loop<C>(ctx, a.num_tiles);
   } else {
     const int quad = warp & 3, half = (warp - 2) >> 2;
     const int row = quad * 32 + lane;
@@ -166,7 +187,7 @@ __global__ void __launch_bounds__(320, 1) field_fused_dgrad_kernel(Args a) {
                    gr.z * cst[fused::C_WRGB + 256 + c0 + j];
           relu_mask32(a.img_hv, tile, row, c0, f);
           uint32_t hi[16], lo[16];
-          eng::split32<SPLIT>(f, hi, lo);
+          eng::split32<SPLIT, false>(f, hi, lo);
           tc::tmem_st16(T_AHI + lane_base + (uint32_t)(c0 >> 1), hi);
           if (SPLIT) tc::tmem_st16(T_ALO + lane_base + (uint32_t)(c0 >> 1), lo);
           eng::dump32<SPLIT>(a.out_dzv, tile, row, c0, hi, lo);
@@ -274,7 +295,7 @@ __global__ void __launch_bounds__(320, 1) field_fused_dgrad_kernel(Args a) {
             }
             if (mask.base) relu_mask32(mask, tile, row, cu, f);
             uint32_t hi[16], lo[16];
-            eng::split32<SPLIT>(f, hi, lo);
+            eng::split32<SPLIT, false>(f, hi, lo);
             tc::tmem_st16(T_AHI + lane_base + (uint32_t)(cu >> 1), hi);
             if (SPLIT) tc::tmem_st16(T_ALO + lane_base + (uint32_t)(cu >> 1), lo);
             eng::dump32<SPLIT>(outd, tile, row, cu, hi, lo);

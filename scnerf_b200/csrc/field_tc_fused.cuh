@@ -52,7 +52,6 @@ struct SrcDef {
   uint8_t kind;      // 0: B[n][k] = W[n][col0+k]   1: B[n][k] = W[row0+k][col0+n]   2: B[n][0] = b[n]
   uint16_t row0, col0, valid_k, valid_n;
   uint16_t pad;
-  uint32_t img_off;  // byte offset of the slab in the NSPLIT==1 image (x2 for NSPLIT==3)
 };
 struct PlanSrc { SrcDef s[eng::MAX_SLABS]; };
 struct PackSrc {
@@ -61,38 +60,62 @@ struct PackSrc {
   const float *alpha_w, *alpha_b, *rgb_w, *rgb_b;
 };
 
-inline void build_fwd_plan(eng::Plan& P, PlanSrc& S) {
+constexpr int N_PAD_SLABS = 4;
+__host__ __device__ constexpr eng::Plan make_fwd_plan() {
+  eng::Plan P{};
   int n = 0;
   uint32_t off = 0;
   for (int s = 0; s < NSTAGE; ++s) {
     const StageDef d = stage_def(s);
     const int nk = d.kx + d.kh + d.kv;
     for (int j = 0; j <= nk; ++j, ++n) {
-      eng::SlabDef& e = P.slab[n];
-      SrcDef& q = S.s[n];
-      e = eng::SlabDef{};
-      q = SrcDef{};
-      e.n = (uint16_t)d.N; e.acc_col = 0;
-      e.flags = (j == 0 ? eng::F_ZERO_ACC : 0) | (j == nk ? eng::F_STAGE_END : 0);
-      q.wsel = (uint8_t)s; q.valid_n = (uint16_t)d.N; q.img_off = off;
-      if (j == nk) {                       // bias slab
-        e.a_kind = eng::A_SMEM; e.a_off = A_ONES / 16; e.flags |= eng::F_HI_ONLY_A;
-        q.kind = 2;
+      eng::SlabDef e{};
+      e.n = (uint16_t)d.N; e.acc_col = 0; e.stage = (uint8_t)s; e.img_off = off;
+      e.flags = (uint8_t)((j == 0 ? (eng::F_ZERO_ACC | eng::F_STAGE_BEGIN) : 0) | (j == nk ? eng::F_STAGE_END : 0));
+      if (j == nk) {                       // bias slab: A = ONES
+        e.a_kind = eng::A_SMEM; e.a_off = A_ONES / 16; e.flags = (uint8_t)(e.flags | eng::F_HI_ONLY_A);
       } else if (j < d.kx) {               // PE(pts) columns
         e.a_kind = eng::A_SMEM; e.a_off = (uint16_t)((A_XHI + j * 4096) / 16); e.a_lo_delta = (A_XLO - A_XHI) / 16;
-        q.col0 = (uint16_t)(16 * j); q.valid_k = (uint16_t)std::min(16, 63 - 16 * j);
       } else if (j < d.kx + d.kh) {        // hidden state
         e.a_kind = eng::A_TMEM; e.a_off = (uint16_t)((j - d.kx) * 8);
-        q.col0 = (uint16_t)((d.kx ? 63 : 0) + 16 * (j - d.kx)); q.valid_k = 16;
       } else {                             // PE(dir) columns
-        const int jv = j - d.kx - d.kh;
-        e.a_kind = eng::A_SMEM; e.a_off = (uint16_t)((A_VHI + jv * 4096) / 16); e.a_lo_delta = (A_VLO - A_VHI) / 16;
-        q.col0 = (uint16_t)(256 + 16 * jv); q.valid_k = (uint16_t)std::min(16, 27 - 16 * jv);
+        e.a_kind = eng::A_SMEM; e.a_off = (uint16_t)((A_VHI + (j - d.kx - d.kh) * 4096) / 16);
+        e.a_lo_delta = (A_VLO - A_VHI) / 16;
       }
+      if (s == NSTAGE - 1 && j == nk) e.flags = (uint8_t)(e.flags & ~eng::F_STAGE_END);   // padding follows
+      P.slab[n] = e;
       off += (uint32_t)d.N * 32u;
     }
   }
+  // 164 real slabs: pad to 168 (= 8 x 21) with zero-weight N=16 slabs (A = ONES, B = 0: adds 0 to 16
+  // accumulator columns) so the ring size divides the slab count and slot / parity are compile-time
+  for (int k = 0; k < N_PAD_SLABS; ++k, ++n) {
+    eng::SlabDef e{};
+    e.n = 16; e.acc_col = 0; e.stage = (uint8_t)(NSTAGE - 1); e.img_off = off;
+    e.a_kind = eng::A_SMEM; e.a_off = A_ONES / 16;
+    e.flags = (uint8_t)(eng::F_HI_ONLY_A | (k == N_PAD_SLABS - 1 ? eng::F_STAGE_END : 0));
+    P.slab[n] = e;
+    off += 16u * 32u;
+  }
   P.n_slabs = n; P.n_stages = NSTAGE;
+  return P;
+}
+inline void build_fwd_plansrc(PlanSrc& S) {
+  int n = 0;
+  for (int s = 0; s < NSTAGE; ++s) {
+    const StageDef d = stage_def(s);
+    const int nk = d.kx + d.kh + d.kv;
+    for (int j = 0; j <= nk; ++j, ++n) {
+      SrcDef q{};
+      q.wsel = (uint8_t)s; q.valid_n = (uint16_t)d.N;
+      if (j == nk) q.kind = 2;
+      else if (j < d.kx) { q.col0 = (uint16_t)(16 * j); q.valid_k = (uint16_t)std::min(16, 63 - 16 * j); }
+      else if (j < d.kx + d.kh) { q.col0 = (uint16_t)((d.kx ? 63 : 0) + 16 * (j - d.kx)); q.valid_k = 16; }
+      else { const int jv = j - d.kx - d.kh; q.col0 = (uint16_t)(256 + 16 * jv); q.valid_k = (uint16_t)std::min(16, 27 - 16 * jv); }
+      S.s[n] = q;
+    }
+  }
+  for (int k = 0; k < N_PAD_SLABS; ++k, ++n) { SrcDef q{}; q.kind = 3; S.s[n] = q; }   // zeros
 }
 inline size_t plan_image_bytes(const eng::Plan& P, int nsplit) {
   size_t b = 0;
@@ -114,7 +137,7 @@ __device__ __forceinline__ void pack_slab_impl(const eng::SlabDef& d, const SrcD
     float x = 0.f;
     if (q.kind == 0) { if (k < q.valid_k && row < q.valid_n) x = src.w[q.wsel][(int64_t)row * src.ld[q.wsel] + q.col0 + k]; }
     else if (q.kind == 1) { if (k < q.valid_k && row < q.valid_n) x = src.w[q.wsel][(int64_t)(q.row0 + k) * src.ld[q.wsel] + q.col0 + row]; }
-    else { if (k == 0 && row < q.valid_n) x = src.b[q.wsel][row]; }
+    else if (q.kind == 2) { if (k == 0 && row < q.valid_n) x = src.b[q.wsel][row]; }
     v[e] = x;
   }
   uint32_t h[4], l[4];
@@ -125,7 +148,7 @@ __device__ __forceinline__ void pack_slab_impl(const eng::SlabDef& d, const SrcD
   }
   const size_t sb = (size_t)d.n * 32;
   const size_t in_slab = (size_t)chunk * d.n * 16 + (row >> 3) * 128 + (row & 7) * 16;
-  uint8_t* dst = img + (size_t)q.img_off * (NSPLIT == 3 ? 2 : 1);
+  uint8_t* dst = img + (size_t)d.img_off * (NSPLIT == 3 ? 2 : 1);
   *reinterpret_cast<uint4*>(dst + in_slab) = make_uint4(h[0], h[1], h[2], h[3]);
   if (NSPLIT == 3) *reinterpret_cast<uint4*>(dst + sb + in_slab) = make_uint4(l[0], l[1], l[2], l[3]);
 }
@@ -146,9 +169,12 @@ __global__ void pack_consts_kernel(PackSrc src, float* __restrict__ cbuf) {
   cbuf[g] = v;
 }
 
-template <int NSPLIT> struct Cfg {
-  static constexpr int NSLOT = NSPLIT == 1 ? 16 : 9;
-  static constexpr int SLOT_BYTES = NSPLIT == 1 ? 8192 : 16384;
+template <int NSPLIT_> struct Cfg {
+  static constexpr int NSPLIT = NSPLIT_;
+  static constexpr eng::Plan PLAN = make_fwd_plan();
+  static constexpr int NSLOT = NSPLIT_ == 1 ? 21 : 8;        // 168 slabs per tile: a multiple of both
+  static constexpr int SLOT_BYTES = NSPLIT_ == 1 ? 8192 : 16384;
+  static_assert(PLAN.n_slabs % NSLOT == 0, "ring size must divide the slab count");
   static constexpr int OFF_RING = 0;
   static constexpr int OFF_A = NSLOT * SLOT_BYTES;
   static constexpr int OFF_C = OFF_A + A_BYTES;
@@ -175,12 +201,12 @@ struct Args {
   float* dump_ped; int dump_ped_ld;
 };
 
-__constant__ eng::Plan c_plan_fwd;
+__device__ eng::Plan d_plan_fwd;       // runtime copy of the constexpr plan, for the pack kernel
 __device__ PlanSrc d_plansrc_fwd;
 template <int NSPLIT>
 __global__ void __launch_bounds__(256) pack_fwd_kernel(PackSrc src, uint8_t* __restrict__ img) {
   const int i = blockIdx.y;
-  if (i < c_plan_fwd.n_slabs) pack_slab_impl<NSPLIT>(c_plan_fwd.slab[i], d_plansrc_fwd.s[i], src, img);
+  if (i < d_plan_fwd.n_slabs) pack_slab_impl<NSPLIT>(d_plan_fwd.slab[i], d_plansrc_fwd.s[i], src, img);
 }
 
 // value of PE column i for a 3-vector (L frequencies): [x, sin(2^0 x), cos(2^0 x), ...]
@@ -221,8 +247,78 @@ __device__ __forceinline__ void pe_chunk(const float (&x)[3], bool valid, int ch
   }
 }
 
+// One epilogue stage for this warp's half of the columns (compile-time stage parameters).
+template <int NSPLIT, int S>
+__device__ __forceinline__ void epi_stage(const Args& a, const float* cst, uint32_t T_ACC, uint32_t T_AHI,
+                                          uint32_t T_ALO, uint32_t lane_base, int half, int row, int tile,
+                                          int64_t p, bool valid, uint32_t acc_full_addr, uint32_t a_ready_addr,
+                                          float& alpha, float (&rgb)[3]) {
+  constexpr bool SPLIT = NSPLIT == 3;
+  constexpr StageDef d = stage_def(S);
+  constexpr int nchunk = d.N / 64;           // 32-column chunks owned by this warp
+  const int cbase = half * (d.N / 2);
+  eng::mbar_wait_a(acc_full_addr, (uint32_t)(S & 1));    // 10 stages per tile (even): parity = S & 1
+  tc::tc_fence_after();
+#pragma unroll
+  for (int cc = 0; cc < nchunk; cc += 2) {
+    uint32_t v0[32], v1[32];
+    const int c0 = cbase + cc * 32, c1 = c0 + 32;
+    tc::tmem_ld32(T_ACC + lane_base + c0, v0);
+    tc::tmem_ld32(T_ACC + lane_base + c1, v1);
+    tc::tmem_ld_wait();
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const uint32_t (&v)[32] = u ? v1 : v0;
+      const int cu = u ? c1 : c0;
+      float f[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+      if (a.dump[S] != nullptr && valid) {
+        float* dp = a.dump[S] + p * a.dump_ld[S] + cu;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) dp[j] = d.relu ? fmaxf(f[j], 0.f) : f[j];
+      }
+      if constexpr (S == 7) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) alpha = fmaf(fmaxf(f[j], 0.f), cst[C_WALPHA + cu + j], alpha);
+      }
+      if constexpr (S == 9) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const float t = fmaxf(f[j], 0.f);
+          rgb[0] = fmaf(t, cst[C_WRGB + cu + j], rgb[0]);
+          rgb[1] = fmaf(t, cst[C_WRGB + 128 + cu + j], rgb[1]);
+          rgb[2] = fmaf(t, cst[C_WRGB + 256 + cu + j], rgb[2]);
+        }
+      }
+      if (S != 9 || a.img_out[9].base != nullptr) {
+        uint32_t hi[16], lo[16];
+        eng::split32<SPLIT, d.relu != 0>(f, hi, lo);
+        if constexpr (S != 9) {
+          tc::tmem_st16(T_AHI + lane_base + (uint32_t)(cu >> 1), hi);
+          if constexpr (SPLIT) tc::tmem_st16(T_ALO + lane_base + (uint32_t)(cu >> 1), lo);
+        }
+        if (a.img_out[S].base != nullptr) eng::dump32<SPLIT>(a.img_out[S], tile, row, cu, hi, lo);
+      }
+    }
+  }
+  if constexpr (S < 9) {
+    tc::tmem_st_wait();
+    tc::tc_fence_before();
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(a_ready_addr) : "memory");
+  }
+}
+template <int NSPLIT, size_t... Ss>
+__device__ __forceinline__ void epi_tile(const Args& a, const float* cst, uint32_t T_ACC, uint32_t T_AHI,
+                                         uint32_t T_ALO, uint32_t lane_base, int half, int row, int tile, int64_t p,
+                                         bool valid, uint32_t acc_full_addr, uint32_t a_ready_addr, float& alpha,
+                                         float (&rgb)[3], std::index_sequence<Ss...>) {
+  (epi_stage<NSPLIT, (int)Ss>(a, cst, T_ACC, T_AHI, T_ALO, lane_base, half, row, tile, p, valid, acc_full_addr,
+                              a_ready_addr, alpha, rgb), ...);
+}
+
 template <int NSPLIT>
-__global__ void __launch_bounds__(320, 1) field_fused_fwd_kernel(Args a) {
+__global__ void __launch_bounds__(320, 1) field_fused_fwd_kernel(const __grid_constant__ Args a) {
   using C = Cfg<NSPLIT>;
   constexpr bool SPLIT = NSPLIT == 3;
   extern __shared__ __align__(128) uint8_t fsm[];
@@ -257,21 +353,20 @@ __global__ void __launch_bounds__(320, 1) field_fused_fwd_kernel(Args a) {
   tc::tc_fence_after();
   const uint32_t tmem = *tmem_slot;
   const uint32_t T_ACC = tmem, T_AHI = tmem + 256, T_ALO = tmem + 384;
-  eng::Ring ring{ringp, full, empty};
+  eng::Ctx ctx;
+  ctx.ring_addr = tc::smem_u32(ringp); ctx.full_addr = tc::smem_u32(full); ctx.empty_addr = tc::smem_u32(empty);
+  ctx.acc_full_addr = tc::smem_u32(acc_full); ctx.a_ready_addr = tc::smem_u32(a_ready);
+  ctx.tmem_acc = T_ACC; ctx.tmem_ahi = T_AHI; ctx.tmem_alo = T_ALO; ctx.smem_a = tc::smem_u32(areg);
 
   if (warp == 0) {
-    if (lane == 0)
-      eng::producer_loop<NSPLIT, C::NSLOT, C::SLOT_BYTES>(c_plan_fwd, a.wimg, ring, a.num_tiles);
+    if (lane == 0) eng::producer_loop<C>(ctx, a.wimg, a.num_tiles);
   } else if (warp == 1) {
-    if (lane == 0)
-      eng::mma_loop<NSPLIT, C::NSLOT, C::SLOT_BYTES>(c_plan_fwd, ring, a_ready, acc_full, T_ACC, T_AHI, T_ALO,
-                                                     tc::smem_u32(areg), a.num_tiles);
+    if (lane == 0) eng::mma_loop<C>(ctx, a.num_tiles);
   } else {
     // ===================== epilogue: 8 warps, 2 per TMEM lane quadrant =============================
     const int quad = warp & 3, half = (warp - 2) >> 2;
     const int row = quad * 32 + lane;
     const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
-    uint32_t m = 0;
     for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
       const int64_t p = (int64_t)tile * TILE_M + row;
       const bool valid = p < a.P;
@@ -312,65 +407,9 @@ __global__ void __launch_bounds__(320, 1) field_fused_fwd_kernel(Args a) {
         tc::mbar_arrive(a_ready);
       }
       float alpha = 0.f, rgb[3] = {0.f, 0.f, 0.f};
-#pragma unroll 1
-      for (int s = 0; s < NSTAGE; ++s, ++m) {
-        const StageDef d = stage_def(s);
-        const int nchunk = d.N / 64;          // 32-column chunks per warp (this warp's half)
-        const int cbase = half * (d.N / 2);
-        tc::mbar_wait(acc_full, m & 1);
-        tc::tc_fence_after();
-#pragma unroll 1
-        for (int cc = 0; cc < nchunk; cc += 2) {
-          uint32_t v0[32], v1[32];
-          const int c0 = cbase + cc * 32, c1 = c0 + 32;
-          tc::tmem_ld32(T_ACC + lane_base + c0, v0);
-          tc::tmem_ld32(T_ACC + lane_base + c1, v1);
-          tc::tmem_ld_wait();
-#pragma unroll
-          for (int u = 0; u < 2; ++u) {
-            const uint32_t (&v)[32] = u ? v1 : v0;
-            const int cu = u ? c1 : c0;
-            float f[32];
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const float t = __uint_as_float(v[j]);
-              f[j] = d.relu ? fmaxf(t, 0.f) : t;
-            }
-            if (a.dump[s] && valid) {
-              float* dp = a.dump[s] + p * a.dump_ld[s] + cu;
-#pragma unroll
-              for (int j = 0; j < 32; ++j) dp[j] = f[j];
-            }
-            if (s == 7) {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) alpha = fmaf(f[j], cst[C_WALPHA + cu + j], alpha);
-            }
-            if (s == 9) {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) {
-                rgb[0] = fmaf(f[j], cst[C_WRGB + cu + j], rgb[0]);
-                rgb[1] = fmaf(f[j], cst[C_WRGB + 128 + cu + j], rgb[1]);
-                rgb[2] = fmaf(f[j], cst[C_WRGB + 256 + cu + j], rgb[2]);
-              }
-            }
-            if (s != 9 || a.img_out[9].base) {
-              uint32_t hi[16], lo[16];
-              eng::split32<SPLIT>(f, hi, lo);
-              if (s != 9) {
-                tc::tmem_st16(T_AHI + lane_base + (uint32_t)(cu >> 1), hi);
-                if (SPLIT) tc::tmem_st16(T_ALO + lane_base + (uint32_t)(cu >> 1), lo);
-              }
-              if (a.img_out[s].base) eng::dump32<SPLIT>(a.img_out[s], tile, row, cu, hi, lo);
-            }
-          }
-        }
-        if (s < 9) {
-          tc::tmem_st_wait();
-          tc::tc_fence_before();
-          tc::mbar_arrive(a_ready);
-        }
-      }
-      // combine the two column-halves of each row: half 1 adds into smem, half 0 finishes
+      epi_tile<NSPLIT>(a, cst, T_ACC, T_AHI, T_ALO, lane_base, half, row, tile, p, valid, ctx.acc_full_addr,
+                       ctx.a_ready_addr, alpha, rgb, std::make_index_sequence<NSTAGE>{});
+      // combine the two column-halves of each row: both add into smem, half 0 finishes
       atomicAdd(out_s + row * 4 + 0, rgb[0]);
       atomicAdd(out_s + row * 4 + 1, rgb[1]);
       atomicAdd(out_s + row * 4 + 2, rgb[2]);

@@ -1,11 +1,17 @@
-// Table-driven tcgen05 "slab engine" shared by the fused field kernels (forward, dgrad).
+// Compile-time tcgen05 "slab engine" shared by the fused field kernels (forward, dgrad).
 //
 // A tile (128 samples) is processed as a fixed sequence of SLABS.  One slab = one K=16 step of one
 // GEMM stage: B operand = an [N x 16] bf16 weight slab (hi [, lo]) that the producer warp streams
 // from the packed weight image with one 1-D bulk TMA copy into a ring slot; A operand = 16 columns of
 // the activation, either in TMEM (TS-mode MMA) or in a shared-memory canonical image (SS-mode).
-// The same table drives the producer (how many bytes per slot) and the single MMA-issuing thread.
+//
+// The slab sequence is a constexpr table.  The producer and the single MMA-issuing thread run a FULLY
+// UNROLLED instantiation of it (one template instance per slab): ring slot, mbarrier address, phase
+// parity, operand offsets and instruction descriptor are all immediates, so the issue thread spends a
+// handful of uniform-datapath instructions per MMA instead of a table walk (first profile: ~450 issue
+// cycles per slab against 128-384 cycles of tensor work).
 #pragma once
+#include <utility>
 #include "common.cuh"
 #include "tc_prims.cuh"
 
@@ -13,22 +19,23 @@ namespace scnerf {
 namespace eng {
 
 constexpr int TILE_M = 128;
-constexpr int MAX_SLABS = 256;
+constexpr int MAX_SLABS = 192;
 
 enum : uint8_t { A_TMEM = 0, A_SMEM = 1 };
-enum : uint8_t { F_ZERO_ACC = 1, F_STAGE_END = 2, F_HI_ONLY_A = 4 };
+enum : uint8_t { F_ZERO_ACC = 1, F_STAGE_END = 2, F_HI_ONLY_A = 4, F_STAGE_BEGIN = 8 };
 
 struct SlabDef {
   uint16_t n;          // rows of the B slab (= GEMM N), multiple of 16
   uint16_t acc_col;    // accumulator column offset in TMEM
-  uint16_t a_off;      // A_TMEM: column offset of this k16 inside the A_hi / A_lo regions (8 per k16)
-                       // A_SMEM: byte offset / 16 of the hi image slab inside the smem A area
+  uint16_t a_off;      // A_TMEM: column offset inside the A_hi / A_lo regions (8 per k16)
+                       // A_SMEM: byte offset / 16 of the hi slab inside the smem A area
   uint16_t a_lo_delta; // A_SMEM: byte distance / 16 from the hi to the lo image
   uint8_t a_kind;
   uint8_t flags;
-  uint16_t pad;
+  uint8_t stage;
+  uint8_t pad;
+  uint32_t img_off;    // byte offset of the slab in the NSPLIT==1 weight image (x2 for NSPLIT==3)
 };
-static_assert(sizeof(SlabDef) == 12, "SlabDef layout");
 
 struct Plan {
   SlabDef slab[MAX_SLABS];
@@ -36,92 +43,113 @@ struct Plan {
   int n_stages;
 };
 
-// bytes one slab occupies in the weight image / ring slot
-template <int NSPLIT> __host__ __device__ __forceinline__ uint32_t slab_bytes(const SlabDef& d) {
-  return (uint32_t)d.n * 32u * (NSPLIT == 3 ? 2u : 1u);
-}
+// Kernel traits K must provide:  static constexpr Plan PLAN;  NSPLIT, NSLOT, SLOT_BYTES.
+// Requirement: PLAN.n_slabs % NSLOT == 0 (ring position of slab I is I % NSLOT in every tile).
 
-struct Ring {
-  uint8_t* base;       // NSLOT x SLOT_BYTES
-  uint64_t* full;
-  uint64_t* empty;
+struct Ctx {
+  uint32_t ring_addr;      // shared address of ring slot 0
+  uint32_t full_addr;      // shared address of full[0]   (8 bytes apart)
+  uint32_t empty_addr;     // shared address of empty[0]
+  uint32_t acc_full_addr, a_ready_addr;
+  uint32_t tmem_acc, tmem_ahi, tmem_alo;
+  uint32_t smem_a;         // shared address of the smem A area
 };
 
-// ---- producer: one elected thread streams the weight image once per tile --------------------------
-template <int NSPLIT, int NSLOT, int SLOT_BYTES>
-__device__ __forceinline__ void producer_loop(const Plan& plan, const uint8_t* __restrict__ wimg,
-                                              const Ring& ring, int num_tiles) {
-  uint32_t n = 0;
-  for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-    const uint8_t* src = wimg;
-#pragma unroll 1
-    for (int i = 0; i < plan.n_slabs; ++i, ++n) {
-      const uint32_t bytes = slab_bytes<NSPLIT>(plan.slab[i]);
-      const uint32_t idx = n % NSLOT, ph = (n / NSLOT) & 1;
-      tc::mbar_wait(&ring.empty[idx], ph ^ 1);
-      tc::mbar_arrive_expect_tx(&ring.full[idx], bytes);
-      tc::bulk_g2s(ring.base + idx * SLOT_BYTES, src, bytes, &ring.full[idx]);
-      src += bytes;
-    }
-  }
+__device__ __forceinline__ void mbar_wait_a(uint32_t addr, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
+  } while (!ok);
+}
+__device__ __forceinline__ void commit_a(uint32_t addr) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(addr) : "memory");
+}
+// descriptor with a compile-time hi word: only the 14-bit start address varies
+template <uint32_t LBO, uint32_t SBO>
+__device__ __forceinline__ uint64_t desc_at(uint32_t saddr) {
+  constexpr uint32_t hi = ((SBO >> 4) & 0x3FFF) | (1u << 14);
+  const uint32_t lo = ((saddr >> 4) & 0x3FFF) | (((LBO >> 4) & 0x3FFF) << 16);
+  return ((uint64_t)hi << 32) | lo;
 }
 
-// ---- MMA issuer: one thread -------------------------------------------------------------------------
-// tmem_acc: TMEM base of the accumulators; tmem_ahi / tmem_alo: TMEM bases of the A operand halves;
-// smem_a: shared address (u32) of the smem A area.
-template <int NSPLIT, int NSLOT, int SLOT_BYTES>
-__device__ __forceinline__ void mma_loop(const Plan& plan, const Ring& ring, uint64_t* a_ready,
-                                         uint64_t* acc_full, uint32_t tmem_acc, uint32_t tmem_ahi,
-                                         uint32_t tmem_alo, uint32_t smem_a, int num_tiles) {
-  constexpr bool SPLIT = NSPLIT == 3;
-  const uint32_t ring_addr = tc::smem_u32(ring.base);
-  uint32_t n = 0, q = 0;
-  for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-    bool stage_start = true;
-#pragma unroll 1
-    for (int i = 0; i < plan.n_slabs; ++i, ++n) {
-      const SlabDef d = plan.slab[i];
-      if (stage_start) {          // A operand of this stage written, accumulator drained
-        tc::mbar_wait(a_ready, q & 1);
-        tc::tc_fence_after();
-        ++q;
-        stage_start = false;
-      }
-      const uint32_t idx = n % NSLOT, ph = (n / NSLOT) & 1;
-      tc::mbar_wait(&ring.full[idx], ph);
-      tc::tc_fence_after();
-      const uint32_t slot = ring_addr + idx * SLOT_BYTES;
-      const uint32_t idesc = tc::idesc_bf16_f32(TILE_M, d.n);
-      const uint32_t lbo_b = (uint32_t)d.n * 16u;
-      const uint64_t b_hi = tc::smem_desc(slot, lbo_b, 128);
-      const uint64_t b_lo = tc::smem_desc(slot + (uint32_t)d.n * 32u, lbo_b, 128);
-      const uint32_t acc = tmem_acc + d.acc_col;
-      const uint32_t zero = (d.flags & F_ZERO_ACC) ? 0u : 1u;
-      if (d.a_kind == A_TMEM) {
-        tc::mma_ts(acc, tmem_ahi + d.a_off, b_hi, idesc, zero);
-        if (SPLIT) {
-          if (!(d.flags & F_HI_ONLY_A)) tc::mma_ts(acc, tmem_alo + d.a_off, b_hi, idesc, 1);
-          tc::mma_ts(acc, tmem_ahi + d.a_off, b_lo, idesc, 1);
-        }
-      } else {
-        const uint32_t a_addr = smem_a + (uint32_t)d.a_off * 16u;
-        const uint64_t a_hi = tc::smem_desc(a_addr, 2048, 128);
-        tc::mma_ss(acc, a_hi, b_hi, idesc, zero);
-        if (SPLIT) {
-          if (!(d.flags & F_HI_ONLY_A)) {
-            const uint64_t a_lo = tc::smem_desc(a_addr + (uint32_t)d.a_lo_delta * 16u, 2048, 128);
-            tc::mma_ss(acc, a_lo, b_hi, idesc, 1);
-          }
-          tc::mma_ss(acc, a_hi, b_lo, idesc, 1);
-        }
-      }
-      tc::tc_commit(&ring.empty[idx]);
-      if (d.flags & F_STAGE_END) {
-        tc::tc_commit(acc_full);
-        stage_start = true;
-      }
+template <class K, int I>
+__device__ __forceinline__ void producer_step(const Ctx& c, const uint8_t* __restrict__ wimg, uint32_t tp) {
+  constexpr SlabDef d = K::PLAN.slab[I];
+  constexpr int idx = I % K::NSLOT, wrap = I / K::NSLOT;
+  constexpr bool wraps_odd = ((K::PLAN.n_slabs / K::NSLOT) & 1) != 0;
+  constexpr uint32_t bytes = (uint32_t)d.n * 32u * (K::NSPLIT == 3 ? 2u : 1u);
+  constexpr uint32_t src_off = d.img_off * (K::NSPLIT == 3 ? 2u : 1u);
+  const uint32_t ph = (uint32_t)(wrap & 1) ^ (wraps_odd ? tp : 0u);
+  mbar_wait_a(c.empty_addr + idx * 8, ph ^ 1u);
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(c.full_addr + idx * 8), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(c.ring_addr + idx * K::SLOT_BYTES), "l"(wimg + src_off), "r"(bytes), "r"(c.full_addr + idx * 8)
+               : "memory");
+}
+template <class K, size_t... Is>
+__device__ __forceinline__ void producer_tile(const Ctx& c, const uint8_t* __restrict__ wimg, uint32_t tp,
+                                              std::index_sequence<Is...>) {
+  (producer_step<K, (int)Is>(c, wimg, tp), ...);
+}
+template <class K>
+__device__ __forceinline__ void producer_loop(const Ctx& c, const uint8_t* __restrict__ wimg, int num_tiles) {
+  uint32_t tp = 0;
+  for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, tp ^= 1u)
+    producer_tile<K>(c, wimg, tp, std::make_index_sequence<K::PLAN.n_slabs>{});
+}
+
+template <class K, int I>
+__device__ __forceinline__ void mma_step(const Ctx& c, uint32_t tp) {
+  constexpr SlabDef d = K::PLAN.slab[I];
+  constexpr bool SPLIT = K::NSPLIT == 3;
+  constexpr int idx = I % K::NSLOT, wrap = I / K::NSLOT;
+  constexpr bool wraps_odd = ((K::PLAN.n_slabs / K::NSLOT) & 1) != 0;
+  constexpr bool stages_odd = (K::PLAN.n_stages & 1) != 0;
+  if constexpr ((d.flags & F_STAGE_BEGIN) != 0) {   // A operand of this stage written, accumulator drained
+    mbar_wait_a(c.a_ready_addr, (uint32_t)(d.stage & 1) ^ (stages_odd ? tp : 0u));
+    tc::tc_fence_after();
+  }
+  mbar_wait_a(c.full_addr + idx * 8, (uint32_t)(wrap & 1) ^ (wraps_odd ? tp : 0u));
+  tc::tc_fence_after();
+  constexpr uint32_t idesc = tc::idesc_bf16_f32(TILE_M, d.n);
+  constexpr uint32_t LBO_B = (uint32_t)d.n * 16u;
+  const uint32_t slot = c.ring_addr + idx * K::SLOT_BYTES;
+  const uint64_t b_hi = desc_at<LBO_B, 128>(slot);
+  const uint64_t b_lo = desc_at<LBO_B, 128>(slot + (uint32_t)d.n * 32u);
+  const uint32_t acc = c.tmem_acc + d.acc_col;
+  constexpr uint32_t first = (d.flags & F_ZERO_ACC) ? 0u : 1u;
+  if constexpr (d.a_kind == A_TMEM) {
+    tc::mma_ts(acc, c.tmem_ahi + d.a_off, b_hi, idesc, first);
+    if constexpr (SPLIT) {
+      if constexpr ((d.flags & F_HI_ONLY_A) == 0) tc::mma_ts(acc, c.tmem_alo + d.a_off, b_hi, idesc, 1);
+      tc::mma_ts(acc, c.tmem_ahi + d.a_off, b_lo, idesc, 1);
+    }
+  } else {
+    const uint32_t a_addr = c.smem_a + (uint32_t)d.a_off * 16u;
+    const uint64_t a_hi = desc_at<2048, 128>(a_addr);
+    tc::mma_ss(acc, a_hi, b_hi, idesc, first);
+    if constexpr (SPLIT) {
+      if constexpr ((d.flags & F_HI_ONLY_A) == 0)
+        tc::mma_ss(acc, desc_at<2048, 128>(a_addr + (uint32_t)d.a_lo_delta * 16u), b_hi, idesc, 1);
+      tc::mma_ss(acc, a_hi, b_lo, idesc, 1);
     }
   }
+  commit_a(c.empty_addr + idx * 8);
+  if constexpr ((d.flags & F_STAGE_END) != 0) commit_a(c.acc_full_addr);
+}
+template <class K, size_t... Is>
+__device__ __forceinline__ void mma_tile(const Ctx& c, uint32_t tp, std::index_sequence<Is...>) {
+  (mma_step<K, (int)Is>(c, tp), ...);
+}
+template <class K>
+__device__ __forceinline__ void mma_loop(const Ctx& c, int num_tiles) {
+  uint32_t tp = 0;
+  for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, tp ^= 1u)
+    mma_tile<K>(c, tp, std::make_index_sequence<K::PLAN.n_slabs>{});
 }
 
 // ---- epilogue helpers ----------------------------------------------------------------------------------
@@ -139,13 +167,17 @@ __device__ __forceinline__ uint32_t cvt_relu_bf16x2(float lo, float hi) {
 __device__ __forceinline__ float bf16lo_f(uint32_t p) { return __uint_as_float(p << 16); }
 __device__ __forceinline__ float bf16hi_f(uint32_t p) { return __uint_as_float(p & 0xffff0000u); }
 
-// split 32 fp32 values (already activated) into packed hi / lo bf16 pairs
-template <bool SPLIT>
+// split 32 fp32 values into packed hi / lo bf16 pairs.  RELU: apply max(x,0) on the fly
+// (cvt.rn.relu for the hi half; the residual uses the clamped value).
+template <bool SPLIT, bool RELU>
 __device__ __forceinline__ void split32(const float (&f)[32], uint32_t (&hi)[16], uint32_t (&lo)[16]) {
 #pragma unroll
   for (int j = 0; j < 16; ++j) {
-    hi[j] = cvt_bf16x2(f[2 * j], f[2 * j + 1]);
-    if (SPLIT) lo[j] = cvt_bf16x2(f[2 * j] - bf16lo_f(hi[j]), f[2 * j + 1] - bf16hi_f(hi[j]));
+    hi[j] = RELU ? cvt_relu_bf16x2(f[2 * j], f[2 * j + 1]) : cvt_bf16x2(f[2 * j], f[2 * j + 1]);
+    if (SPLIT) {
+      const float a = RELU ? fmaxf(f[2 * j], 0.f) : f[2 * j], b = RELU ? fmaxf(f[2 * j + 1], 0.f) : f[2 * j + 1];
+      lo[j] = cvt_bf16x2(a - bf16lo_f(hi[j]), b - bf16hi_f(hi[j]));
+    }
   }
 }
 
@@ -158,7 +190,7 @@ struct ImgDump {
   uint8_t* base;       // NULL = disabled
   uint32_t F;          // features (multiple of 8)
   uint32_t nhalf;      // 1 (hi) or 2 (hi, lo)
-  __device__ __forceinline__ size_t tile_bytes() const { return (size_t)F * 256u * nhalf; }
+  __host__ __device__ __forceinline__ size_t tile_bytes() const { return (size_t)F * 256u * nhalf; }
   // address of the 16-byte chunk (8 features starting at mn0, sample k of tile `tile`, half h)
   __device__ __forceinline__ uint8_t* chunk(int tile, uint32_t k, uint32_t mn0, uint32_t h) const {
     return base + (size_t)tile * tile_bytes() + (size_t)(k >> 4) * (F * 32u * nhalf) + (size_t)h * (F * 32u) +
@@ -169,12 +201,12 @@ struct ImgDump {
 template <bool SPLIT>
 __device__ __forceinline__ void dump32(const ImgDump& d, int tile, uint32_t k, uint32_t c0,
                                        const uint32_t (&hi)[16], const uint32_t (&lo)[16]) {
+  uint8_t* p = d.chunk(tile, k, c0, 0);
 #pragma unroll
   for (int g = 0; g < 4; ++g) {
-    *reinterpret_cast<uint4*>(d.chunk(tile, k, c0 + 8 * g, 0)) =
-        make_uint4(hi[4 * g], hi[4 * g + 1], hi[4 * g + 2], hi[4 * g + 3]);
+    *reinterpret_cast<uint4*>(p + g * 256) = make_uint4(hi[4 * g], hi[4 * g + 1], hi[4 * g + 2], hi[4 * g + 3]);
     if (SPLIT && d.nhalf == 2)
-      *reinterpret_cast<uint4*>(d.chunk(tile, k, c0 + 8 * g, 1)) =
+      *reinterpret_cast<uint4*>(p + d.F * 32u + g * 256) =
           make_uint4(lo[4 * g], lo[4 * g + 1], lo[4 * g + 2], lo[4 * g + 3]);
   }
 }
