@@ -246,6 +246,10 @@ int scnerf_train_step(const scnerf_camera* cam, const scnerf_camera_grads* g_cam
 int scnerf_tc_selftest(const float* A, const float* B, float* D, int32_t N, int32_t K, int32_t variant,
                        void* workspace, size_t workspace_bytes, void* stream);
 
+/* Diagnostics: have the next fused-forward launches record clock64() stamps of CTA 0 for the first
+ * `tiles` tiles into dev_buf[tiles][10 stages][4] (NULL disables).  Not part of the product path. */
+int scnerf_debug_timeline(long long* dev_buf, int32_t tiles);
+
 /* Kernel-launch counter (bench.py's gpu_launches): number of kernels this library has launched
  * in this process since the last reset. */
 int64_t scnerf_launch_count(int32_t reset);

@@ -32,6 +32,12 @@ int64_t scnerf_launch_count(int32_t reset) {
   return v;
 }
 
+int scnerf_debug_timeline(long long* dev_buf, int32_t tiles) {
+  tc_dbg_ptr() = dev_buf;
+  tc_dbg_tiles() = tiles;
+  return 0;
+}
+
 int scnerf_tc_selftest(const float* A, const float* B, float* D, int32_t N, int32_t K, int32_t variant,
                        void* workspace, size_t workspace_bytes, void* stream) {
   SCNERF_CHECK_ARG(A && B && D, "selftest: null pointer");

@@ -156,6 +156,10 @@ inline int tc_selftest(const float* A, const float* B, float* D, int N, int K, i
   return 0;
 }
 
+// optional in-kernel timeline buffer for the next fused forward launch (diagnostics only)
+inline long long*& tc_dbg_ptr() { static long long* p = nullptr; return p; }
+inline int& tc_dbg_tiles() { static int n = 0; return n; }
+
 inline int device_sm_count() {
   static int n = 0;
   if (n == 0) {
@@ -260,6 +264,7 @@ inline int field_tc_fwd_impl(const scnerf_mlp& m, const float* rays, int ray_col
     a.dump_pe = B.X5; a.dump_pe_ld = (int)B.ldx5;
     a.dump_ped = B.F + 256; a.dump_ped_ld = (int)B.ldf;
   }
+  a.dbg = tc_dbg_ptr(); a.dbg_tiles = tc_dbg_tiles();
   int grid = std::min(device_sm_count(), a.num_tiles);
   SCNERF_LAUNCH((field_fused_fwd_kernel<NSPLIT>), grid, 320, Cfg<NSPLIT>::SMEM_BYTES, stream, a);
   return 0;

@@ -159,6 +159,7 @@ __global__ void __launch_bounds__(320, 1) field_fused_dgrad_kernel(const __grid_
   ctx.ring_addr = tc::smem_u32(ringp); ctx.full_addr = tc::smem_u32(full); ctx.empty_addr = tc::smem_u32(empty);
   ctx.acc_full_addr = tc::smem_u32(acc_full); ctx.a_ready_addr = tc::smem_u32(a_ready);
   ctx.tmem_acc = T_ACC; ctx.tmem_ahi = T_AHI; ctx.tmem_alo = T_ALO; ctx.smem_a = 0;
+  ctx.dbg = nullptr; ctx.dbg_tiles = 0;
 
   if (warp == 0) {
     if (lane == 0) eng::producer_loop<C>(ctx, a.wimg, a.num_tiles);

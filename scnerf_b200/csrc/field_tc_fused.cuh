@@ -199,6 +199,7 @@ struct Args {
   float* dump[NSTAGE]; int dump_ld[NSTAGE];
   float* dump_pe; int dump_pe_ld;
   float* dump_ped; int dump_ped_ld;
+  long long* dbg; int dbg_tiles;       // optional in-kernel timeline (see eng::Ctx)
 };
 
 __device__ eng::Plan d_plan_fwd;       // runtime copy of the constexpr plan, for the pack kernel
@@ -252,13 +253,14 @@ template <int NSPLIT, int S>
 __device__ __forceinline__ void epi_stage(const Args& a, const float* cst, uint32_t T_ACC, uint32_t T_AHI,
                                           uint32_t T_ALO, uint32_t lane_base, int half, int row, int tile,
                                           int64_t p, bool valid, uint32_t acc_full_addr, uint32_t a_ready_addr,
-                                          float& alpha, float (&rgb)[3]) {
+                                          float& alpha, float (&rgb)[3], const eng::Ctx& ctx, int tile_iter) {
   constexpr bool SPLIT = NSPLIT == 3;
   constexpr StageDef d = stage_def(S);
   constexpr int nchunk = d.N / 64;           // 32-column chunks owned by this warp
   const int cbase = half * (d.N / 2);
   eng::mbar_wait_a(acc_full_addr, (uint32_t)(S & 1));    // 10 stages per tile (even): parity = S & 1
   tc::tc_fence_after();
+  if (threadIdx.x == 64) eng::dbg_stamp(ctx, tile_iter, S, NSTAGE, 2);
 #pragma unroll
   for (int cc = 0; cc < nchunk; cc += 2) {
     uint32_t v0[32], v1[32];
@@ -307,14 +309,16 @@ __device__ __forceinline__ void epi_stage(const Args& a, const float* cst, uint3
     tc::tc_fence_before();
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(a_ready_addr) : "memory");
   }
+  if (threadIdx.x == 64) eng::dbg_stamp(ctx, tile_iter, S, NSTAGE, 3);
 }
 template <int NSPLIT, size_t... Ss>
 __device__ __forceinline__ void epi_tile(const Args& a, const float* cst, uint32_t T_ACC, uint32_t T_AHI,
                                          uint32_t T_ALO, uint32_t lane_base, int half, int row, int tile, int64_t p,
                                          bool valid, uint32_t acc_full_addr, uint32_t a_ready_addr, float& alpha,
-                                         float (&rgb)[3], std::index_sequence<Ss...>) {
+                                         float (&rgb)[3], const eng::Ctx& ctx, int tile_iter,
+                                         std::index_sequence<Ss...>) {
   (epi_stage<NSPLIT, (int)Ss>(a, cst, T_ACC, T_AHI, T_ALO, lane_base, half, row, tile, p, valid, acc_full_addr,
-                              a_ready_addr, alpha, rgb), ...);
+                              a_ready_addr, alpha, rgb, ctx, tile_iter), ...);
 }
 
 template <int NSPLIT>
@@ -357,6 +361,7 @@ __global__ void __launch_bounds__(320, 1) field_fused_fwd_kernel(const __grid_co
   ctx.ring_addr = tc::smem_u32(ringp); ctx.full_addr = tc::smem_u32(full); ctx.empty_addr = tc::smem_u32(empty);
   ctx.acc_full_addr = tc::smem_u32(acc_full); ctx.a_ready_addr = tc::smem_u32(a_ready);
   ctx.tmem_acc = T_ACC; ctx.tmem_ahi = T_AHI; ctx.tmem_alo = T_ALO; ctx.smem_a = tc::smem_u32(areg);
+  ctx.dbg = a.dbg; ctx.dbg_tiles = a.dbg_tiles;
 
   if (warp == 0) {
     if (lane == 0) eng::producer_loop<C>(ctx, a.wimg, a.num_tiles);
@@ -367,7 +372,8 @@ __global__ void __launch_bounds__(320, 1) field_fused_fwd_kernel(const __grid_co
     const int quad = warp & 3, half = (warp - 2) >> 2;
     const int row = quad * 32 + lane;
     const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
-    for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
+    int tile_iter = 0;
+    for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x, ++tile_iter) {
       const int64_t p = (int64_t)tile * TILE_M + row;
       const bool valid = p < a.P;
       // ---- positional encodings -> smem A slabs (half 0: X chunks 0-3; half 1: X 4-7 and V 0-3)
@@ -408,7 +414,7 @@ __global__ void __launch_bounds__(320, 1) field_fused_fwd_kernel(const __grid_co
       }
       float alpha = 0.f, rgb[3] = {0.f, 0.f, 0.f};
       epi_tile<NSPLIT>(a, cst, T_ACC, T_AHI, T_ALO, lane_base, half, row, tile, p, valid, ctx.acc_full_addr,
-                       ctx.a_ready_addr, alpha, rgb, std::make_index_sequence<NSTAGE>{});
+                       ctx.a_ready_addr, alpha, rgb, ctx, tile_iter, std::make_index_sequence<NSTAGE>{});
       // combine the two column-halves of each row: both add into smem, half 0 finishes
       atomicAdd(out_s + row * 4 + 0, rgb[0]);
       atomicAdd(out_s + row * 4 + 1, rgb[1]);

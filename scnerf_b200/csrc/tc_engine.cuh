@@ -53,7 +53,15 @@ struct Ctx {
   uint32_t acc_full_addr, a_ready_addr;
   uint32_t tmem_acc, tmem_ahi, tmem_alo;
   uint32_t smem_a;         // shared address of the smem A area
+  long long* dbg;          // optional timeline (CTA 0 only): [tile][stage][4] clock64 stamps
+                           //   0: MMA thread passed a_ready   1: MMA thread issued the stage's last commit
+                           //   2: epilogue (warp 2) saw acc_full   3: epilogue (warp 2) arrived on a_ready
+  int dbg_tiles;
 };
+__device__ __forceinline__ void dbg_stamp(const Ctx& c, int tile_iter, int stage, int n_stages, int slot) {
+  if (c.dbg != nullptr && blockIdx.x == 0 && tile_iter < c.dbg_tiles)
+    c.dbg[((size_t)tile_iter * n_stages + stage) * 4 + slot] = clock64();
+}
 
 __device__ __forceinline__ void mbar_wait_a(uint32_t addr, uint32_t parity) {
   uint32_t ok;
@@ -103,7 +111,7 @@ __device__ __forceinline__ void producer_loop(const Ctx& c, const uint8_t* __res
 }
 
 template <class K, int I>
-__device__ __forceinline__ void mma_step(const Ctx& c, uint32_t tp) {
+__device__ __forceinline__ void mma_step(const Ctx& c, uint32_t tp, int tile_iter) {
   constexpr SlabDef d = K::PLAN.slab[I];
   constexpr bool SPLIT = K::NSPLIT == 3;
   constexpr int idx = I % K::NSLOT, wrap = I / K::NSLOT;
@@ -112,6 +120,7 @@ __device__ __forceinline__ void mma_step(const Ctx& c, uint32_t tp) {
   if constexpr ((d.flags & F_STAGE_BEGIN) != 0) {   // A operand of this stage written, accumulator drained
     mbar_wait_a(c.a_ready_addr, (uint32_t)(d.stage & 1) ^ (stages_odd ? tp : 0u));
     tc::tc_fence_after();
+    dbg_stamp(c, tile_iter, d.stage, K::PLAN.n_stages, 0);
   }
   mbar_wait_a(c.full_addr + idx * 8, (uint32_t)(wrap & 1) ^ (wraps_odd ? tp : 0u));
   tc::tc_fence_after();
@@ -139,17 +148,21 @@ __device__ __forceinline__ void mma_step(const Ctx& c, uint32_t tp) {
     }
   }
   commit_a(c.empty_addr + idx * 8);
-  if constexpr ((d.flags & F_STAGE_END) != 0) commit_a(c.acc_full_addr);
+  if constexpr ((d.flags & F_STAGE_END) != 0) {
+    commit_a(c.acc_full_addr);
+    dbg_stamp(c, tile_iter, d.stage, K::PLAN.n_stages, 1);
+  }
 }
 template <class K, size_t... Is>
-__device__ __forceinline__ void mma_tile(const Ctx& c, uint32_t tp, std::index_sequence<Is...>) {
-  (mma_step<K, (int)Is>(c, tp), ...);
+__device__ __forceinline__ void mma_tile(const Ctx& c, uint32_t tp, int tile_iter, std::index_sequence<Is...>) {
+  (mma_step<K, (int)Is>(c, tp, tile_iter), ...);
 }
 template <class K>
 __device__ __forceinline__ void mma_loop(const Ctx& c, int num_tiles) {
   uint32_t tp = 0;
-  for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, tp ^= 1u)
-    mma_tile<K>(c, tp, std::make_index_sequence<K::PLAN.n_slabs>{});
+  int it = 0;
+  for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, tp ^= 1u, ++it)
+    mma_tile<K>(c, tp, it, std::make_index_sequence<K::PLAN.n_slabs>{});
 }
 
 // ---- epilogue helpers ----------------------------------------------------------------------------------
