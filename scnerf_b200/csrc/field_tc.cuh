@@ -176,7 +176,7 @@ inline int fwd_plan_init() {
   int dev = 0;
   SCNERF_CUDA(cudaGetDevice(&dev));
   if (dev < 64 && done[dev]) return 0;
-  static eng::Plan P = fused::make_fwd_plan();
+  static eng::Plan P = fused::make_fwd_plan<3>();   // (image offsets and sources do not depend on NSPLIT)
   static fused::PlanSrc S;
   fused::build_fwd_plansrc(S);
   if (fused::plan_image_bytes(P, 3) > TC_IMG_BYTES) return fail(SCNERF_ERR_WORKSPACE, "TC_IMG_BYTES too small");
@@ -190,7 +190,7 @@ inline int fwd_plan_init() {
   return 0;
 }
 inline const eng::Plan& fwd_plan_host() {
-  static eng::Plan P = fused::make_fwd_plan();
+  static eng::Plan P = fused::make_fwd_plan<3>();
   return P;
 }
 

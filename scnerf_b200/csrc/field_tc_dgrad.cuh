@@ -89,9 +89,10 @@ __global__ void __launch_bounds__(256) pack_dgrad_kernel(fused::PackSrc src, uin
 template <int NSPLIT_> struct Cfg {
   static constexpr int NSPLIT = NSPLIT_;
   static constexpr eng::Plan PLAN = make_plan();
-  static constexpr int NSLOT = NSPLIT_ == 1 ? 22 : 11;        // 176 slabs per tile
-  static constexpr int SLOT_BYTES = NSPLIT_ == 1 ? 8192 : 16384;
-  static_assert(PLAN.n_slabs % NSLOT == 0, "ring size must divide the slab count");
+  static constexpr int GROUP = NSPLIT_ == 1 ? 2 : 1;          // slabs per ring slot
+  static constexpr int NSLOT = 11;                            // 176 slabs per tile = 88 pairs = 11*8 = 11*16
+  static constexpr int SLOT_BYTES = 16384;
+  static_assert((PLAN.n_slabs / GROUP) % NSLOT == 0 && PLAN.n_slabs % GROUP == 0, "ring size must divide the slab-group count");
   static constexpr int OFF_RING = 0;
   static constexpr int OFF_C = NSLOT * SLOT_BYTES;
   static constexpr int OFF_GX = OFF_C + ((fused::C_TOTAL * 4 + 127) / 128) * 128;   // [64][128] fp32 skip-branch d(PE)

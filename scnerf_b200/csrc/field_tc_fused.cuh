@@ -43,8 +43,15 @@ __host__ __device__ constexpr StageDef stage_def(int s) {
                 : StageDef{256, 0, 16, 0, 1};
 }
 
-// smem A area (byte offsets from its base)
-constexpr int A_XHI = 0, A_XLO = 16384, A_VHI = 32768, A_VLO = 40960, A_ONES = 49152, A_BYTES = 53248;
+// smem A area (byte offsets from its base); the lo images exist only in the split-bf16 build
+template <int NSPLIT> struct ALay {
+  static constexpr int XHI = 0;
+  static constexpr int XLO = 16384;
+  static constexpr int VHI = NSPLIT == 3 ? 32768 : 16384;
+  static constexpr int VLO = VHI + 8192;
+  static constexpr int ONES = NSPLIT == 3 ? 49152 : 24576;
+  static constexpr int BYTES = ONES + 4096;
+};
 
 // source of each slab for the pack kernel (parallel to the plan)
 struct SrcDef {
@@ -61,7 +68,10 @@ struct PackSrc {
 };
 
 constexpr int N_PAD_SLABS = 4;
+template <int NSPLIT>
 __host__ __device__ constexpr eng::Plan make_fwd_plan() {
+  constexpr int A_XHI = ALay<NSPLIT>::XHI, A_XLO = ALay<NSPLIT>::XLO, A_VHI = ALay<NSPLIT>::VHI,
+                A_VLO = ALay<NSPLIT>::VLO, A_ONES = ALay<NSPLIT>::ONES;
   eng::Plan P{};
   int n = 0;
   uint32_t off = 0;
@@ -171,16 +181,18 @@ __global__ void pack_consts_kernel(PackSrc src, float* __restrict__ cbuf) {
 
 template <int NSPLIT_> struct Cfg {
   static constexpr int NSPLIT = NSPLIT_;
-  static constexpr eng::Plan PLAN = make_fwd_plan();
-  static constexpr int NSLOT = NSPLIT_ == 1 ? 21 : 8;        // 168 slabs per tile: a multiple of both
-  static constexpr int SLOT_BYTES = NSPLIT_ == 1 ? 8192 : 16384;
-  static_assert(PLAN.n_slabs % NSLOT == 0, "ring size must divide the slab count");
+  static constexpr eng::Plan PLAN = make_fwd_plan<NSPLIT_>();
+  static constexpr int GROUP = NSPLIT_ == 1 ? 2 : 1;         // slabs per ring slot
+  static constexpr int NSLOT = NSPLIT_ == 1 ? 12 : 8;        // 168 slabs per tile = 84 pairs = 12*7 = 8*21
+  static constexpr int SLOT_BYTES = 16384;
+  static_assert((PLAN.n_slabs / GROUP) % NSLOT == 0 && PLAN.n_slabs % GROUP == 0, "ring size must divide the slab-group count");
   static constexpr int OFF_RING = 0;
   static constexpr int OFF_A = NSLOT * SLOT_BYTES;
-  static constexpr int OFF_C = OFF_A + A_BYTES;
+  static constexpr int OFF_C = OFF_A + ALay<NSPLIT_>::BYTES;
   static constexpr int OFF_OUT = OFF_C + ((C_TOTAL * 4 + 127) / 128) * 128;   // [128][4] head partial sums
   static constexpr int OFF_BAR = OFF_OUT + 128 * 4 * 4;
   static constexpr int SMEM_BYTES = OFF_BAR + (2 * NSLOT + 2) * 8 + 16;
+  static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB shared-memory limit");
 };
 
 struct Args {
@@ -210,41 +222,46 @@ __global__ void __launch_bounds__(256) pack_fwd_kernel(PackSrc src, uint8_t* __r
   if (i < d_plan_fwd.n_slabs) pack_slab_impl<NSPLIT>(d_plan_fwd.slab[i], d_plansrc_fwd.s[i], src, img);
 }
 
-// value of PE column i for a 3-vector (L frequencies): [x, sin(2^0 x), cos(2^0 x), ...]
-template <int L>
-__device__ __forceinline__ float pe_col(const float (&x)[3], int i) {
-  if (i < 3) return x[i];
-  if (i >= 3 + 6 * L) return 0.f;
-  const int f = (i - 3) / 6, r = (i - 3) % 6;
-  const float arg = x[r % 3] * (float)(1 << f);
-  return r < 3 ? sinf(arg) : cosf(arg);
+// PE columns [LO, LO+32) of a 3-vector with L frequencies ([x, sin(2^0 x), cos(2^0 x), ...], zero padded):
+// one sincosf per (frequency, component) pair that touches the range; all indices are compile-time.
+template <int L, int LO>
+__device__ __forceinline__ void pe_fill32(const float (&x)[3], bool valid, float (&e)[32]) {
+#pragma unroll
+  for (int i = 0; i < 32; ++i) e[i] = (valid && LO + i < 3) ? x[(LO + i) % 3] : 0.f;
+  if (!valid) return;
+#pragma unroll
+  for (int f = 0; f < L; ++f) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const int is = 3 + 6 * f + c, ic = is + 3;
+      const bool need_s = is >= LO && is < LO + 32, need_c = ic >= LO && ic < LO + 32;
+      if (need_s || need_c) {
+        float sv, cv;
+        sincosf(x[c] * (float)(1 << f), &sv, &cv);
+        if (need_s) e[is - LO] = sv;
+        if (need_c) e[ic - LO] = cv;
+      }
+    }
+  }
 }
-// write PE columns [8*ch, 8*ch+8) of row `row` into the canonical K-major smem image (+ dumps)
-template <int L, bool SPLIT>
-__device__ __forceinline__ void pe_chunk(const float (&x)[3], bool valid, int ch, uint8_t* hi_img,
-                                         uint8_t* lo_img, int row, const eng::ImgDump& img, int tile,
-                                         float* dump) {
-  float v[8];
+// store 32 PE columns [LO, LO+32) of row `row`: canonical K-major smem image (+ tile image, + fp32 dump)
+template <bool SPLIT>
+__device__ __forceinline__ void pe_store32(const float (&e)[32], int lo_col, int ncols_valid, uint8_t* hi_img,
+                                           uint8_t* lo_img, int row, const eng::ImgDump& img, int tile,
+                                           float* dump, bool valid) {
+  uint32_t hi[16], lo[16];
+  eng::split32<SPLIT, false>(e, hi, lo);
 #pragma unroll
-  for (int i = 0; i < 8; ++i) v[i] = valid ? pe_col<L>(x, ch * 8 + i) : 0.f;
-  uint32_t h[4], l[4];
-#pragma unroll
-  for (int e = 0; e < 4; ++e) {
-    h[e] = eng::cvt_bf16x2(v[2 * e], v[2 * e + 1]);
-    l[e] = eng::cvt_bf16x2(v[2 * e] - eng::bf16lo_f(h[e]), v[2 * e + 1] - eng::bf16hi_f(h[e]));
+  for (int g = 0; g < 4; ++g) {
+    const uint32_t off = tc::canon_off(row, lo_col + 8 * g, TILE_M);
+    *reinterpret_cast<uint4*>(hi_img + off) = make_uint4(hi[4 * g], hi[4 * g + 1], hi[4 * g + 2], hi[4 * g + 3]);
+    if (SPLIT) *reinterpret_cast<uint4*>(lo_img + off) = make_uint4(lo[4 * g], lo[4 * g + 1], lo[4 * g + 2], lo[4 * g + 3]);
   }
-  const uint32_t off = tc::canon_off(row, ch * 8, TILE_M);
-  *reinterpret_cast<uint4*>(hi_img + off) = make_uint4(h[0], h[1], h[2], h[3]);
-  if (SPLIT) *reinterpret_cast<uint4*>(lo_img + off) = make_uint4(l[0], l[1], l[2], l[3]);
-  if (img.base) {
-    *reinterpret_cast<uint4*>(img.chunk(tile, row, ch * 8, 0)) = make_uint4(h[0], h[1], h[2], h[3]);
-    if (SPLIT && img.nhalf == 2)
-      *reinterpret_cast<uint4*>(img.chunk(tile, row, ch * 8, 1)) = make_uint4(l[0], l[1], l[2], l[3]);
-  }
+  if (img.base) eng::dump32<SPLIT>(img, tile, row, lo_col, hi, lo);
   if (dump && valid) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i)
-      if (ch * 8 + i < 3 + 6 * L) dump[ch * 8 + i] = v[i];
+    for (int i = 0; i < 32; ++i)
+      if (lo_col + i < ncols_valid) dump[lo_col + i] = e[i];
   }
 }
 
@@ -261,47 +278,43 @@ __device__ __forceinline__ void epi_stage(const Args& a, const float* cst, uint3
   eng::mbar_wait_a(acc_full_addr, (uint32_t)(S & 1));    // 10 stages per tile (even): parity = S & 1
   tc::tc_fence_after();
   if (threadIdx.x == 64) eng::dbg_stamp(ctx, tile_iter, S, NSTAGE, 2);
+  // all of this warp's TMEM loads for the stage are issued back to back, then one wait
+  uint32_t v[nchunk][32];
 #pragma unroll
-  for (int cc = 0; cc < nchunk; cc += 2) {
-    uint32_t v0[32], v1[32];
-    const int c0 = cbase + cc * 32, c1 = c0 + 32;
-    tc::tmem_ld32(T_ACC + lane_base + c0, v0);
-    tc::tmem_ld32(T_ACC + lane_base + c1, v1);
-    tc::tmem_ld_wait();
+  for (int cc = 0; cc < nchunk; ++cc) tc::tmem_ld32(T_ACC + lane_base + cbase + cc * 32, v[cc]);
+  tc::tmem_ld_wait();
 #pragma unroll
-    for (int u = 0; u < 2; ++u) {
-      const uint32_t (&v)[32] = u ? v1 : v0;
-      const int cu = u ? c1 : c0;
-      float f[32];
+  for (int cc = 0; cc < nchunk; ++cc) {
+    const int cu = cbase + cc * 32;
+    float f[32];
 #pragma unroll
-      for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-      if (a.dump[S] != nullptr && valid) {
-        float* dp = a.dump[S] + p * a.dump_ld[S] + cu;
+    for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[cc][j]);
+    if (a.dump[S] != nullptr && valid) {
+      float* dp = a.dump[S] + p * a.dump_ld[S] + cu;
 #pragma unroll
-        for (int j = 0; j < 32; ++j) dp[j] = d.relu ? fmaxf(f[j], 0.f) : f[j];
+      for (int j = 0; j < 32; ++j) dp[j] = d.relu ? fmaxf(f[j], 0.f) : f[j];
+    }
+    if constexpr (S == 7) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) alpha = fmaf(fmaxf(f[j], 0.f), cst[C_WALPHA + cu + j], alpha);
+    }
+    if constexpr (S == 9) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const float t = fmaxf(f[j], 0.f);
+        rgb[0] = fmaf(t, cst[C_WRGB + cu + j], rgb[0]);
+        rgb[1] = fmaf(t, cst[C_WRGB + 128 + cu + j], rgb[1]);
+        rgb[2] = fmaf(t, cst[C_WRGB + 256 + cu + j], rgb[2]);
       }
-      if constexpr (S == 7) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) alpha = fmaf(fmaxf(f[j], 0.f), cst[C_WALPHA + cu + j], alpha);
+    }
+    if (S != 9 || a.img_out[9].base != nullptr) {
+      uint32_t hi[16], lo[16];
+      eng::split32<SPLIT, d.relu != 0>(f, hi, lo);
+      if constexpr (S != 9) {
+        tc::tmem_st16(T_AHI + lane_base + (uint32_t)(cu >> 1), hi);
+        if constexpr (SPLIT) tc::tmem_st16(T_ALO + lane_base + (uint32_t)(cu >> 1), lo);
       }
-      if constexpr (S == 9) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const float t = fmaxf(f[j], 0.f);
-          rgb[0] = fmaf(t, cst[C_WRGB + cu + j], rgb[0]);
-          rgb[1] = fmaf(t, cst[C_WRGB + 128 + cu + j], rgb[1]);
-          rgb[2] = fmaf(t, cst[C_WRGB + 256 + cu + j], rgb[2]);
-        }
-      }
-      if (S != 9 || a.img_out[9].base != nullptr) {
-        uint32_t hi[16], lo[16];
-        eng::split32<SPLIT, d.relu != 0>(f, hi, lo);
-        if constexpr (S != 9) {
-          tc::tmem_st16(T_AHI + lane_base + (uint32_t)(cu >> 1), hi);
-          if constexpr (SPLIT) tc::tmem_st16(T_ALO + lane_base + (uint32_t)(cu >> 1), lo);
-        }
-        if (a.img_out[S].base != nullptr) eng::dump32<SPLIT>(a.img_out[S], tile, row, cu, hi, lo);
-      }
+      if (a.img_out[S].base != nullptr) eng::dump32<SPLIT>(a.img_out[S], tile, row, cu, hi, lo);
     }
   }
   if constexpr (S < 9) {
@@ -325,6 +338,8 @@ template <int NSPLIT>
 __global__ void __launch_bounds__(320, 1) field_fused_fwd_kernel(const __grid_constant__ Args a) {
   using C = Cfg<NSPLIT>;
   constexpr bool SPLIT = NSPLIT == 3;
+  constexpr int A_XHI = ALay<NSPLIT>::XHI, A_XLO = ALay<NSPLIT>::XLO, A_VHI = ALay<NSPLIT>::VHI,
+                A_VLO = ALay<NSPLIT>::VLO, A_ONES = ALay<NSPLIT>::ONES;
   extern __shared__ __align__(128) uint8_t fsm[];
   uint8_t* ringp = fsm + C::OFF_RING;
   uint8_t* areg = fsm + C::OFF_A;
@@ -396,18 +411,16 @@ __global__ void __launch_bounds__(320, 1) field_fused_fwd_kernel(const __grid_co
         }
         float* dpe = a.dump_pe ? a.dump_pe + p * a.dump_pe_ld : nullptr;
         float* dped = a.dump_ped ? a.dump_ped + p * a.dump_ped_ld : nullptr;
-        if (half == 0) {          // compile-time chunk indices keep the PE column maths constant-folded
-#pragma unroll
-          for (int c = 0; c < 4; ++c)
-            pe_chunk<10, SPLIT>(x, valid, c, areg + A_XHI, areg + A_XLO, row, a.img_x, tile, dpe);
+        float e[32];
+        if (half == 0) {          // X columns 0..31 (15 sincosf) + PE(dir) (12 sincosf)
+          pe_fill32<10, 0>(x, valid, e);
+          pe_store32<SPLIT>(e, 0, 63, areg + A_XHI, areg + A_XLO, row, a.img_x, tile, dpe, valid);
+          pe_fill32<4, 0>(vd, valid, e);
+          pe_store32<SPLIT>(e, 0, 27, areg + A_VHI, areg + A_VLO, row, a.img_v, tile, dped, valid);
           *reinterpret_cast<float4*>(out_s + row * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
-        } else {
-#pragma unroll
-          for (int c = 4; c < 8; ++c)
-            pe_chunk<10, SPLIT>(x, valid, c, areg + A_XHI, areg + A_XLO, row, a.img_x, tile, dpe);
-#pragma unroll
-          for (int c = 0; c < 4; ++c)
-            pe_chunk<4, SPLIT>(vd, valid, c, areg + A_VHI, areg + A_VLO, row, a.img_v, tile, dped);
+        } else {                  // X columns 32..63 (16 sincosf)
+          pe_fill32<10, 32>(x, valid, e);
+          pe_store32<SPLIT>(e, 32, 63, areg + A_XHI, areg + A_XLO, row, a.img_x, tile, dpe, valid);
         }
         tc::fence_proxy_async();
         tc::mbar_arrive(a_ready);

@@ -104,50 +104,66 @@ __global__ void __launch_bounds__(192, 1) field_wgrad_kernel(const __grid_consta
 
   if (warp == 0) {
     if (lane == 0) {
-      uint32_t n = 0;
-      for (int tile = t0; tile < t1; ++tile)
+      // a tile's 8 slabs are contiguous in each image: one running pointer per image
+      const uint8_t* pa0 = job.a[0].base + (size_t)t0 * job.a[0].tile_bytes();
+      const uint8_t* pa1 = job.na > 1 ? job.a[1].base + (size_t)t0 * job.a[1].tile_bytes() : nullptr;
+      const uint8_t* pb0 = job.b[0].base + (size_t)t0 * job.b[0].tile_bytes();
+      const uint8_t* pb1 = job.nb > 1 ? job.b[1].base + (size_t)t0 * job.b[1].tile_bytes() : nullptr;
+      uint32_t idx = 0, ph = 0;
+      const int nslots = (t1 - t0) * 8;
 #pragma unroll 1
-        for (int ks = 0; ks < 8; ++ks, ++n) {
-          const uint32_t idx = n % C::NSLOT, ph = (n / C::NSLOT) & 1;
-          tc::mbar_wait(&empty[idx], ph ^ 1);
-          tc::mbar_arrive_expect_tx(&full[idx], slot_bytes);
-          uint8_t* dst = wsm + idx * C::SLOT_BYTES;
-          for (int i = 0; i < job.na; ++i)
-            tc::bulk_g2s(dst + offA[i], job.a[i].base + (size_t)tile * job.a[i].tile_bytes() + (size_t)ks * bytesA[i],
-                         bytesA[i], &full[idx]);
-          for (int i = 0; i < job.nb; ++i)
-            tc::bulk_g2s(dst + offB[i], job.b[i].base + (size_t)tile * job.b[i].tile_bytes() + (size_t)ks * bytesB[i],
-                         bytesB[i], &full[idx]);
-        }
+      for (int it = 0; it < nslots; ++it) {
+        tc::mbar_wait(&empty[idx], ph ^ 1);
+        tc::mbar_arrive_expect_tx(&full[idx], slot_bytes);
+        uint8_t* dst = wsm + idx * C::SLOT_BYTES;
+        tc::bulk_g2s(dst + offA[0], pa0, bytesA[0], &full[idx]); pa0 += bytesA[0];
+        if (pa1) { tc::bulk_g2s(dst + offA[1], pa1, bytesA[1], &full[idx]); pa1 += bytesA[1]; }
+        tc::bulk_g2s(dst + offB[0], pb0, bytesB[0], &full[idx]); pb0 += bytesB[0];
+        if (pb1) { tc::bulk_g2s(dst + offB[1], pb1, bytesB[1], &full[idx]); pb1 += bytesB[1]; }
+        if (++idx == C::NSLOT) { idx = 0; ph ^= 1u; }
+      }
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      uint32_t n = 0;
+      // everything that does not depend on the ring slot is hoisted: per unit the operand offsets inside
+      // a slot, the instruction descriptor and the accumulator address; per slot only the 14-bit start
+      // address field of each descriptor changes (one add)
       const uint32_t base = tc::smem_u32(wsm);
-      for (int tile = t0; tile < t1; ++tile)
+      const uint32_t full0 = tc::smem_u32(full), empty0 = tc::smem_u32(empty);
+      uint32_t ua[MAX_UNITS], ual[MAX_UNITS], ub[MAX_UNITS], ubl[MAX_UNITS], uid[MAX_UNITS], uacc[MAX_UNITS];
+#pragma unroll
+      for (int ui = 0; ui < MAX_UNITS; ++ui) {
+        const Unit& u = job.u[ui < job.nu ? ui : 0];
+        ua[ui] = offA[u.a_img] + (uint32_t)u.a_half * 4096u;      // 16 mn-groups x 256 B
+        ual[ui] = ua[ui] + job.a[u.a_img].F * 32u;
+        ub[ui] = offB[u.b_img];
+        ubl[ui] = ub[ui] + job.b[u.b_img].F * 32u;
+        uid[ui] = idesc_mn(128, (uint32_t)u.n);
+        uacc[ui] = tmem + (uint32_t)u.acc_col;
+      }
+      const int nu = job.nu;
+      uint32_t idx = 0, ph = 0, first = 0;
+      const int nslots = (t1 - t0) * 8;
 #pragma unroll 1
-        for (int ks = 0; ks < 8; ++ks, ++n) {
-          const uint32_t idx = n % C::NSLOT, ph = (n / C::NSLOT) & 1;
-          tc::mbar_wait(&full[idx], ph);
-          tc::tc_fence_after();
-          const uint32_t slot = base + idx * C::SLOT_BYTES;
-          for (int ui = 0; ui < job.nu; ++ui) {
-            const Unit& u = job.u[ui];
-            const uint32_t a_hi = slot + offA[u.a_img] + (uint32_t)u.a_half * 4096u;   // 16 mn-groups x 256 B
-            const uint32_t a_lo = a_hi + job.a[u.a_img].F * 32u;
-            const uint32_t b_hi = slot + offB[u.b_img];
-            const uint32_t b_lo = b_hi + job.b[u.b_img].F * 32u;
-            const uint32_t idesc = idesc_mn(128, (uint32_t)u.n);
-            const uint32_t acc = tmem + (uint32_t)u.acc_col;
-            const uint64_t dah = tc::smem_desc(a_hi, 128, 256), dbh = tc::smem_desc(b_hi, 128, 256);
-            tc::mma_ss(acc, dah, dbh, idesc, n > 0);
+      for (int it = 0; it < nslots; ++it) {
+        eng::mbar_wait_a(full0 + idx * 8, ph);
+        tc::tc_fence_after();
+        const uint32_t slot = base + idx * C::SLOT_BYTES;
+#pragma unroll
+        for (int ui = 0; ui < MAX_UNITS; ++ui) {
+          if (ui < nu) {
+            const uint64_t dah = eng::desc_at<128, 256>(slot + ua[ui]), dbh = eng::desc_at<128, 256>(slot + ub[ui]);
+            tc::mma_ss(uacc[ui], dah, dbh, uid[ui], first);
             if (SPLIT) {
-              tc::mma_ss(acc, tc::smem_desc(a_lo, 128, 256), dbh, idesc, 1);
-              tc::mma_ss(acc, dah, tc::smem_desc(b_lo, 128, 256), idesc, 1);
+              tc::mma_ss(uacc[ui], eng::desc_at<128, 256>(slot + ual[ui]), dbh, uid[ui], 1);
+              tc::mma_ss(uacc[ui], dah, eng::desc_at<128, 256>(slot + ubl[ui]), uid[ui], 1);
             }
           }
-          tc::tc_commit(&empty[idx]);
         }
+        first = 1;
+        eng::commit_a(empty0 + idx * 8);
+        if (++idx == C::NSLOT) { idx = 0; ph ^= 1u; }
+      }
       tc::tc_commit(acc_done);
     }
   } else {
@@ -158,11 +174,10 @@ __global__ void __launch_bounds__(192, 1) field_wgrad_kernel(const __grid_consta
     const bool do_bias = job.db != nullptr && g * 8 < FA;
     const bool do_alpha = job.dw_alpha != nullptr;
     float accb[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, acca[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    uint32_t n = 0;
+    uint32_t idx = 0, ph = 0;
     for (int tile = t0; tile < t1; ++tile)
 #pragma unroll 1
-      for (int ks = 0; ks < 8; ++ks, ++n) {
-        const uint32_t idx = n % C::NSLOT, ph = (n / C::NSLOT) & 1;
+      for (int ks = 0; ks < 8; ++ks) {
         tc::mbar_wait(&full[idx], ph);
         const uint8_t* slot = wsm + idx * C::SLOT_BYTES;
         if (do_bias || do_alpha) {
@@ -184,6 +199,7 @@ __global__ void __launch_bounds__(192, 1) field_wgrad_kernel(const __grid_consta
         }
         __syncwarp();
         if (lane == 0) tc::mbar_arrive(&empty[idx]);
+        if (++idx == C::NSLOT) { idx = 0; ph ^= 1u; }
       }
     // reduce the 4 sample sub-slices of each mn-group (lanes 4g..4g+3) and publish
 #pragma unroll

@@ -43,8 +43,8 @@ struct Plan {
   int n_stages;
 };
 
-// Kernel traits K must provide:  static constexpr Plan PLAN;  NSPLIT, NSLOT, SLOT_BYTES.
-// Requirement: PLAN.n_slabs % NSLOT == 0 (ring position of slab I is I % NSLOT in every tile).
+// Kernel traits K must provide:  static constexpr Plan PLAN;  NSPLIT, GROUP, NSLOT, SLOT_BYTES.
+// Requirement: (PLAN.n_slabs / GROUP) % NSLOT == 0 (ring position of a slab group is fixed in every tile).
 
 struct Ctx {
   uint32_t ring_addr;      // shared address of ring slot 0
@@ -84,19 +84,32 @@ __device__ __forceinline__ uint64_t desc_at(uint32_t saddr) {
   return ((uint64_t)hi << 32) | lo;
 }
 
+// bytes of slabs [I0, I1) in the weight image
+template <class K>
+__host__ __device__ constexpr uint32_t group_bytes(int i0, int i1) {
+  uint32_t b = 0;
+  for (int i = i0; i < i1; ++i) b += (uint32_t)K::PLAN.slab[i].n * 32u * (K::NSPLIT == 3 ? 2u : 1u);
+  return b;
+}
+// K::GROUP consecutive slabs share one ring slot (one expect_tx + one bulk copy, one commit): keeps the
+// per-slot issue overhead (~150 cycles) below the MMA time of the slot also in single-pass bf16
 template <class K, int I>
 __device__ __forceinline__ void producer_step(const Ctx& c, const uint8_t* __restrict__ wimg, uint32_t tp) {
-  constexpr SlabDef d = K::PLAN.slab[I];
-  constexpr int idx = I % K::NSLOT, wrap = I / K::NSLOT;
-  constexpr bool wraps_odd = ((K::PLAN.n_slabs / K::NSLOT) & 1) != 0;
-  constexpr uint32_t bytes = (uint32_t)d.n * 32u * (K::NSPLIT == 3 ? 2u : 1u);
-  constexpr uint32_t src_off = d.img_off * (K::NSPLIT == 3 ? 2u : 1u);
-  const uint32_t ph = (uint32_t)(wrap & 1) ^ (wraps_odd ? tp : 0u);
-  mbar_wait_a(c.empty_addr + idx * 8, ph ^ 1u);
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(c.full_addr + idx * 8), "r"(bytes) : "memory");
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-               ::"r"(c.ring_addr + idx * K::SLOT_BYTES), "l"(wimg + src_off), "r"(bytes), "r"(c.full_addr + idx * 8)
-               : "memory");
+  if constexpr (I % K::GROUP == 0) {
+    constexpr SlabDef d = K::PLAN.slab[I];
+    constexpr int G = I / K::GROUP;
+    constexpr int idx = G % K::NSLOT, wrap = G / K::NSLOT;
+    constexpr bool wraps_odd = (((K::PLAN.n_slabs / K::GROUP) / K::NSLOT) & 1) != 0;
+    constexpr uint32_t bytes = group_bytes<K>(I, I + K::GROUP);
+    static_assert(bytes <= (uint32_t)K::SLOT_BYTES, "slab group does not fit a ring slot");
+    constexpr uint32_t src_off = d.img_off * (K::NSPLIT == 3 ? 2u : 1u);
+    const uint32_t ph = (uint32_t)(wrap & 1) ^ (wraps_odd ? tp : 0u);
+    mbar_wait_a(c.empty_addr + idx * 8, ph ^ 1u);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(c.full_addr + idx * 8), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(c.ring_addr + idx * K::SLOT_BYTES), "l"(wimg + src_off), "r"(bytes), "r"(c.full_addr + idx * 8)
+                 : "memory");
+  }
 }
 template <class K, size_t... Is>
 __device__ __forceinline__ void producer_tile(const Ctx& c, const uint8_t* __restrict__ wimg, uint32_t tp,
@@ -114,19 +127,23 @@ template <class K, int I>
 __device__ __forceinline__ void mma_step(const Ctx& c, uint32_t tp, int tile_iter) {
   constexpr SlabDef d = K::PLAN.slab[I];
   constexpr bool SPLIT = K::NSPLIT == 3;
-  constexpr int idx = I % K::NSLOT, wrap = I / K::NSLOT;
-  constexpr bool wraps_odd = ((K::PLAN.n_slabs / K::NSLOT) & 1) != 0;
+  constexpr int G = I / K::GROUP;
+  constexpr int idx = G % K::NSLOT, wrap = G / K::NSLOT;
+  constexpr bool wraps_odd = (((K::PLAN.n_slabs / K::GROUP) / K::NSLOT) & 1) != 0;
   constexpr bool stages_odd = (K::PLAN.n_stages & 1) != 0;
+  constexpr uint32_t in_slot = group_bytes<K>(G * K::GROUP, I);   // offset of this slab inside its slot
   if constexpr ((d.flags & F_STAGE_BEGIN) != 0) {   // A operand of this stage written, accumulator drained
     mbar_wait_a(c.a_ready_addr, (uint32_t)(d.stage & 1) ^ (stages_odd ? tp : 0u));
     tc::tc_fence_after();
     dbg_stamp(c, tile_iter, d.stage, K::PLAN.n_stages, 0);
   }
-  mbar_wait_a(c.full_addr + idx * 8, (uint32_t)(wrap & 1) ^ (wraps_odd ? tp : 0u));
-  tc::tc_fence_after();
+  if constexpr (I % K::GROUP == 0) {
+    mbar_wait_a(c.full_addr + idx * 8, (uint32_t)(wrap & 1) ^ (wraps_odd ? tp : 0u));
+    tc::tc_fence_after();
+  }
   constexpr uint32_t idesc = tc::idesc_bf16_f32(TILE_M, d.n);
   constexpr uint32_t LBO_B = (uint32_t)d.n * 16u;
-  const uint32_t slot = c.ring_addr + idx * K::SLOT_BYTES;
+  const uint32_t slot = c.ring_addr + idx * K::SLOT_BYTES + in_slot;
   const uint64_t b_hi = desc_at<LBO_B, 128>(slot);
   const uint64_t b_lo = desc_at<LBO_B, 128>(slot + (uint32_t)d.n * 32u);
   const uint32_t acc = c.tmem_acc + d.acc_col;
@@ -147,7 +164,7 @@ __device__ __forceinline__ void mma_step(const Ctx& c, uint32_t tp, int tile_ite
       tc::mma_ss(acc, a_hi, b_lo, idesc, 1);
     }
   }
-  commit_a(c.empty_addr + idx * 8);
+  if constexpr (I % K::GROUP == K::GROUP - 1) commit_a(c.empty_addr + idx * 8);
   if constexpr ((d.flags & F_STAGE_END) != 0) {
     commit_a(c.acc_full_addr);
     dbg_stamp(c, tile_iter, d.stage, K::PLAN.n_stages, 1);
