@@ -250,6 +250,10 @@ int scnerf_tc_selftest(const float* A, const float* B, float* D, int32_t N, int3
  * `tiles` tiles into dev_buf[tiles][10 stages][4] (NULL disables).  Not part of the product path. */
 int scnerf_debug_timeline(long long* dev_buf, int32_t tiles);
 
+/* Diagnostics: raw tcgen05 throughput probe (cycles for iters*16 MMAs of 128x256x16 per CTA).
+ * mode 0 SS K-major, 1 TS, 2 SS MN-major/MN-major, 3 SS MN-major A + K-major B. */
+int scnerf_debug_mma_bench(int32_t mode, int32_t iters, long long* dev_out, int32_t nblocks, void* stream);
+
 /* Kernel-launch counter (bench.py's gpu_launches): number of kernels this library has launched
  * in this process since the last reset. */
 int64_t scnerf_launch_count(int32_t reset);

@@ -90,6 +90,7 @@ SIGNATURES = {
     "scnerf_built_for_sm": (_I, []),
     "scnerf_device_sm": (_I, []),
     "scnerf_launch_count": (_I64, [C.c_int32]),
+    "scnerf_debug_mma_bench": (_I, [C.c_int32, C.c_int32, vp, C.c_int32, vp]),
     "scnerf_debug_timeline": (_I, [vp, C.c_int32]),
     "scnerf_tc_selftest": (_I, [vp, vp, vp, C.c_int32, C.c_int32, C.c_int32, vp, _SZ, vp]),
     "scnerf_searchsorted_f32": (_I, [vp, vp, vp, _I64, _I64, _I64, _I64, _I, vp]),

@@ -32,6 +32,10 @@ int64_t scnerf_launch_count(int32_t reset) {
   return v;
 }
 
+int scnerf_debug_mma_bench(int32_t mode, int32_t iters, long long* dev_out, int32_t nblocks, void* stream) {
+  return tc_mma_bench(mode, iters, dev_out, nblocks, stream);
+}
+
 int scnerf_debug_timeline(long long* dev_buf, int32_t tiles) {
   tc_dbg_ptr() = dev_buf;
   tc_dbg_tiles() = tiles;

@@ -132,6 +132,53 @@ __global__ void __launch_bounds__(128) tc_selftest_kernel(const uint8_t* __restr
   if (warp == 0) tc::tmem_dealloc(tmem, ncols);
 }
 
+// Tensor-pipe throughput probe: every CTA issues `iters` x 16 MMAs (M=128, N=256, K=16) on fixed
+// (uninitialised) operands and reports cycles per MMA.  mode 0: SS K-major (forward X/V slabs),
+// 1: TS (A in TMEM), 2: SS with both operands MN-major in the wgrad slab layout (LBO 128, SBO 256),
+// 3: SS MN-major A + K-major B.
+__global__ void __launch_bounds__(128) tc_mma_bench_kernel(int mode, int iters, long long* out) {
+  extern __shared__ __align__(1024) uint8_t tc_smem[];
+  __shared__ __align__(8) uint64_t bar;
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  if (tid == 0) { tc::mbar_init(&bar, 1); tc::fence_mbar_init(); }
+  for (int i = tid; i < 32768 / 4; i += 128) reinterpret_cast<uint32_t*>(tc_smem)[i] = 0x3c003c00u;
+  tc::fence_proxy_async();
+  __syncthreads();
+  if (warp == 0) tc::tmem_alloc(&tmem_base_s, 512);
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem = tmem_base_s;
+  if (tid == 0) {
+    const uint32_t sa = tc::smem_u32(tc_smem), sb = sa + 16384;
+    const uint32_t idk = tc::idesc_bf16_f32(128, 256);
+    const uint32_t idmn = idk | (1u << 15) | (1u << 16), idamn = idk | (1u << 15);
+    const long long t0 = clock64();
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        if (mode == 0) tc::mma_ss(tmem, eng::desc_at<2048, 128>(sa), eng::desc_at<4096, 128>(sb), idk, 1);
+        else if (mode == 1) tc::mma_ts(tmem, tmem + 256 + (j & 7) * 8, eng::desc_at<4096, 128>(sb), idk, 1);
+        else if (mode == 2) tc::mma_ss(tmem, eng::desc_at<128, 256>(sa), eng::desc_at<128, 256>(sb), idmn, 1);
+        else tc::mma_ss(tmem, eng::desc_at<128, 256>(sa), eng::desc_at<4096, 128>(sb), idamn, 1);
+      }
+    }
+    tc::tc_commit(&bar);
+    tc::mbar_wait(&bar, 0);
+    const long long t1 = clock64();
+    out[blockIdx.x] = t1 - t0;
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tc::tmem_dealloc(tmem, 512);
+}
+inline int tc_mma_bench(int mode, int iters, long long* out, int nblocks, void* stream) {
+  SCNERF_CUDA(cudaFuncSetAttribute(tc_mma_bench_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 32768));
+  SCNERF_LAUNCH(tc_mma_bench_kernel, nblocks, 128, 32768, stream, mode, iters, out);
+  return 0;
+}
+
 // host side of the self-test: A[128,K], B[N,K] fp32 row-major -> D[128,N] fp32
 inline int tc_selftest(const float* A, const float* B, float* D, int N, int K, int variant,
                        void* workspace, size_t workspace_bytes, void* stream) {

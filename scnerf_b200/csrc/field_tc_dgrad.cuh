@@ -126,6 +126,23 @@ __device__ __forceinline__ void relu_mask32(const eng::ImgDump& img, int tile, u
   }
 }
 
+// bit j of the result = (h[c0 + j] > 0): 4 x 16-byte loads from the forward image (hi half) of sample k
+__device__ __forceinline__ uint32_t relu_bits32(const eng::ImgDump& img, int tile, uint32_t k, uint32_t c0) {
+  const uint8_t* p = img.chunk(tile, k, c0, 0);
+  uint32_t bits = 0;
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    const uint4 h = *reinterpret_cast<const uint4*>(p + g * 256);
+    const uint32_t w[4] = {h.x, h.y, h.z, h.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      bits |= ((w[e] & 0x0000ffffu) != 0u ? 1u : 0u) << (8 * g + 2 * e);
+      bits |= ((w[e] & 0xffff0000u) != 0u ? 1u : 0u) << (8 * g + 2 * e + 1);
+    }
+  }
+  return bits;
+}
+
 template <int NSPLIT>
 __global__ void __launch_bounds__(320, 1) field_fused_dgrad_kernel(const __grid_constant__ Args a) {
   using C = Cfg<NSPLIT>;
@@ -200,6 +217,28 @@ __global__ void __launch_bounds__(320, 1) field_fused_dgrad_kernel(const __grid_
       }
 #pragma unroll 1
       for (int s = 0; s < NSTAGE; ++s, ++m) {
+        // stage -> (mask image, output image); by value: taking the address of a kernel parameter would
+        // spill the whole struct to local memory
+        eng::ImgDump mask{}, outd{};
+        switch (s) {
+          case 0: outd = a.out_dfeat; break;                        // g_feat: feature_linear has no ReLU
+          case 1: mask = a.img_h[7]; outd = a.out_dz[7]; break;
+          case 2: mask = a.img_h[6]; outd = a.out_dz[6]; break;
+          case 3: mask = a.img_h[5]; outd = a.out_dz[5]; break;
+          case 5: mask = a.img_h[4]; outd = a.out_dz[4]; break;
+          case 6: mask = a.img_h[3]; outd = a.out_dz[3]; break;
+          case 7: mask = a.img_h[2]; outd = a.out_dz[2]; break;
+          case 8: mask = a.img_h[1]; outd = a.out_dz[1]; break;
+          case 9: mask = a.img_h[0]; outd = a.out_dz[0]; break;
+          default: break;                                            // 4, 10: d(PE) stages
+        }
+        // ReLU masks of this warp's 128 columns are fetched BEFORE waiting for the accumulator, i.e.
+        // under the MMA phase of this stage
+        uint32_t mk[4] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};
+        if (mask.base) {
+#pragma unroll
+          for (int cc = 0; cc < 4; ++cc) mk[cc] = relu_bits32(mask, tile, row, half * 128 + cc * 32);
+        }
         tc::mbar_wait(acc_full, m & 1);
         tc::tc_fence_after();
         if (s == 4 || s == 10) {
@@ -241,20 +280,6 @@ __global__ void __launch_bounds__(320, 1) field_fused_dgrad_kernel(const __grid_
           continue;
         }
         // ---- 256-wide stages: this warp owns 128 columns = 4 chunks
-        // stage -> (mask image, output image)
-        // (by value: taking the address of a kernel parameter would spill the whole struct to local memory)
-        eng::ImgDump mask{}, outd{};
-        switch (s) {
-          case 0: outd = a.out_dfeat; break;                        // g_feat: feature_linear has no ReLU
-          case 1: mask = a.img_h[7]; outd = a.out_dz[7]; break;
-          case 2: mask = a.img_h[6]; outd = a.out_dz[6]; break;
-          case 3: mask = a.img_h[5]; outd = a.out_dz[5]; break;
-          case 5: mask = a.img_h[4]; outd = a.out_dz[4]; break;
-          case 6: mask = a.img_h[3]; outd = a.out_dz[3]; break;
-          case 7: mask = a.img_h[2]; outd = a.out_dz[2]; break;
-          case 8: mask = a.img_h[1]; outd = a.out_dz[1]; break;
-          default: mask = a.img_h[0]; outd = a.out_dz[0]; break;    // s == 9
-        }
         if (s == 0 && half == 1) {
           // d(PE(dir)) lives in ACC2: read it before this warp's stores overwrite those TMEM columns
           uint32_t v[32];
@@ -277,31 +302,27 @@ __global__ void __launch_bounds__(320, 1) field_fused_dgrad_kernel(const __grid_
           }
           if (valid) { a.g_vd[p * 3] = gv[0]; a.g_vd[p * 3 + 1] = gv[1]; a.g_vd[p * 3 + 2] = gv[2]; }
         }
-#pragma unroll 1
-        for (int cc = 0; cc < 4; cc += 2) {
-          uint32_t v0[32], v1[32];
-          const int c0 = half * 128 + cc * 32, c1 = c0 + 32;
-          tc::tmem_ld32(T_ACC + lane_base + c0, v0);
-          tc::tmem_ld32(T_ACC + lane_base + c1, v1);
-          tc::tmem_ld_wait();
+        uint32_t v[4][32];
 #pragma unroll
-          for (int u = 0; u < 2; ++u) {
-            const uint32_t (&v)[32] = u ? v1 : v0;
-            const int cu = u ? c1 : c0;
-            float f[32];
+        for (int cc = 0; cc < 4; ++cc) tc::tmem_ld32(T_ACC + lane_base + half * 128 + cc * 32, v[cc]);
+        tc::tmem_ld_wait();
 #pragma unroll
-            for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-            if (s == 1) {   // alpha head: g_h7 += g_alpha * w_alpha
+        for (int cc = 0; cc < 4; ++cc) {
+          const int cu = half * 128 + cc * 32;
+          float f[32];
 #pragma unroll
-              for (int j = 0; j < 32; ++j) f[j] = fmaf(gr.w, cst[fused::C_WALPHA + cu + j], f[j]);
-            }
-            if (mask.base) relu_mask32(mask, tile, row, cu, f);
-            uint32_t hi[16], lo[16];
-            eng::split32<SPLIT, false>(f, hi, lo);
-            tc::tmem_st16(T_AHI + lane_base + (uint32_t)(cu >> 1), hi);
-            if (SPLIT) tc::tmem_st16(T_ALO + lane_base + (uint32_t)(cu >> 1), lo);
-            eng::dump32<SPLIT>(outd, tile, row, cu, hi, lo);
+          for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[cc][j]);
+          if (s == 1) {   // alpha head: g_h7 += g_alpha * w_alpha
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] = fmaf(gr.w, cst[fused::C_WALPHA + cu + j], f[j]);
           }
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = ((mk[cc] >> j) & 1u) ? f[j] : 0.f;
+          uint32_t hi[16], lo[16];
+          eng::split32<SPLIT, false>(f, hi, lo);
+          tc::tmem_st16(T_AHI + lane_base + (uint32_t)(cu >> 1), hi);
+          if (SPLIT) tc::tmem_st16(T_ALO + lane_base + (uint32_t)(cu >> 1), lo);
+          eng::dump32<SPLIT>(outd, tile, row, cu, hi, lo);
         }
         tc::tmem_st_wait();
         tc::tc_fence_before();
