@@ -209,7 +209,6 @@ __global__ void __launch_bounds__(320, 1) field_fused_dgrad_kernel(const __grid_
           eng::split32<SPLIT, false>(f, hi, lo);
           tc::tmem_st16(T_AHI + lane_base + (uint32_t)(c0 >> 1), hi);
           if (SPLIT) tc::tmem_st16(T_ALO + lane_base + (uint32_t)(c0 >> 1), lo);
-          eng::dump32<SPLIT>(a.out_dzv, tile, row, c0, hi, lo);
         }
         tc::tmem_st_wait();
         tc::tc_fence_before();
@@ -231,6 +230,21 @@ __global__ void __launch_bounds__(320, 1) field_fused_dgrad_kernel(const __grid_
           case 8: mask = a.img_h[1]; outd = a.out_dz[1]; break;
           case 9: mask = a.img_h[0]; outd = a.out_dz[0]; break;
           default: break;                                            // 4, 10: d(PE) stages
+        }
+        // this stage's A operand (TMEM) is a dZ the wgrad kernel needs: write its tile image now, under
+        // the MMA phase (off the critical path)
+        switch (s) {
+          case 0: eng::dump_from_tmem<SPLIT, 2>(a.out_dzv, tile, row, T_AHI, T_ALO, lane_base, half * 64); break;
+          case 1: eng::dump_from_tmem<SPLIT, 4>(a.out_dfeat, tile, row, T_AHI, T_ALO, lane_base, half * 128); break;
+          case 2: eng::dump_from_tmem<SPLIT, 4>(a.out_dz[7], tile, row, T_AHI, T_ALO, lane_base, half * 128); break;
+          case 3: eng::dump_from_tmem<SPLIT, 4>(a.out_dz[6], tile, row, T_AHI, T_ALO, lane_base, half * 128); break;
+          case 4: eng::dump_from_tmem<SPLIT, 4>(a.out_dz[5], tile, row, T_AHI, T_ALO, lane_base, half * 128); break;
+          case 6: eng::dump_from_tmem<SPLIT, 4>(a.out_dz[4], tile, row, T_AHI, T_ALO, lane_base, half * 128); break;
+          case 7: eng::dump_from_tmem<SPLIT, 4>(a.out_dz[3], tile, row, T_AHI, T_ALO, lane_base, half * 128); break;
+          case 8: eng::dump_from_tmem<SPLIT, 4>(a.out_dz[2], tile, row, T_AHI, T_ALO, lane_base, half * 128); break;
+          case 9: eng::dump_from_tmem<SPLIT, 4>(a.out_dz[1], tile, row, T_AHI, T_ALO, lane_base, half * 128); break;
+          case 10: eng::dump_from_tmem<SPLIT, 4>(a.out_dz[0], tile, row, T_AHI, T_ALO, lane_base, half * 128); break;
+          default: break;   // 5 (S5b): A is still dZ5
         }
         // ReLU masks of this warp's 128 columns are fetched BEFORE waiting for the accumulator, i.e.
         // under the MMA phase of this stage
@@ -322,7 +336,6 @@ __global__ void __launch_bounds__(320, 1) field_fused_dgrad_kernel(const __grid_
           eng::split32<SPLIT, false>(f, hi, lo);
           tc::tmem_st16(T_AHI + lane_base + (uint32_t)(cu >> 1), hi);
           if (SPLIT) tc::tmem_st16(T_ALO + lane_base + (uint32_t)(cu >> 1), lo);
-          eng::dump32<SPLIT>(outd, tile, row, cu, hi, lo);
         }
         tc::tmem_st_wait();
         tc::tc_fence_before();

@@ -275,6 +275,12 @@ __device__ __forceinline__ void epi_stage(const Args& a, const float* cst, uint3
   constexpr StageDef d = stage_def(S);
   constexpr int nchunk = d.N / 64;           // 32-column chunks owned by this warp
   const int cbase = half * (d.N / 2);
+  if constexpr (S >= 1) {
+    // training: the previous stage's output (this stage's A operand, in TMEM) goes to its tile image now,
+    // under this stage's MMA phase
+    if (a.img_out[S - 1].base != nullptr)
+      eng::dump_from_tmem<SPLIT, 4>(a.img_out[S - 1], tile, row, T_AHI, T_ALO, lane_base, half * 128);
+  }
   eng::mbar_wait_a(acc_full_addr, (uint32_t)(S & 1));    // 10 stages per tile (even): parity = S & 1
   tc::tc_fence_after();
   if (threadIdx.x == 64) eng::dbg_stamp(ctx, tile_iter, S, NSTAGE, 2);
@@ -314,7 +320,9 @@ __device__ __forceinline__ void epi_stage(const Args& a, const float* cst, uint3
         tc::tmem_st16(T_AHI + lane_base + (uint32_t)(cu >> 1), hi);
         if constexpr (SPLIT) tc::tmem_st16(T_ALO + lane_base + (uint32_t)(cu >> 1), lo);
       }
-      if (a.img_out[S].base != nullptr) eng::dump32<SPLIT>(a.img_out[S], tile, row, cu, hi, lo);
+      if constexpr (S == 9) {
+        if (a.img_out[9].base != nullptr) eng::dump32<SPLIT>(a.img_out[9], tile, row, cu, hi, lo);
+      }
     }
   }
   if constexpr (S < 9) {

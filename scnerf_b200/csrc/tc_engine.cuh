@@ -241,5 +241,22 @@ __device__ __forceinline__ void dump32(const ImgDump& d, int tile, uint32_t k, u
   }
 }
 
+// Dump `nchunk` x 32 features starting at feature c0 of this thread's row straight from the TMEM A
+// operand (packed bf16 pairs: hi region [+ lo region]) into a tile image.  Called by the epilogue warps
+// while the tensor pipe runs the NEXT stage, so the HBM stores are off the stage's critical path.
+template <bool SPLIT, int NCHUNK>
+__device__ __forceinline__ void dump_from_tmem(const ImgDump& d, int tile, uint32_t row, uint32_t t_ahi,
+                                               uint32_t t_alo, uint32_t lane_base, uint32_t c0) {
+  uint32_t hi[NCHUNK][16], lo[NCHUNK][16];
+#pragma unroll
+  for (int cc = 0; cc < NCHUNK; ++cc) {
+    tc::tmem_ld16(t_ahi + lane_base + ((c0 + cc * 32) >> 1), hi[cc]);
+    if (SPLIT) tc::tmem_ld16(t_alo + lane_base + ((c0 + cc * 32) >> 1), lo[cc]);
+  }
+  tc::tmem_ld_wait();
+#pragma unroll
+  for (int cc = 0; cc < NCHUNK; ++cc) dump32<SPLIT>(d, tile, row, c0 + cc * 32, hi[cc], lo[cc]);
+}
+
 }  // namespace eng
 }  // namespace scnerf
