@@ -390,6 +390,11 @@ inline int field_tc_bwd_impl(const scnerf_mlp& m, const scnerf_mlp& g, const flo
   wgrad::Args w{};
   w.num_tiles = T; w.P = P;
   w.nslices = std::max(1, device_sm_count() / wgrad::NJOBS);
+  {
+    static int pf = -1;   // tuning knob (default off: measured slower on B200, profiles/README.md)
+    if (pf < 0) { const char* e = getenv("SCNERF_WGRAD_L2_PREFETCH"); pf = e ? atoi(e) : 0; }
+    w.l2_prefetch_slots = pf;
+  }
   auto std_job = [&](wgrad::Job& J, const eng::ImgDump& A, const eng::ImgDump& Bi, float* dW, int ld, int col0,
                      int cols_valid, float* db) {
     J.a[0] = A; J.na = 1; J.b[0] = Bi; J.nb = 1; J.nu = 2; J.db = db;

@@ -42,6 +42,7 @@ struct Args {
   Job job[NJOBS];
   int num_tiles, nslices;
   int64_t P;
+  int l2_prefetch_slots;   // 0 = off
 };
 
 template <int NSPLIT> struct Cfg {
@@ -114,7 +115,7 @@ __global__ void __launch_bounds__(192, 1) field_wgrad_kernel(const __grid_consta
       // The TMA unit keeps only ~16 KB of requests outstanding per SM, so copies that miss L2 stream at
       // ~11 B/clk/SM (2.7 TB/s chip-wide, measured).  L2 prefetches are fire-and-forget: run them PF
       // slots ahead so the bulk copies themselves hit L2.
-      constexpr int PF = 16;
+      const int PF = ap->l2_prefetch_slots;
       for (int it = 0; it < min(PF, nslots); ++it) {
         tc::bulk_prefetch_l2(pa0 + (size_t)it * bytesA[0], bytesA[0]);
         if (pa1) tc::bulk_prefetch_l2(pa1 + (size_t)it * bytesA[1], bytesA[1]);
@@ -123,7 +124,7 @@ __global__ void __launch_bounds__(192, 1) field_wgrad_kernel(const __grid_consta
       }
 #pragma unroll 1
       for (int it = 0; it < nslots; ++it) {
-        if (it + PF < nslots) {
+        if (PF > 0 && it + PF < nslots) {
           tc::bulk_prefetch_l2(pa0 + (size_t)PF * bytesA[0], bytesA[0]);
           if (pa1) tc::bulk_prefetch_l2(pa1 + (size_t)PF * bytesA[1], bytesA[1]);
           tc::bulk_prefetch_l2(pb0 + (size_t)PF * bytesB[0], bytesB[0]);
