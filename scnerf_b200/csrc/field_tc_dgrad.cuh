@@ -127,12 +127,13 @@ __device__ __forceinline__ void relu_mask32(const eng::ImgDump& img, int tile, u
 }
 
 // bit j of the result = (h[c0 + j] > 0): 4 x 16-byte loads from the forward image (hi half) of sample k
-__device__ __forceinline__ uint32_t relu_bits32(const eng::ImgDump& img, int tile, uint32_t k, uint32_t c0) {
+__device__ __forceinline__ uint32_t relu_bits32(const eng::ImgDump& img, int tile, uint32_t k, uint32_t c0,
+                                                uint64_t pol) {
   const uint8_t* p = img.chunk(tile, k, c0, 0);
   uint32_t bits = 0;
 #pragma unroll
   for (int g = 0; g < 4; ++g) {
-    const uint4 h = *reinterpret_cast<const uint4*>(p + g * 256);
+    const uint4 h = tc::ld_v4_hint(p + g * 256, pol);
     const uint32_t w[4] = {h.x, h.y, h.z, h.w};
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
@@ -178,6 +179,7 @@ __global__ void __launch_bounds__(320, 1) field_fused_dgrad_kernel(const __grid_
   ctx.acc_full_addr = tc::smem_u32(acc_full); ctx.a_ready_addr = tc::smem_u32(a_ready);
   ctx.tmem_acc = T_ACC; ctx.tmem_ahi = T_AHI; ctx.tmem_alo = T_ALO; ctx.smem_a = 0;
   ctx.dbg = nullptr; ctx.dbg_tiles = 0;
+  ctx.pol_keep = tc::policy_evict_last(); ctx.pol_stream = tc::policy_evict_first();
 
   if (warp == 0) {
     if (lane == 0) eng::producer_loop<C>(ctx, a.wimg, a.num_tiles);
@@ -234,16 +236,16 @@ __global__ void __launch_bounds__(320, 1) field_fused_dgrad_kernel(const __grid_
         // this stage's A operand (TMEM) is a dZ the wgrad kernel needs: write its tile image now, under
         // the MMA phase (off the critical path)
         switch (s) {
-          case 0: eng::dump_from_tmem<SPLIT, 2>(a.out_dzv, tile, row, T_AHI, T_ALO, lane_base, half * 64); break;
-          case 1: eng::dump_from_tmem<SPLIT, 4>(a.out_dfeat, tile, row, T_AHI, T_ALO, lane_base, half * 128); break;
-          case 2: eng::dump_from_tmem<SPLIT, 4>(a.out_dz[7], tile, row, T_AHI, T_ALO, lane_base, half * 128); break;
-          case 3: eng::dump_from_tmem<SPLIT, 4>(a.out_dz[6], tile, row, T_AHI, T_ALO, lane_base, half * 128); break;
-          case 4: eng::dump_from_tmem<SPLIT, 4>(a.out_dz[5], tile, row, T_AHI, T_ALO, lane_base, half * 128); break;
-          case 6: eng::dump_from_tmem<SPLIT, 4>(a.out_dz[4], tile, row, T_AHI, T_ALO, lane_base, half * 128); break;
-          case 7: eng::dump_from_tmem<SPLIT, 4>(a.out_dz[3], tile, row, T_AHI, T_ALO, lane_base, half * 128); break;
-          case 8: eng::dump_from_tmem<SPLIT, 4>(a.out_dz[2], tile, row, T_AHI, T_ALO, lane_base, half * 128); break;
-          case 9: eng::dump_from_tmem<SPLIT, 4>(a.out_dz[1], tile, row, T_AHI, T_ALO, lane_base, half * 128); break;
-          case 10: eng::dump_from_tmem<SPLIT, 4>(a.out_dz[0], tile, row, T_AHI, T_ALO, lane_base, half * 128); break;
+          case 0: eng::dump_from_tmem<SPLIT, 2>(a.out_dzv, tile, row, T_AHI, T_ALO, lane_base, half * 64, ctx.pol_stream); break;
+          case 1: eng::dump_from_tmem<SPLIT, 4>(a.out_dfeat, tile, row, T_AHI, T_ALO, lane_base, half * 128, ctx.pol_stream); break;
+          case 2: eng::dump_from_tmem<SPLIT, 4>(a.out_dz[7], tile, row, T_AHI, T_ALO, lane_base, half * 128, ctx.pol_stream); break;
+          case 3: eng::dump_from_tmem<SPLIT, 4>(a.out_dz[6], tile, row, T_AHI, T_ALO, lane_base, half * 128, ctx.pol_stream); break;
+          case 4: eng::dump_from_tmem<SPLIT, 4>(a.out_dz[5], tile, row, T_AHI, T_ALO, lane_base, half * 128, ctx.pol_stream); break;
+          case 6: eng::dump_from_tmem<SPLIT, 4>(a.out_dz[4], tile, row, T_AHI, T_ALO, lane_base, half * 128, ctx.pol_stream); break;
+          case 7: eng::dump_from_tmem<SPLIT, 4>(a.out_dz[3], tile, row, T_AHI, T_ALO, lane_base, half * 128, ctx.pol_stream); break;
+          case 8: eng::dump_from_tmem<SPLIT, 4>(a.out_dz[2], tile, row, T_AHI, T_ALO, lane_base, half * 128, ctx.pol_stream); break;
+          case 9: eng::dump_from_tmem<SPLIT, 4>(a.out_dz[1], tile, row, T_AHI, T_ALO, lane_base, half * 128, ctx.pol_stream); break;
+          case 10: eng::dump_from_tmem<SPLIT, 4>(a.out_dz[0], tile, row, T_AHI, T_ALO, lane_base, half * 128, ctx.pol_stream); break;
           default: break;   // 5 (S5b): A is still dZ5
         }
         // ReLU masks of this warp's 128 columns are fetched BEFORE waiting for the accumulator, i.e.
@@ -251,7 +253,7 @@ __global__ void __launch_bounds__(320, 1) field_fused_dgrad_kernel(const __grid_
         uint32_t mk[4] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};
         if (mask.base) {
 #pragma unroll
-          for (int cc = 0; cc < 4; ++cc) mk[cc] = relu_bits32(mask, tile, row, half * 128 + cc * 32);
+          for (int cc = 0; cc < 4; ++cc) mk[cc] = relu_bits32(mask, tile, row, half * 128 + cc * 32, ctx.pol_stream);
         }
         tc::mbar_wait(acc_full, m & 1);
         tc::tc_fence_after();

@@ -272,7 +272,7 @@ __device__ __forceinline__ void pe_fill32(const float (&x)[3], bool valid, float
 template <bool SPLIT>
 __device__ __forceinline__ void pe_store32(const float (&e)[32], int lo_col, int ncols_valid, uint8_t* hi_img,
                                            uint8_t* lo_img, int row, const eng::ImgDump& img, int tile,
-                                           float* dump, bool valid) {
+                                           float* dump, bool valid, uint64_t pol) {
   uint32_t hi[16], lo[16];
   eng::split32<SPLIT, false>(e, hi, lo);
 #pragma unroll
@@ -281,7 +281,7 @@ __device__ __forceinline__ void pe_store32(const float (&e)[32], int lo_col, int
     *reinterpret_cast<uint4*>(hi_img + off) = make_uint4(hi[4 * g], hi[4 * g + 1], hi[4 * g + 2], hi[4 * g + 3]);
     if (SPLIT) *reinterpret_cast<uint4*>(lo_img + off) = make_uint4(lo[4 * g], lo[4 * g + 1], lo[4 * g + 2], lo[4 * g + 3]);
   }
-  if (img.base) eng::dump32<SPLIT>(img, tile, row, lo_col, hi, lo);
+  if (img.base) eng::dump32<SPLIT>(img, tile, row, lo_col, hi, lo, pol);
   if (dump && valid) {
 #pragma unroll
     for (int i = 0; i < 32; ++i)
@@ -303,7 +303,7 @@ __device__ __forceinline__ void epi_stage(const Args& a, const float* cst, uint3
     // training: the previous stage's output (this stage's A operand, in TMEM) goes to its tile image now,
     // under this stage's MMA phase
     if (a.img_out[S - 1].base != nullptr)
-      eng::dump_from_tmem<SPLIT, 4>(a.img_out[S - 1], tile, row, T_AHI, T_ALO, lane_base, half * 128);
+      eng::dump_from_tmem<SPLIT, 4>(a.img_out[S - 1], tile, row, T_AHI, T_ALO, lane_base, half * 128, ctx.pol_stream);
   }
   eng::mbar_wait_a(acc_full_addr, (uint32_t)(S & 1));    // 10 stages per tile (even): parity = S & 1
   tc::tc_fence_after();
@@ -345,7 +345,7 @@ __device__ __forceinline__ void epi_stage(const Args& a, const float* cst, uint3
         if constexpr (SPLIT) tc::tmem_st16(T_ALO + lane_base + (uint32_t)(cu >> 1), lo);
       }
       if constexpr (S == 9) {
-        if (a.img_out[9].base != nullptr) eng::dump32<SPLIT>(a.img_out[9], tile, row, cu, hi, lo);
+        if (a.img_out[9].base != nullptr) eng::dump32<SPLIT>(a.img_out[9], tile, row, cu, hi, lo, ctx.pol_stream);
       }
     }
   }
@@ -409,6 +409,7 @@ __global__ void __launch_bounds__(320, 1) field_fused_fwd_kernel(const __grid_co
   ctx.acc_full_addr = tc::smem_u32(acc_full); ctx.a_ready_addr = tc::smem_u32(a_ready);
   ctx.tmem_acc = T_ACC; ctx.tmem_ahi = T_AHI; ctx.tmem_alo = T_ALO; ctx.smem_a = tc::smem_u32(areg);
   ctx.dbg = a.dbg; ctx.dbg_tiles = a.dbg_tiles;
+  ctx.pol_keep = tc::policy_evict_last(); ctx.pol_stream = tc::policy_evict_first();
 
   if (warp == 0) {
     if (lane == 0) eng::producer_loop<C>(ctx, a.wimg, a.num_tiles);
@@ -446,13 +447,13 @@ __global__ void __launch_bounds__(320, 1) field_fused_fwd_kernel(const __grid_co
         float e[32];
         if (half == 0) {          // X columns 0..31 (15 sincosf) + PE(dir) (12 sincosf)
           pe_fill32<10, 0>(x, valid, e);
-          pe_store32<SPLIT>(e, 0, 63, areg + A_XHI, areg + A_XLO, row, a.img_x, tile, dpe, valid);
+          pe_store32<SPLIT>(e, 0, 63, areg + A_XHI, areg + A_XLO, row, a.img_x, tile, dpe, valid, ctx.pol_stream);
           pe_fill32<4, 0>(vd, valid, e);
-          pe_store32<SPLIT>(e, 0, 27, areg + A_VHI, areg + A_VLO, row, a.img_v, tile, dped, valid);
+          pe_store32<SPLIT>(e, 0, 27, areg + A_VHI, areg + A_VLO, row, a.img_v, tile, dped, valid, ctx.pol_stream);
           *reinterpret_cast<float4*>(out_s + row * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
         } else {                  // X columns 32..63 (16 sincosf)
           pe_fill32<10, 32>(x, valid, e);
-          pe_store32<SPLIT>(e, 32, 63, areg + A_XHI, areg + A_XLO, row, a.img_x, tile, dpe, valid);
+          pe_store32<SPLIT>(e, 32, 63, areg + A_XHI, areg + A_XLO, row, a.img_x, tile, dpe, valid, ctx.pol_stream);
         }
         tc::fence_proxy_async();
         tc::mbar_arrive(a_ready);

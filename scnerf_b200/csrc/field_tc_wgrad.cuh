@@ -112,6 +112,7 @@ __global__ void __launch_bounds__(192, 1) field_wgrad_kernel(const __grid_consta
       const uint8_t* pb1 = job.nb > 1 ? job.b[1].base + (size_t)t0 * job.b[1].tile_bytes() : nullptr;
       uint32_t idx = 0, ph = 0;
       const int nslots = (t1 - t0) * 8;
+      const uint64_t pol = tc::policy_evict_first();   // read-once streams: do not displace the weights in L2
       // The TMA unit keeps only ~16 KB of requests outstanding per SM, so copies that miss L2 stream at
       // ~11 B/clk/SM (2.7 TB/s chip-wide, measured).  L2 prefetches are fire-and-forget: run them PF
       // slots ahead so the bulk copies themselves hit L2.
@@ -133,10 +134,11 @@ __global__ void __launch_bounds__(192, 1) field_wgrad_kernel(const __grid_consta
         tc::mbar_wait(&empty[idx], ph ^ 1);
         tc::mbar_arrive_expect_tx(&full[idx], slot_bytes);
         uint8_t* dst = wsm + idx * C::SLOT_BYTES;
-        tc::bulk_g2s(dst + offA[0], pa0, bytesA[0], &full[idx]); pa0 += bytesA[0];
-        if (pa1) { tc::bulk_g2s(dst + offA[1], pa1, bytesA[1], &full[idx]); pa1 += bytesA[1]; }
-        tc::bulk_g2s(dst + offB[0], pb0, bytesB[0], &full[idx]); pb0 += bytesB[0];
-        if (pb1) { tc::bulk_g2s(dst + offB[1], pb1, bytesB[1], &full[idx]); pb1 += bytesB[1]; }
+        const uint32_t d32 = tc::smem_u32(dst), fb = tc::smem_u32(&full[idx]);
+        tc::bulk_g2s_hint(d32 + offA[0], pa0, bytesA[0], fb, pol); pa0 += bytesA[0];
+        if (pa1) { tc::bulk_g2s_hint(d32 + offA[1], pa1, bytesA[1], fb, pol); pa1 += bytesA[1]; }
+        tc::bulk_g2s_hint(d32 + offB[0], pb0, bytesB[0], fb, pol); pb0 += bytesB[0];
+        if (pb1) { tc::bulk_g2s_hint(d32 + offB[1], pb1, bytesB[1], fb, pol); pb1 += bytesB[1]; }
         if (++idx == C::NSLOT) { idx = 0; ph ^= 1u; }
       }
     }

@@ -53,6 +53,8 @@ struct Ctx {
   uint32_t acc_full_addr, a_ready_addr;
   uint32_t tmem_acc, tmem_ahi, tmem_alo;
   uint32_t smem_a;         // shared address of the smem A area
+  uint64_t pol_keep;       // L2 evict_last  (weight slabs: re-read by every SM for every tile)
+  uint64_t pol_stream;     // L2 evict_first (write-once / read-once tile images)
   long long* dbg;          // optional timeline (CTA 0 only): [tile][stage][4] clock64 stamps
                            //   0: MMA thread passed a_ready   1: MMA thread issued the stage's last commit
                            //   2: epilogue (warp 2) saw acc_full   3: epilogue (warp 2) arrived on a_ready
@@ -106,9 +108,7 @@ __device__ __forceinline__ void producer_step(const Ctx& c, const uint8_t* __res
     const uint32_t ph = (uint32_t)(wrap & 1) ^ (wraps_odd ? tp : 0u);
     mbar_wait_a(c.empty_addr + idx * 8, ph ^ 1u);
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(c.full_addr + idx * 8), "r"(bytes) : "memory");
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(c.ring_addr + idx * K::SLOT_BYTES), "l"(wimg + src_off), "r"(bytes), "r"(c.full_addr + idx * 8)
-                 : "memory");
+    tc::bulk_g2s_hint(c.ring_addr + idx * K::SLOT_BYTES, wimg + src_off, bytes, c.full_addr + idx * 8, c.pol_keep);
   }
 }
 template <class K, size_t... Is>
@@ -230,14 +230,13 @@ struct ImgDump {
 // store 32 consecutive features [c0, c0+32) of sample k (packed pairs) into the image
 template <bool SPLIT>
 __device__ __forceinline__ void dump32(const ImgDump& d, int tile, uint32_t k, uint32_t c0,
-                                       const uint32_t (&hi)[16], const uint32_t (&lo)[16]) {
+                                       const uint32_t (&hi)[16], const uint32_t (&lo)[16], uint64_t pol) {
   uint8_t* p = d.chunk(tile, k, c0, 0);
 #pragma unroll
   for (int g = 0; g < 4; ++g) {
-    *reinterpret_cast<uint4*>(p + g * 256) = make_uint4(hi[4 * g], hi[4 * g + 1], hi[4 * g + 2], hi[4 * g + 3]);
+    tc::st_v4_hint(p + g * 256, make_uint4(hi[4 * g], hi[4 * g + 1], hi[4 * g + 2], hi[4 * g + 3]), pol);
     if (SPLIT && d.nhalf == 2)
-      *reinterpret_cast<uint4*>(p + d.F * 32u + g * 256) =
-          make_uint4(lo[4 * g], lo[4 * g + 1], lo[4 * g + 2], lo[4 * g + 3]);
+      tc::st_v4_hint(p + d.F * 32u + g * 256, make_uint4(lo[4 * g], lo[4 * g + 1], lo[4 * g + 2], lo[4 * g + 3]), pol);
   }
 }
 
@@ -246,7 +245,7 @@ __device__ __forceinline__ void dump32(const ImgDump& d, int tile, uint32_t k, u
 // while the tensor pipe runs the NEXT stage, so the HBM stores are off the stage's critical path.
 template <bool SPLIT, int NCHUNK>
 __device__ __forceinline__ void dump_from_tmem(const ImgDump& d, int tile, uint32_t row, uint32_t t_ahi,
-                                               uint32_t t_alo, uint32_t lane_base, uint32_t c0) {
+                                               uint32_t t_alo, uint32_t lane_base, uint32_t c0, uint64_t pol) {
   uint32_t hi[NCHUNK][16], lo[NCHUNK][16];
 #pragma unroll
   for (int cc = 0; cc < NCHUNK; ++cc) {
@@ -255,7 +254,7 @@ __device__ __forceinline__ void dump_from_tmem(const ImgDump& d, int tile, uint3
   }
   tc::tmem_ld_wait();
 #pragma unroll
-  for (int cc = 0; cc < NCHUNK; ++cc) dump32<SPLIT>(d, tile, row, c0 + cc * 32, hi[cc], lo[cc]);
+  for (int cc = 0; cc < NCHUNK; ++cc) dump32<SPLIT>(d, tile, row, c0 + cc * 32, hi[cc], lo[cc], pol);
 }
 
 }  // namespace eng

@@ -53,6 +53,37 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
       ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
+// ---- L2 cache policies ---------------------------------------------------------------------------------
+// The training step streams ~20 GB of write-once / read-once tile images past a 2.5 MB weight image
+// that every SM re-reads for every tile: without hints the stream evicts the weights and the slab
+// copies fall to the TMA's HBM-miss rate (~11 B/clk/SM).
+__device__ __forceinline__ uint64_t policy_evict_last() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ uint64_t policy_evict_first() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ void bulk_g2s_hint(uint32_t dst_smem, const void* src_gmem, uint32_t bytes,
+                                              uint32_t bar, uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+      ::"r"(dst_smem), "l"(src_gmem), "r"(bytes), "r"(bar), "l"(policy) : "memory");
+}
+__device__ __forceinline__ void st_v4_hint(void* p, const uint4& v, uint64_t policy) {
+  asm volatile("st.global.L2::cache_hint.v4.b32 [%0], {%1, %2, %3, %4}, %5;"
+               ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "l"(policy) : "memory");
+}
+__device__ __forceinline__ uint4 ld_v4_hint(const void* p, uint64_t policy) {
+  uint4 v;
+  asm volatile("ld.global.L2::cache_hint.v4.b32 {%0, %1, %2, %3}, [%4], %5;"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p), "l"(policy) : "memory");
+  return v;
+}
+
 // fire-and-forget prefetch of a global range into L2 (no shared-memory destination, no barrier)
 __device__ __forceinline__ void bulk_prefetch_l2(const void* src_gmem, uint32_t bytes) {
   asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src_gmem), "r"(bytes) : "memory");
