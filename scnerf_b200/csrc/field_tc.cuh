@@ -421,7 +421,7 @@ inline int field_tc_bwd_impl(const scnerf_mlp& m, const scnerf_mlp& g, const flo
     wgrad_unit(J.u[0], 0, 0, 0, 256, 0, g.views_w, 283, 128, 256);
     wgrad_unit(J.u[1], 0, 0, 1, 32, 256, g.views_w + 256, 283, 128, 27);
   }
-  SCNERF_LAUNCH((wgrad::field_wgrad_kernel<NSPLIT>), (unsigned)(w.nslices * wgrad::NJOBS), 192,
+  SCNERF_LAUNCH((wgrad::field_wgrad_kernel<NSPLIT>), (unsigned)(w.nslices * wgrad::NJOBS), 320,
                 wgrad::Cfg<NSPLIT>::SMEM_BYTES, stream, w);
   SCNERF_LAUNCH((wgrad::head_wgrad_img_kernel<(NSPLIT == 3 ? 2 : 1)>), (unsigned)std::min(T, 2 * device_sm_count()), 128, 0,
                 stream, I.hv, g_raw, P, T, g.rgb_w, g.rgb_b, g.alpha_b);

@@ -69,7 +69,7 @@ __device__ __forceinline__ void add_chunk(const uint4& c, float s, float (&acc)[
 }
 
 template <int NSPLIT>
-__global__ void __launch_bounds__(192, 1) field_wgrad_kernel(const __grid_constant__ Args a_) {
+__global__ void __launch_bounds__(320, 1) field_wgrad_kernel(const __grid_constant__ Args a_) {
   const Args* ap = &a_;
   using C = Cfg<NSPLIT>;
   constexpr int NH = C::NH;
@@ -85,7 +85,8 @@ __global__ void __launch_bounds__(192, 1) field_wgrad_kernel(const __grid_consta
   const int jid = blockIdx.x % NJOBS, slice = blockIdx.x / NJOBS;
   if (tid == 0) job = ap->job[jid];
   if (tid == 32) {
-    for (int i = 0; i < C::NSLOT; ++i) { tc::mbar_init(&full[i], 1); tc::mbar_init(&empty[i], 5); }
+    // full: 1 (producer expect_tx for the TMA part) + 128 (cp.async loader threads); empty: MMA commit + 4 helper warps
+    for (int i = 0; i < C::NSLOT; ++i) { tc::mbar_init(&full[i], 1 + 128); tc::mbar_init(&empty[i], 5); }
     tc::mbar_init(acc_done, 1);
     tc::fence_mbar_init();
   }
@@ -132,13 +133,11 @@ __global__ void __launch_bounds__(192, 1) field_wgrad_kernel(const __grid_consta
           if (pb1) tc::bulk_prefetch_l2(pb1 + (size_t)PF * bytesB[1], bytesB[1]);
         }
         tc::mbar_wait(&empty[idx], ph ^ 1);
-        tc::mbar_arrive_expect_tx(&full[idx], slot_bytes);
+        tc::mbar_arrive_expect_tx(&full[idx], bytesA[0] + (pa1 ? bytesA[1] : 0u));   // A images ride the TMA
         uint8_t* dst = wsm + idx * C::SLOT_BYTES;
         const uint32_t d32 = tc::smem_u32(dst), fb = tc::smem_u32(&full[idx]);
         tc::bulk_g2s_hint(d32 + offA[0], pa0, bytesA[0], fb, pol); pa0 += bytesA[0];
         if (pa1) { tc::bulk_g2s_hint(d32 + offA[1], pa1, bytesA[1], fb, pol); pa1 += bytesA[1]; }
-        tc::bulk_g2s_hint(d32 + offB[0], pb0, bytesB[0], fb, pol); pb0 += bytesB[0];
-        if (pb1) { tc::bulk_g2s_hint(d32 + offB[1], pb1, bytesB[1], fb, pol); pb1 += bytesB[1]; }
         if (++idx == C::NSLOT) { idx = 0; ph ^= 1u; }
       }
     }
@@ -166,6 +165,7 @@ __global__ void __launch_bounds__(192, 1) field_wgrad_kernel(const __grid_consta
 #pragma unroll 1
       for (int it = 0; it < nslots; ++it) {
         eng::mbar_wait_a(full0 + idx * 8, ph);
+        tc::fence_proxy_async();   // B slabs arrive through cp.async (generic proxy); the MMA reads via the async proxy
         tc::tc_fence_after();
         const uint32_t slot = base + idx * C::SLOT_BYTES;
 #pragma unroll
@@ -184,6 +184,31 @@ __global__ void __launch_bounds__(192, 1) field_wgrad_kernel(const __grid_consta
         if (++idx == C::NSLOT) { idx = 0; ph ^= 1u; }
       }
       tc::tc_commit(acc_done);
+    }
+  } else if (warp >= 6) {
+    // ===================== loader warps 6..9: B images through the LSU path (cp.async) ==============
+    // The TMA unit alone sustains ~11 B/clk/SM against HBM latency; 128 threads x 16-byte cp.async keep
+    // far more requests in flight, so the two paths together roughly double the stream.
+    const int lt = tid - 192;                // 0..127
+    const uint8_t* pb0 = job.b[0].base + (size_t)t0 * job.b[0].tile_bytes();
+    const uint8_t* pb1 = job.nb > 1 ? job.b[1].base + (size_t)t0 * job.b[1].tile_bytes() : nullptr;
+    uint32_t idx = 0, ph = 0;
+    const int nslots = (t1 - t0) * 8;
+#pragma unroll 1
+    for (int it = 0; it < nslots; ++it) {
+      tc::mbar_wait(&empty[idx], ph ^ 1);
+      const uint32_t d32 = tc::smem_u32(wsm + idx * C::SLOT_BYTES);
+      for (uint32_t o = (uint32_t)lt * 16u; o < bytesB[0]; o += 128u * 16u)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d32 + offB[0] + o), "l"(pb0 + o) : "memory");
+      pb0 += bytesB[0];
+      if (pb1) {
+        for (uint32_t o = (uint32_t)lt * 16u; o < bytesB[1]; o += 128u * 16u)
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d32 + offB[1] + o), "l"(pb1 + o) : "memory");
+        pb1 += bytesB[1];
+      }
+      // arrives on full[idx] when this thread's copies have landed (counted in the barrier's 1+128)
+      asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(tc::smem_u32(&full[idx])) : "memory");
+      if (++idx == C::NSLOT) { idx = 0; ph ^= 1u; }
     }
   } else {
     // ===================== helper warps 2..5: bias / alpha-weight gradients, then the dW epilogue ===
