@@ -395,6 +395,7 @@ inline int field_tc_bwd_impl(const scnerf_mlp& m, const scnerf_mlp& g, const flo
     if (pf < 0) { const char* e = getenv("SCNERF_WGRAD_L2_PREFETCH"); pf = e ? atoi(e) : 0; }
     w.l2_prefetch_slots = pf;
   }
+  w.dbg = tc_dbg_ptr(); w.dbg_slots = tc_dbg_tiles() * 8;
   auto std_job = [&](wgrad::Job& J, const eng::ImgDump& A, const eng::ImgDump& Bi, float* dW, int ld, int col0,
                      int cols_valid, float* db) {
     J.a[0] = A; J.na = 1; J.b[0] = Bi; J.nb = 1; J.nu = 2; J.db = db;

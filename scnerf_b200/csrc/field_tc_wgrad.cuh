@@ -43,6 +43,8 @@ struct Args {
   int num_tiles, nslices;
   int64_t P;
   int l2_prefetch_slots;   // 0 = off
+  long long* dbg; int dbg_slots;   // optional timeline of CTA 0: [slot][4] = producer got slot free, MMA saw
+                                   // slot full, MMA committed, helper warp 2 released the slot
 };
 
 template <int NSPLIT> struct Cfg {
@@ -133,6 +135,7 @@ __global__ void __launch_bounds__(320, 1) field_wgrad_kernel(const __grid_consta
           if (pb1) tc::bulk_prefetch_l2(pb1 + (size_t)PF * bytesB[1], bytesB[1]);
         }
         tc::mbar_wait(&empty[idx], ph ^ 1);
+        if (ap->dbg && blockIdx.x == 0 && it < ap->dbg_slots) ap->dbg[it * 4 + 0] = clock64();
         tc::mbar_arrive_expect_tx(&full[idx], bytesA[0] + (pa1 ? bytesA[1] : 0u));   // A images ride the TMA
         uint8_t* dst = wsm + idx * C::SLOT_BYTES;
         const uint32_t d32 = tc::smem_u32(dst), fb = tc::smem_u32(&full[idx]);
@@ -165,6 +168,7 @@ __global__ void __launch_bounds__(320, 1) field_wgrad_kernel(const __grid_consta
 #pragma unroll 1
       for (int it = 0; it < nslots; ++it) {
         eng::mbar_wait_a(full0 + idx * 8, ph);
+        if (ap->dbg && blockIdx.x == 0 && it < ap->dbg_slots) ap->dbg[it * 4 + 1] = clock64();
         tc::fence_proxy_async();   // B slabs arrive through cp.async (generic proxy); the MMA reads via the async proxy
         tc::tc_fence_after();
         const uint32_t slot = base + idx * C::SLOT_BYTES;
@@ -181,6 +185,7 @@ __global__ void __launch_bounds__(320, 1) field_wgrad_kernel(const __grid_consta
         }
         first = 1;
         eng::commit_a(empty0 + idx * 8);
+        if (ap->dbg && blockIdx.x == 0 && it < ap->dbg_slots) ap->dbg[it * 4 + 2] = clock64();
         if (++idx == C::NSLOT) { idx = 0; ph ^= 1u; }
       }
       tc::tc_commit(acc_done);
@@ -219,9 +224,10 @@ __global__ void __launch_bounds__(320, 1) field_wgrad_kernel(const __grid_consta
     const bool do_alpha = job.dw_alpha != nullptr;
     float accb[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, acca[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     uint32_t idx = 0, ph = 0;
+    int hit = 0;
     for (int tile = t0; tile < t1; ++tile)
 #pragma unroll 1
-      for (int ks = 0; ks < 8; ++ks) {
+      for (int ks = 0; ks < 8; ++ks, ++hit) {
         tc::mbar_wait(&full[idx], ph);
         const uint8_t* slot = wsm + idx * C::SLOT_BYTES;
         if (do_bias || do_alpha) {
@@ -243,6 +249,7 @@ __global__ void __launch_bounds__(320, 1) field_wgrad_kernel(const __grid_consta
         }
         __syncwarp();
         if (lane == 0) tc::mbar_arrive(&empty[idx]);
+        if (ap->dbg && blockIdx.x == 0 && tid == 64 && hit < ap->dbg_slots) ap->dbg[hit * 4 + 3] = clock64();
         if (++idx == C::NSLOT) { idx = 0; ph ^= 1u; }
       }
     // reduce the 4 sample sub-slices of each mn-group (lanes 4g..4g+3) and publish
