@@ -389,13 +389,31 @@ inline int field_tc_bwd_impl(const scnerf_mlp& m, const scnerf_mlp& g, const flo
   // ---- wgrad jobs --------------------------------------------------------------------------------------
   wgrad::Args w{};
   w.num_tiles = T; w.P = P;
-  w.nslices = std::max(1, device_sm_count() / wgrad::NJOBS);
+  {
+    // CTAs per job in proportion to the measured cycles per K=16 slot of each job (profiles/README.md, r1h):
+    // J0 issues 12 N=64 MMAs, J8 also reduces d(alpha_linear.weight), J9 has the narrowest slab
+    static const int weight[wgrad::NJOBS] = {1385, 1170, 1170, 1170, 1170, 1170, 1170, 1170, 1500, 1100};
+    const int ncta = std::max(device_sm_count(), wgrad::NJOBS);
+    int wsum = 0, used = 0, n[wgrad::NJOBS];
+    for (int j = 0; j < wgrad::NJOBS; ++j) wsum += weight[j];
+    for (int j = 0; j < wgrad::NJOBS; ++j) { n[j] = std::max(1, ncta * weight[j] / wsum); used += n[j]; }
+    for (int j = 0; used < ncta; j = (j + 1) % wgrad::NJOBS)     // leftovers to the heaviest jobs first
+      if (weight[j] >= 1385 || used + wgrad::NJOBS <= ncta) { ++n[j]; ++used; }
+    w.cta0[0] = 0;
+    for (int j = 0; j < wgrad::NJOBS; ++j) w.cta0[j + 1] = w.cta0[j] + n[j];
+  }
   {
     static int pf = -1;   // tuning knob (default off: measured slower on B200, profiles/README.md)
     if (pf < 0) { const char* e = getenv("SCNERF_WGRAD_L2_PREFETCH"); pf = e ? atoi(e) : 0; }
     w.l2_prefetch_slots = pf;
   }
-  w.dbg = tc_dbg_ptr(); w.dbg_slots = tc_dbg_tiles() * 8;
+  {
+    static int min_tiles = -1;   // debug timeline: only launches with at least this many tiles write it
+    if (min_tiles < 0) { const char* e = getenv("SCNERF_DBG_MIN_TILES"); min_tiles = e ? atoi(e) : 0; }
+    static int dbg_cta = -1;
+    if (dbg_cta < 0) { const char* e = getenv("SCNERF_DBG_CTA"); dbg_cta = e ? atoi(e) : 0; }
+    w.dbg = T >= min_tiles ? tc_dbg_ptr() : nullptr; w.dbg_slots = tc_dbg_tiles() * 8; w.dbg_cta = dbg_cta;
+  }
   auto std_job = [&](wgrad::Job& J, const eng::ImgDump& A, const eng::ImgDump& Bi, float* dW, int ld, int col0,
                      int cols_valid, float* db) {
     J.a[0] = A; J.na = 1; J.b[0] = Bi; J.nb = 1; J.nu = 2; J.db = db;
@@ -422,7 +440,7 @@ inline int field_tc_bwd_impl(const scnerf_mlp& m, const scnerf_mlp& g, const flo
     wgrad_unit(J.u[0], 0, 0, 0, 256, 0, g.views_w, 283, 128, 256);
     wgrad_unit(J.u[1], 0, 0, 1, 32, 256, g.views_w + 256, 283, 128, 27);
   }
-  SCNERF_LAUNCH((wgrad::field_wgrad_kernel<NSPLIT>), (unsigned)(w.nslices * wgrad::NJOBS), 320,
+  SCNERF_LAUNCH((wgrad::field_wgrad_kernel<NSPLIT>), (unsigned)w.cta0[wgrad::NJOBS], 320,
                 wgrad::Cfg<NSPLIT>::SMEM_BYTES, stream, w);
   SCNERF_LAUNCH((wgrad::head_wgrad_img_kernel<(NSPLIT == 3 ? 2 : 1)>), (unsigned)std::min(T, 2 * device_sm_count()), 128, 0,
                 stream, I.hv, g_raw, P, T, g.rgb_w, g.rgb_b, g.alpha_b);

@@ -40,10 +40,11 @@ struct Job {
 };
 struct Args {
   Job job[NJOBS];
-  int num_tiles, nslices;
+  int num_tiles;
+  int cta0[NJOBS + 1];     // job j owns CTAs [cta0[j], cta0[j+1]): its tiles are split evenly over them
   int64_t P;
   int l2_prefetch_slots;   // 0 = off
-  long long* dbg; int dbg_slots;   // optional timeline of CTA 0: [slot][4] = producer got slot free, MMA saw
+  long long* dbg; int dbg_slots, dbg_cta;   // optional timeline of CTA 0: [slot][4] = producer got slot free, MMA saw
                                    // slot full, MMA committed, helper warp 2 released the slot
 };
 
@@ -84,8 +85,16 @@ __global__ void __launch_bounds__(320, 1) field_wgrad_kernel(const __grid_consta
   __shared__ Job job;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int jid = blockIdx.x % NJOBS, slice = blockIdx.x / NJOBS;
+  int jid = 0;
+#pragma unroll
+  for (int j = 1; j < NJOBS; ++j) jid += (int)blockIdx.x >= ap->cta0[j];
+  const int slice = (int)blockIdx.x - ap->cta0[jid];
   if (tid == 0) job = ap->job[jid];
+  if (ap->dbg && tid == 0) {
+    unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    ap->dbg[ap->dbg_slots * 4 + blockIdx.x * 4 + 0] = (long long)t;
+    ap->dbg[ap->dbg_slots * 4 + blockIdx.x * 4 + 3] = clock64();
+  }
   if (tid == 32) {
     // full: 1 (producer expect_tx for the TMA part) + 128 (cp.async loader threads); empty: MMA commit + 4 helper warps
     for (int i = 0; i < C::NSLOT; ++i) { tc::mbar_init(&full[i], 1 + 128); tc::mbar_init(&empty[i], 5); }
@@ -98,7 +107,7 @@ __global__ void __launch_bounds__(320, 1) field_wgrad_kernel(const __grid_consta
   __syncthreads();
   tc::tc_fence_after();
   const uint32_t tmem = *tmem_slot;
-  const int nslices = ap->nslices;
+  const int nslices = ap->cta0[jid + 1] - ap->cta0[jid];
   const int per = (ap->num_tiles + nslices - 1) / nslices;
   const int t0 = min(slice * per, ap->num_tiles), t1 = min(t0 + per, ap->num_tiles);
   // byte offsets of each image's slab inside a slot
@@ -135,7 +144,7 @@ __global__ void __launch_bounds__(320, 1) field_wgrad_kernel(const __grid_consta
           if (pb1) tc::bulk_prefetch_l2(pb1 + (size_t)PF * bytesB[1], bytesB[1]);
         }
         tc::mbar_wait(&empty[idx], ph ^ 1);
-        if (ap->dbg && blockIdx.x == 0 && it < ap->dbg_slots) ap->dbg[it * 4 + 0] = clock64();
+        if (ap->dbg && blockIdx.x == ap->dbg_cta && (it & 31) == 0 && (it >> 5) < ap->dbg_slots) ap->dbg[(it >> 5) * 4 + 0] = clock64();
         tc::mbar_arrive_expect_tx(&full[idx], bytesA[0] + (pa1 ? bytesA[1] : 0u));   // A images ride the TMA
         uint8_t* dst = wsm + idx * C::SLOT_BYTES;
         const uint32_t d32 = tc::smem_u32(dst), fb = tc::smem_u32(&full[idx]);
@@ -168,7 +177,7 @@ __global__ void __launch_bounds__(320, 1) field_wgrad_kernel(const __grid_consta
 #pragma unroll 1
       for (int it = 0; it < nslots; ++it) {
         eng::mbar_wait_a(full0 + idx * 8, ph);
-        if (ap->dbg && blockIdx.x == 0 && it < ap->dbg_slots) ap->dbg[it * 4 + 1] = clock64();
+        if (ap->dbg && blockIdx.x == ap->dbg_cta && (it & 31) == 0 && (it >> 5) < ap->dbg_slots) ap->dbg[(it >> 5) * 4 + 1] = clock64();
         tc::fence_proxy_async();   // B slabs arrive through cp.async (generic proxy); the MMA reads via the async proxy
         tc::tc_fence_after();
         const uint32_t slot = base + idx * C::SLOT_BYTES;
@@ -185,10 +194,14 @@ __global__ void __launch_bounds__(320, 1) field_wgrad_kernel(const __grid_consta
         }
         first = 1;
         eng::commit_a(empty0 + idx * 8);
-        if (ap->dbg && blockIdx.x == 0 && it < ap->dbg_slots) ap->dbg[it * 4 + 2] = clock64();
+        if (ap->dbg && blockIdx.x == ap->dbg_cta && (it & 31) == 0 && (it >> 5) < ap->dbg_slots) ap->dbg[(it >> 5) * 4 + 2] = clock64();
         if (++idx == C::NSLOT) { idx = 0; ph ^= 1u; }
       }
       tc::tc_commit(acc_done);
+      if (ap->dbg) {
+        unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        ap->dbg[ap->dbg_slots * 4 + blockIdx.x * 4 + 1] = (long long)t;
+      }
     }
   } else if (warp >= 6) {
     // ===================== loader warps 6..9: B images through the LSU path (cp.async) ==============
@@ -217,54 +230,84 @@ __global__ void __launch_bounds__(320, 1) field_wgrad_kernel(const __grid_consta
     }
   } else {
     // ===================== helper warps 2..5: bias / alpha-weight gradients, then the dW epilogue ===
-    const int ht = tid - 64;                 // 0..127
+    // Lane -> (sample k, mn-group parity): the 16 samples of one mn-group are 256 contiguous bytes of the
+    // slab, so a warp's 32 x 16-byte reads cover 512 contiguous bytes: conflict-free.  (The earlier
+    // group-major mapping was 4-way bank conflicted and, with the MMA operand reads and the ring fills,
+    // saturated shared-memory bandwidth: profiles/README.md, r1h.)
+    const int hw = warp - 2;                 // 0..3
+    const int k = lane & 15, gs = lane >> 4; // sample within the slab, mn-group parity
     const int FA = (int)job.a[0].F;          // 256 or 128 features
-    const int g = ht >> 2, q = ht & 3;       // mn-group, sample sub-slice (4 samples)
-    const bool do_bias = job.db != nullptr && g * 8 < FA;
+    const bool do_bias = job.db != nullptr;
     const bool do_alpha = job.dw_alpha != nullptr;
-    float accb[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, acca[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    float accb[4][8], acca[4][8];            // mn-groups hw*8 + 2j + gs, j = 0..3
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int e = 0; e < 8; ++e) { accb[j][e] = 0.f; acca[j][e] = 0.f; }
     uint32_t idx = 0, ph = 0;
     int hit = 0;
-    for (int tile = t0; tile < t1; ++tile)
-#pragma unroll 1
+    // d(raw)[:, 3] of the NEXT tile is fetched while the current one is consumed: a dependent global load
+    // inside the slot loop would hold the ring slot for a full HBM round trip (measured: 2.2x on job 8)
+    float gcur[8], gnext[8];
+    auto load_alpha = [&](int tile, float (&dst)[8]) {
+#pragma unroll
+      for (int ks = 0; ks < 8; ++ks) {
+        const int64_t p = (int64_t)tile * 128 + ks * 16 + k;
+        dst[ks] = p < ap->P ? __ldg(job.g_raw + p * 4 + 3) : 0.f;
+      }
+    };
+    if (do_alpha && t0 < t1) load_alpha(t0, gnext);
+    for (int tile = t0; tile < t1; ++tile) {
+      if (do_alpha) {
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks) gcur[ks] = gnext[ks];
+        if (tile + 1 < t1) load_alpha(tile + 1, gnext);
+      }
+#pragma unroll
       for (int ks = 0; ks < 8; ++ks, ++hit) {
         tc::mbar_wait(&full[idx], ph);
         const uint8_t* slot = wsm + idx * C::SLOT_BYTES;
         if (do_bias || do_alpha) {
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const int kk = q * 4 + i;        // sample within the slab (0..15)
-            const uint32_t coff = (uint32_t)g * 256u + (uint32_t)(kk >> 3) * 128u + (uint32_t)(kk & 7) * 16u;
-            if (do_bias) {
-              add_chunk(*reinterpret_cast<const uint4*>(slot + offA[0] + coff), 1.f, accb);
-              if (SPLIT) add_chunk(*reinterpret_cast<const uint4*>(slot + offA[0] + (uint32_t)FA * 32u + coff), 1.f, accb);
+          for (int j = 0; j < 4; ++j) {
+            const int g = hw * 8 + j * 2 + gs;
+            const uint32_t coff = (uint32_t)g * 256u + (uint32_t)k * 16u;
+            if (do_bias && g * 8 < FA) {
+              add_chunk(*reinterpret_cast<const uint4*>(slot + offA[0] + coff), 1.f, accb[j]);
+              if (SPLIT) add_chunk(*reinterpret_cast<const uint4*>(slot + offA[0] + (uint32_t)FA * 32u + coff), 1.f, accb[j]);
             }
             if (do_alpha) {
-              const int64_t p = (int64_t)tile * 128 + ks * 16 + kk;
-              const float ga = p < ap->P ? job.g_raw[p * 4 + 3] : 0.f;
-              add_chunk(*reinterpret_cast<const uint4*>(slot + offB[0] + coff), ga, acca);
-              if (SPLIT) add_chunk(*reinterpret_cast<const uint4*>(slot + offB[0] + job.b[0].F * 32u + coff), ga, acca);
+              const float ga = gcur[ks];
+              add_chunk(*reinterpret_cast<const uint4*>(slot + offB[0] + coff), ga, acca[j]);
+              if (SPLIT) add_chunk(*reinterpret_cast<const uint4*>(slot + offB[0] + job.b[0].F * 32u + coff), ga, acca[j]);
             }
           }
         }
         __syncwarp();
         if (lane == 0) tc::mbar_arrive(&empty[idx]);
-        if (ap->dbg && blockIdx.x == 0 && tid == 64 && hit < ap->dbg_slots) ap->dbg[hit * 4 + 3] = clock64();
+        if (ap->dbg && blockIdx.x == ap->dbg_cta && tid == 64 && (hit & 31) == 0 && (hit >> 5) < ap->dbg_slots) ap->dbg[(hit >> 5) * 4 + 3] = clock64();
         if (++idx == C::NSLOT) { idx = 0; ph ^= 1u; }
       }
-    // reduce the 4 sample sub-slices of each mn-group (lanes 4g..4g+3) and publish
-#pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      accb[e] += __shfl_xor_sync(0xffffffffu, accb[e], 1); accb[e] += __shfl_xor_sync(0xffffffffu, accb[e], 2);
-      acca[e] += __shfl_xor_sync(0xffffffffu, acca[e], 1); acca[e] += __shfl_xor_sync(0xffffffffu, acca[e], 2);
     }
-    if (q == 0 && t1 > t0) {
-      if (do_bias)
+    // reduce over the 16 samples (lanes with equal parity) and publish
+    if (t1 > t0) {
 #pragma unroll
-        for (int e = 0; e < 8; ++e) atomicAdd(job.db + g * 8 + e, accb[e]);
-      if (do_alpha)
+      for (int j = 0; j < 4; ++j) {
+        const int g = hw * 8 + j * 2 + gs;
 #pragma unroll
-        for (int e = 0; e < 8; ++e) atomicAdd(job.dw_alpha + g * 8 + e, acca[e]);
+        for (int e = 0; e < 8; ++e) {
+          float vb = accb[j][e], va = acca[j][e];
+#pragma unroll
+          for (int m = 1; m < 16; m <<= 1) {
+            vb += __shfl_xor_sync(0xffffffffu, vb, m);
+            va += __shfl_xor_sync(0xffffffffu, va, m);
+          }
+          if (k == 0) {
+            if (do_bias && g * 8 < FA) atomicAdd(job.db + g * 8 + e, vb);
+            if (do_alpha) atomicAdd(job.dw_alpha + g * 8 + e, va);
+          }
+        }
+      }
     }
     // ---- dW epilogue: TMEM -> atomicAdd into the fp32 gradient -------------------------------------
     tc::mbar_wait(acc_done, 0);
@@ -301,6 +344,11 @@ __global__ void __launch_bounds__(320, 1) field_wgrad_kernel(const __grid_consta
   }
   tc::tc_fence_before();
   __syncthreads();
+  if (ap->dbg && tid == 0) {
+    unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    ap->dbg[ap->dbg_slots * 4 + blockIdx.x * 4 + 2] = (long long)t;
+    ap->dbg[ap->dbg_slots * 4 + blockIdx.x * 4 + 3] = clock64() - ap->dbg[ap->dbg_slots * 4 + blockIdx.x * 4 + 3];
+  }
   if (warp == 1) tc::tmem_dealloc(tmem, 512);
 }
 

@@ -19,9 +19,22 @@ lib.scnerf_debug_timeline(_lib.ptr(big), T)
 eng.step_device()
 torch.cuda.synchronize()
 lib.scnerf_debug_timeline(None, 0)
-b = big.cpu().numpy()[:T * 8 * 4].reshape(T * 8, 4)
-t0 = b[b > 0].min()
-print("slot: prod_free  mma_full  mma_commit  helper_release | full-free  commit-full  next_free-free")
-for i in range(40, 72):
-    f, m, c, h = b[i] - t0
-    print(f"{i:3d}: {f:8d} {m:8d} {c:8d} {h:8d} | {m - f:6d} {c - m:6d} {b[i + 1, 0] - b[i, 0]:6d}")
+b = big.cpu().numpy()
+tl = b[:T * 8 * 4].reshape(T * 8, 4)
+t0 = tl[tl > 0].min()
+print("every 32nd slot: prod_free  mma_full  mma_commit helper_release | full-free  commit-full release-full cycles/slot since previous stamp")
+for i in range(0, T * 8 - 1):
+    if tl[i, 0] == 0 or tl[i + 1, 0] == 0: break
+    f, m, c, h = tl[i] - t0
+    if i % 8 == 0: print(f"{i * 32:5d}: {f:9d} {m:9d} {c:9d} {h:9d} | {m - f:6d} {c - m:6d} {h - m:6d} {(tl[i + 1, 0] - tl[i, 0]) / 32:8.0f}")
+nct = 148
+c = b[T * 8 * 4: T * 8 * 4 + nct * 4].reshape(nct, 4)
+g0 = c[:, 0].min()
+import numpy as np
+alloc = [18, 14, 14, 14, 14, 14, 14, 14, 19, 13]          # field_tc.cuh: CTAs per job on a 148-SM part
+print("per job: start_us  loop_end_us  end_us  sm_cycles (min..max over the job's CTAs)")
+o = 0
+for j, n in enumerate(alloc):
+    rows = c[o:o + n]; o += n
+    print(f"job {j} ({n:2d} CTAs): start {np.min(rows[:,0]-g0)/1e3:7.1f}..{np.max(rows[:,0]-g0)/1e3:7.1f}  loop_end {np.min(rows[:,1]-g0)/1e3:7.1f}..{np.max(rows[:,1]-g0)/1e3:7.1f}"
+          f"  end {np.min(rows[:,2]-g0)/1e3:7.1f}..{np.max(rows[:,2]-g0)/1e3:7.1f}  cycles {rows[:,3].min()}..{rows[:,3].max()}")
