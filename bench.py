@@ -222,6 +222,12 @@ def main():
     torch.cuda.synchronize()
     ms_field = e0.elapsed_time(e1) / reps
     burst, sustained, hbm, src = measured_peaks()
+    # DRAM bytes per launch of that kernel from the committed `ncu --set full` capture (profiles/traffic.json,
+    # written by tools/ncu_traffic.py); null when the capture for this precision is missing
+    traffic = None
+    tpath = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        traffic = json.load(open(tpath)).get(f"field_fused_fwd_kernel/{args.precision}/inference", {}).get("dram_bytes")
     field_flop = P_rays * (NC + NF) * FLOP_PER_SAMPLE
     achieved = field_flop / (ms_field * 1e-3) / 1e12
 
@@ -262,7 +268,7 @@ def main():
         "loss": loss,
         "clocks": clk.summary(),
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": burst, "unit": "TFLOP/s",
-                     "frac": achieved / burst, "traffic": None, "peak_source": f"{src} cuBLAS bf16 burst",
+                     "frac": achieved / burst, "traffic": traffic, "peak_source": f"{src} cuBLAS bf16 burst",
                      "kernel": f"fine-network field forward (PE + 8x256 MLP, {args.precision}) on {P_rays * (NC + NF)} samples",
                      "ms": ms_field, "algorithmic_flop": field_flop,
                      "step_frac_of_sustained": (TRAIN_FLOP_PER_RAY * N_RAYS / (ms_dev * 1e-3) / 1e12) / sustained},
