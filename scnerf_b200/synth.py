@@ -116,3 +116,62 @@ def reference_pytest_rand(shape):
     cast to float32 (NeRF/render.py:252-255, 333-336, 432-440)."""
     np.random.seed(0)
     return np.random.rand(*shape).astype(np.float32)
+
+
+# ---------------------------------------------------------------------------------------------
+# NeRF++ (inverted sphere) configs — BASELINE.json configs[3], configs[4] (SURVEY.md §8d C4/C5)
+# ---------------------------------------------------------------------------------------------
+PP_H, PP_W, PP_NCAM, PP_FOCAL = 120, 200, 8, 160.0
+
+
+def pp_camera_poses(seed=0, n_cams=PP_NCAM, radius=0.5):
+    """[n,4,4] float32 camera-to-world, OpenCV convention (+z forward): cameras on a jittered ring of
+    radius ~0.5 looking at the origin, i.e. inside the unit sphere as `intersect_sphere` requires
+    (nerfplusplus/ddp_train_nerf.py:50-68)."""
+    rng = np.random.default_rng(seed + 4000)
+    out = np.tile(np.eye(4), (n_cams, 1, 1))
+    for i in range(n_cams):
+        ang = 2 * np.pi * i / n_cams + rng.uniform(-0.1, 0.1)
+        pos = np.array([radius * np.cos(ang), rng.uniform(-0.1, 0.1), radius * np.sin(ang)])
+        z = -pos / np.linalg.norm(pos)                       # forward: towards the origin
+        x = np.cross(np.array([0.0, 1.0, 0.0]), z); x /= np.linalg.norm(x)
+        y = np.cross(z, x)
+        out[i, :3, 0], out[i, :3, 1], out[i, :3, 2], out[i, :3, 3] = x, y, z, pos
+    return out.astype(np.float32)
+
+
+def pp_camera_args(**kw):
+    kw.setdefault("camera_model", "pinhole_rot_noise_10k_rayo_rayd_dist")
+    return camera_args(**kw)
+
+
+def pp_mlp_layer_shapes(input_ch, input_ch_views=27, D=8, W=256, skips=(4,)):
+    """(key, out, in) of nerfplusplus/nerf_network.py:68-118 MLPNet in parameters() order."""
+    layers = [("base_layers.0.0", W, input_ch)]
+    for i in range(D - 1):
+        layers.append((f"base_layers.{i + 1}.0", W, W + input_ch if i in skips else W))
+    layers += [("sigma_layers.0", 1, W), ("base_remap_layers.0", 256, W),
+               ("rgb_layers.0", W // 2, 256 + input_ch_views), ("rgb_layers.2", 3, W // 2)]
+    return layers
+
+
+def pp_mlp_state(seed, input_ch, input_ch_views=27, bias_sigma=0.05):
+    """PyTorch-default-like init (the reference keeps nn.Linear defaults, nerf_network.py:98-118):
+    U(-1/sqrt(in), 1/sqrt(in)) weights; widened a little so sigma is not vanishing; small biases."""
+    rng = np.random.default_rng(seed + 5000)
+    st = {}
+    for name, fo, fi in pp_mlp_layer_shapes(input_ch, input_ch_views):
+        a = 1.7 / np.sqrt(fi)
+        st[name + ".weight"] = rng.uniform(-a, a, (fo, fi)).astype(np.float32)
+        st[name + ".bias"] = (rng.standard_normal(fo) * bias_sigma).astype(np.float32)
+    return st
+
+
+def pp_pixel_batch(seed, N, H=PP_H, W=PP_W, n_cams=PP_NCAM):
+    """select_inds[N] int64 (flat y*W+x, no replacement like np.random.choice(..., replace=False),
+    nerf_sample_ray_split.py:147), camera index, target rgb[N,3]."""
+    rng = np.random.default_rng(seed + 6000)
+    sel = rng.choice(H * W, size=N, replace=False).astype(np.int64)
+    cam_idx = int(rng.integers(0, n_cams))
+    target = rng.uniform(0, 1, (N, 3)).astype(np.float32)
+    return sel, cam_idx, target

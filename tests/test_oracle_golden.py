@@ -191,3 +191,114 @@ def test_searchsorted_rows_matches_torch(right):
                 nrow = max(Ba, Bv)
                 ref = torch.searchsorted(T(a).expand(nrow, A).contiguous(), T(v).expand(nrow, V).contiguous(), right=right)
                 assert np.array_equal(got, ref.numpy())
+
+
+# ---------------------------------------------------------------------------------------------
+# NeRF++ rows: oracle/scnerf_pp_oracle.py vs tests/golden/pp_*.npz
+# ---------------------------------------------------------------------------------------------
+from oracle import scnerf_pp_oracle as OP   # noqa: E402
+
+PH, PW, PF, PN = synth.PP_H, synth.PP_W, synth.PP_FOCAL, synth.PP_NCAM
+
+
+def make_cam_pp(seed, requires_grad=False, dtype=torch.float32):
+    cam = OP.CameraPP(synth.intrinsic_init(PH, PW, PF), synth.pp_camera_poses(seed), synth.pp_camera_args(),
+                      PH, PW, k=(-0.05, 0.01), dtype=dtype)
+    return cam.load(synth.camera_noise_state(seed, n_cams=PN, H=PH, W=PW, with_distortion=True), requires_grad)
+
+
+def pp_nets(seed, dtype=torch.float32):
+    cv = lambda st: {k: T(v).to(dtype) for k, v in st.items()}
+    return cv(synth.pp_mlp_state(seed, 63)), cv(synth.pp_mlp_state(seed + 1, 84))
+
+
+def test_pp_raygen(golden):
+    g = golden("pp_raygen")
+    for tag, seed in (("a", 30), ("b", 31)):
+        cam = make_cam_pp(seed, requires_grad=True)
+        o, d, depth = OP.rays_from_camera(cam, int(g[f"{tag}_cam_idx"]), T(g[f"{tag}_sel"]))
+        close(o, g[f"{tag}_o"], 1e-6, 1e-7)
+        close(d, g[f"{tag}_d"], 1e-5, 2e-7)
+        close(depth, g[f"{tag}_depth"], 0, 0)
+        ((o * T(g[f"{tag}_wo"])).sum() + (d * T(g[f"{tag}_wd"])).sum()).backward()
+        for name in OP.CameraPP.LEARNABLE:
+            ref = g[f"{tag}_g_{name}"]
+            close(getattr(cam, name).grad, ref, 2e-3, 2e-5 * np.abs(ref).max())
+    cam = make_cam_pp(32)
+    o, d, depth = OP.rays_from_camera(cam, None, T(g["c_sel"]), extrinsic=g["c_E"])
+    close(o, g["c_o"], 1e-6, 1e-7)
+    close(d, g["c_d"], 1e-5, 2e-7)
+
+
+def test_pp_sampling(golden):
+    g = golden("pp_sampling")
+    o, d = T(g["o"]), T(g["d"])
+    far = OP.intersect_sphere(o, d)
+    close(far, g["far"], 1e-6, 1e-7)
+    fg, bg = OP.level0_depths(1e-4 * torch.ones_like(far), far, 32, T(g["t_fg"]), T(g["t_bg"]))
+    close(fg, g["fg_p"], 1e-6, 1e-7)
+    close(bg, g["bg_p"], 1e-6, 1e-7)
+    mid = 0.5 * (T(g["fg_p"])[..., 1:] + T(g["fg_p"])[..., :-1])
+    w = T(g["w"])[..., 1:-1]
+    s, _ = OP.sample_pdf(mid, w, 64, u=T(g["u"]))
+    close(s, g["s_rand"], 1e-6, 1e-7)
+    s, _ = OP.sample_pdf(mid, w, 64, det=True)
+    close(s, g["s_det"], 1e-6, 1e-7)
+    merged = OP.level1_depths(T(g["fg_p"]), T(g["w"]), 64, u=T(g["u"]))
+    close(merged, g["merged"], 1e-6, 1e-7)
+    with pytest.raises(Exception, match="unit sphere"):
+        OP.intersect_sphere(torch.tensor([[2.0, 0.0, 0.0]]), torch.tensor([[0.0, 1.0, 0.0]]))   # misses the sphere
+
+
+def test_pp_field(golden):
+    g = golden("pp_field")
+    st_fg, st_bg = pp_nets(40)
+    for v in list(st_fg.values()) + list(st_bg.values()):
+        v.requires_grad_(True)
+    o, d = T(g["o"]).requires_grad_(True), T(g["d"]).requires_grad_(True)
+    far = OP.intersect_sphere(o, d)
+    fg, bg = OP.level0_depths(1e-4 * torch.ones_like(far), far, 24, T(g["t_fg"]), T(g["t_bg"]))
+    close(fg, g["fg"], 1e-6, 1e-7)
+    pts4, depth_real = OP.depth2pts_outside(o.detach()[:, None, :].expand(48, 24, 3),
+                                            d.detach()[:, None, :].expand(48, 24, 3), T(g["bg"]))
+    close(pts4, g["pts4"], 1e-5, 1e-6)
+    close(depth_real, g["depth_real"], 1e-4, 1e-4)
+    ret = OP.nerfnet_forward(st_fg, st_bg, o, d, far, fg, bg)
+    for k, v in ret.items():
+        close(v, g["ret_" + k], 1e-4, 2e-6)
+    loss = torch.mean((ret["rgb"] - T(g["target"])) ** 2)
+    close(loss, g["loss"], 1e-5, 0)
+    loss.backward()
+    for k in list(g):
+        if k.startswith("g_fg_net.") or k.startswith("g_bg_net."):
+            st = st_fg if k.startswith("g_fg") else st_bg
+            ref = g[k]
+            close(st[k[9:]].grad[:8], ref, 5e-3, 5e-5 * np.abs(ref).max())
+    close(o.grad, g["g_o"], 5e-3, 5e-5 * np.abs(g["g_o"]).max())
+    close(d.grad, g["g_d"], 5e-3, 5e-5 * np.abs(g["g_d"]).max())
+
+
+def test_pp_train_step(golden):
+    g = golden("pp_train_step")
+    cam = make_cam_pp(35, requires_grad=True)
+    nets = [pp_nets(50), pp_nets(52)]
+    for fgst, bgst in nets:
+        for v in list(fgst.values()) + list(bgst.values()):
+            v.requires_grad_(True)
+    rand = {k: T(g[k]) for k in ("t_fg", "t_bg", "u_fg", "u_bg")}
+    loss, rets, (fg1, bg1) = OP.train_step(cam, int(g["cam_idx"]), T(g["sel"]), T(g["target"]), nets, [24, 48], rand)
+    close(rets[0]["rgb"], g["rgb0"], 1e-4, 2e-6)
+    close(fg1, g["fg1"], 1e-5, 1e-6)
+    close(bg1, g["bg1"], 1e-5, 1e-6)
+    close(rets[1]["rgb"], g["rgb1"], 1e-4, 2e-6)
+    close(loss, g["loss"], 1e-5, 0)
+    loss.backward()
+    for name in OP.CameraPP.LEARNABLE:
+        ref = g["g_cam_" + name]
+        close(getattr(cam, name).grad, ref, 1e-2, 1e-4 * np.abs(ref).max())
+    for k in list(g):
+        if k.startswith("g_net"):
+            m, name = int(k[5]), k[7:]
+            st = nets[m][0] if name.startswith("fg_net.") else nets[m][1]
+            ref = g[k]
+            close(st[name[7:]].grad[:8], ref, 1e-2, 1e-4 * np.abs(ref).max())
