@@ -128,6 +128,7 @@ typedef struct scnerf_mlp {
   float *alpha_w, *alpha_b;     /* [1, W] */
   float *rgb_w, *rgb_b;         /* [3, W/2] */
   float *output_w, *output_b;   /* [output_ch, W] (use_viewdirs == 0) */
+  int32_t pts_dim;              /* 0|3: xyz points; 4: NeRF++ background (x,y,z,1/r), input_ch = 4*(1+2*L_pos) */
 } scnerf_mlp; /* the same struct carries parameters (read) or their gradients (+=) */
 
 /* ------------------------------------------------------------------------------------------------

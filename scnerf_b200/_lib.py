@@ -1,4 +1,4 @@
-"""ctypes binding of ``csrc/libscnerf_b200.so`` (C ABI: ``include/scnerf_b200.h``).
+"""ctypes binding of ``csrc/libscnerf_b200.so`` (C ABI: ``include/scnerf_b200.h``, ``include/scnerf_b200_nerfpp.h``).
 
 There is NO fallback: if the shared library is missing or a call fails, a ``RuntimeError`` is
 raised.  PyTorch is used only for device memory (``tensor.data_ptr()``) and the current stream.
@@ -52,7 +52,13 @@ class Mlp(C.Structure):
                 ("pts_w", vp * MAX_DEPTH), ("pts_b", vp * MAX_DEPTH),
                 ("views_w", vp), ("views_b", vp), ("feature_w", vp), ("feature_b", vp),
                 ("alpha_w", vp), ("alpha_b", vp), ("rgb_w", vp), ("rgb_b", vp),
-                ("output_w", vp), ("output_b", vp)]
+                ("output_w", vp), ("output_b", vp), ("pts_dim", C.c_int32)]
+
+
+class PPRaygenArgs(C.Structure):          # include/scnerf_b200_nerfpp.h
+    _fields_ = [("cam", C.POINTER(Camera)), ("distortion_initial", vp), ("distortion_noise", vp),
+                ("distortion_noise_scale", C.c_float), ("select_inds", vp), ("camera_idx", C.c_int64),
+                ("extrinsic", vp), ("N", C.c_int64)]
 
 
 class RenderCfg(C.Structure):
@@ -115,6 +121,30 @@ SIGNATURES = {
     "scnerf_train_step": (_I, [_P(Camera), _P(CameraGrads), _P(RenderCfg), C.c_int32, C.c_float,
                                C.c_float, _P(Mlp), _P(Mlp), _P(Mlp), _P(Mlp), _P(StepIO), C.c_int32,
                                _I64, vp, _SZ, vp]),
+    # ---- include/scnerf_b200_nerfpp.h ----
+    "scnerf_pp_raygen_fwd": (_I, [_P(PPRaygenArgs), vp, vp, vp, vp]),
+    "scnerf_pp_raygen_bwd": (_I, [_P(PPRaygenArgs), vp, vp, _P(CameraGrads), vp, vp]),
+    "scnerf_pp_intersect_sphere_fwd": (_I, [vp, vp, _I64, vp, vp, vp]),
+    "scnerf_pp_intersect_sphere_bwd": (_I, [vp, vp, vp, _I64, vp, vp, vp]),
+    "scnerf_pp_level0_depths": (_I, [vp, C.c_float, _I64, _I64, vp, vp, vp, vp, vp, vp]),
+    "scnerf_pp_sample_pdf": (_I, [vp, vp, vp, vp, _I64, _I64, _I64, vp, vp, vp, vp, vp]),
+    "scnerf_pp_sample_pdf_bins": (_I, [vp, vp, vp, _I64, _I64, _I64, vp, vp, vp, vp]),
+    "scnerf_pp_sample_pdf_bins_bwd": (_I, [vp, vp, vp, _I64, _I64, _I64, vp, vp]),
+    "scnerf_pp_perturb_samples_fwd": (_I, [vp, vp, _I64, _I64, vp, vp]),
+    "scnerf_pp_perturb_samples_bwd": (_I, [vp, vp, _I64, _I64, vp, vp]),
+    "scnerf_pp_depth_bwd": (_I, [vp, vp, _I64, _I64, vp, vp]),
+    "scnerf_field_train_workspace_bytes": (_SZ, [_P(Mlp), _I64, _I64, C.c_int32]),
+    "scnerf_field_train_fwd": (_I, [_P(Mlp), vp, C.c_int32, vp, vp, vp, _I64, _I64, vp, C.c_int32, vp, _SZ, vp]),
+    "scnerf_field_train_bwd": (_I, [_P(Mlp), _P(Mlp), vp, C.c_int32, vp, vp, vp, _I64, _I64, vp, vp, vp, vp, vp,
+                                    C.c_int32, vp, _SZ, vp]),
+    "scnerf_pp_pack_rays": (_I, [vp, vp, _I64, vp, vp]),
+    "scnerf_pp_pack_rays_bwd": (_I, [vp, vp, _I64, vp, vp, vp]),
+    "scnerf_pp_bg_points_fwd": (_I, [vp, vp, vp, _I64, _I64, vp, vp, vp]),
+    "scnerf_pp_bg_points_bwd": (_I, [vp, vp, vp, vp, _I64, _I64, vp, vp, vp]),
+    "scnerf_pp_composite_fg_fwd": (_I, [vp, vp, vp, vp, _I64, _I64, vp, vp, vp, vp, vp]),
+    "scnerf_pp_composite_fg_bwd": (_I, [vp, vp, vp, vp, _I64, _I64, vp, vp, vp, vp, vp, vp, vp]),
+    "scnerf_pp_composite_bg_fwd": (_I, [vp, vp, vp, vp, _I64, _I64, vp, vp, vp, vp, vp]),
+    "scnerf_pp_composite_bg_bwd": (_I, [vp, vp, vp, _I64, _I64, vp, vp, vp, vp]),
 }
 
 _lib = None

@@ -11,6 +11,8 @@
 #include "gemm_simt.cuh"
 #include "field_simt.cuh"
 #include "field_tc.cuh"
+#include "nerfpp.cuh"
+#include "../../include/scnerf_b200_nerfpp.h"
 
 using namespace scnerf;
 
@@ -545,3 +547,5 @@ int scnerf_train_step(const scnerf_camera* cam, const scnerf_camera_grads* g_cam
 }
 
 }  // extern "C"
+
+#include "api_pp.inc"

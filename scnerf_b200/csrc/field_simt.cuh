@@ -19,12 +19,28 @@ __global__ void __launch_bounds__(256) pe_points_kernel(const float* __restrict_
                                                         const float* __restrict__ z,
                                                         const float* __restrict__ pts_in,
                                                         int64_t P, int S, int L,
-                                                        float* __restrict__ out, int64_t ldo) {
+                                                        float* __restrict__ out, int64_t ldo, int dim = 3) {
   int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   int nb = L + 1;
   if (g >= P * nb) return;
   int64_t p = g / nb;
   int band = (int)(g % nb);
+  if (dim == 4) {   // NeRF++ background points (x, y, z, 1/r): nerfplusplus/nerf_network.py:42-60
+    const float* xi = pts_in + p * 4;
+    float* o = out + p * ldo;
+    if (band == 0) { o[0] = xi[0]; o[1] = xi[1]; o[2] = xi[2]; o[3] = xi[3]; }
+    else {
+      float f = (float)(1 << (band - 1));
+      o += 4 + 8 * (band - 1);
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        float sn, cs;
+        sincosf(xi[c] * f, &sn, &cs);
+        o[c] = sn; o[4 + c] = cs;
+      }
+    }
+    return;
+  }
   float x[3];
   if (pts_in) {
     x[0] = pts_in[p * 3]; x[1] = pts_in[p * 3 + 1]; x[2] = pts_in[p * 3 + 2];
@@ -97,7 +113,8 @@ __global__ void __launch_bounds__(256) pe_bwd_kernel(const float* __restrict__ r
                                                      const float* __restrict__ z, int S, int L_pos,
                                                      int L_dir, const float* __restrict__ g_pe,
                                                      int64_t ld_gpe, const float* __restrict__ g_ped,
-                                                     int64_t ld_gped, float* __restrict__ d_rays) {
+                                                     int64_t ld_gped, float* __restrict__ d_rays,
+                                                     float* __restrict__ g_z = nullptr) {
   const int64_t r = blockIdx.x;
   const float* ry = rays + r * ray_cols;
   float acc[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
@@ -109,6 +126,7 @@ __global__ void __launch_bounds__(256) pe_bwd_kernel(const float* __restrict__ r
     pe_bwd_point(x, g_pe + p * ld_gpe, L_pos, gx);
 #pragma unroll
     for (int c = 0; c < 3; ++c) { acc[c] += gx[c]; acc[3 + c] += zz * gx[c]; }
+    if (g_z) g_z[p] = gx[0] * ry[3] + gx[1] * ry[4] + gx[2] * ry[5];   // pts = o + z d
     if (g_ped) {
       // sum the raw PE-dir gradients over samples first is equivalent (PE is per ray), but the
       // contraction is linear so do it per sample and reduce the 3-vector
@@ -131,6 +149,55 @@ __global__ void __launch_bounds__(256) pe_bwd_kernel(const float* __restrict__ r
     for (int i = 0; i < nw; ++i) v += red[i][k];
     int col = k < 6 ? k : 8 + (k - 6);
     if (col < ray_cols) d_rays[r * ray_cols + col] += v;
+  }
+}
+
+// Backward of the encodings for EXPLICIT points [P,dim] and per-ray view directions [N,3]:
+// g_pts[p, 0:dim] (overwrite), g_viewdirs[r, 0:3] (+=).  One CTA per ray.
+__global__ void __launch_bounds__(128) pe_bwd_pts_kernel(const float* __restrict__ pts, int dim,
+                                                         const float* __restrict__ viewdirs, int S,
+                                                         int L_pos, int L_dir,
+                                                         const float* __restrict__ g_pe, int64_t ld_gpe,
+                                                         const float* __restrict__ g_ped, int64_t ld_gped,
+                                                         float* __restrict__ g_pts,
+                                                         float* __restrict__ g_viewdirs) {
+  const int64_t r = blockIdx.x;
+  float acc[3] = {0.f, 0.f, 0.f};
+  for (int s = threadIdx.x; s < S; s += blockDim.x) {
+    const int64_t p = r * S + s;
+    if (g_pts) {
+      const float* x = pts + p * dim;
+      const float* g = g_pe + p * ld_gpe;
+      for (int c = 0; c < dim; ++c) {
+        float gx = g[c];
+        for (int f = 0; f < L_pos; ++f) {
+          float fr = (float)(1 << f), sn, cs;
+          sincosf(x[c] * fr, &sn, &cs);
+          const float* gs = g + dim + 2 * dim * f;
+          gx += fr * (cs * gs[c] - sn * gs[dim + c]);
+        }
+        g_pts[p * dim + c] = gx;
+      }
+    }
+    if (g_viewdirs && g_ped) {
+      float gx[3];
+      pe_bwd_point(viewdirs + r * 3, g_ped + p * ld_gped, L_dir, gx);
+      acc[0] += gx[0]; acc[1] += gx[1]; acc[2] += gx[2];
+    }
+  }
+  if (g_viewdirs && g_ped) {
+    __shared__ float red[4][3];
+    int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      float v = warp_sum(acc[k]);
+      if (lane == 0) red[w][k] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < 3) {
+      int k = threadIdx.x;
+      g_viewdirs[r * 3 + k] += red[0][k] + red[1][k] + red[2][k] + red[3][k];
+    }
   }
 }
 
@@ -270,7 +337,9 @@ inline void field_grad_bufs_alloc(Arena& ar, const scnerf_mlp& m, int64_t P, Fie
 inline int field_check(const scnerf_mlp& m) {
   SCNERF_CHECK_ARG(m.D >= 2 && m.D <= SCNERF_MAX_DEPTH, "mlp depth %d unsupported", m.D);
   SCNERF_CHECK_ARG(m.skip < m.D - 1, "skip connection after the last trunk layer unsupported");
-  SCNERF_CHECK_ARG(m.input_ch == 3 + 6 * m.L_pos, "input_ch %d != 3+6*%d", m.input_ch, m.L_pos);
+  const int dim = m.pts_dim == 4 ? 4 : 3;
+  SCNERF_CHECK_ARG(m.pts_dim == 0 || m.pts_dim == 3 || m.pts_dim == 4, "pts_dim %d unsupported", m.pts_dim);
+  SCNERF_CHECK_ARG(m.input_ch == dim * (1 + 2 * m.L_pos), "input_ch %d != %d*(1+2*%d)", m.input_ch, dim, m.L_pos);
   if (m.use_viewdirs)
     SCNERF_CHECK_ARG(m.input_ch_views == 3 + 6 * m.L_dir, "input_ch_views mismatch");
   else
@@ -288,7 +357,7 @@ inline int field_simt_fwd(const scnerf_mlp& m, const float* rays, int ray_cols, 
   {
     int64_t tot = P * (m.L_pos + 1);
     SCNERF_LAUNCH(pe_points_kernel, (unsigned)cdiv(tot, 256), 256, 0, stream, rays, ray_cols, z, pts,
-                  P, S, m.L_pos, B.X5, B.ldx5);
+                  P, S, m.L_pos, B.X5, B.ldx5, m.pts_dim == 4 ? 4 : 3);
   }
   const float* in = B.X5;
   int64_t ld_in = B.ldx5;
@@ -327,7 +396,9 @@ inline int field_simt_fwd(const scnerf_mlp& m, const float* rays, int ray_cols, 
 // Backward: g_raw [P,4] -> parameter grads (+=) and d_rays (+=).  B holds the forward activations.
 inline int field_simt_bwd(const scnerf_mlp& m, const scnerf_mlp& g, const float* rays, int ray_cols,
                           const float* z, int64_t N, int S, const FieldBufs& B,
-                          const FieldGradBufs& G, const float* g_raw, float* d_rays, void* stream) {
+                          const FieldGradBufs& G, const float* g_raw, float* d_rays, void* stream,
+                          float* g_z = nullptr, const float* pts = nullptr, const float* viewdirs = nullptr,
+                          float* g_pts = nullptr, float* g_viewdirs = nullptr) {
   const int64_t P = N * S;
   const int W = m.W, Hh = m.W / 2;
   const int64_t rpb = 2048;
@@ -402,7 +473,12 @@ inline int field_simt_bwd(const scnerf_mlp& m, const scnerf_mlp& g, const float*
     const float* g_ped = m.use_viewdirs && ray_cols > 8 ? G.Gf + W : nullptr;
     int threads = S >= 192 ? 256 : (S > 64 ? 128 : 64);
     SCNERF_LAUNCH(pe_bwd_kernel, (unsigned)N, threads, 0, stream, rays, ray_cols, z, S, m.L_pos,
-                  m.L_dir, G.Gx5, B.ldx5, g_ped, B.ldf, d_rays);
+                  m.L_dir, G.Gx5, B.ldx5, g_ped, B.ldf, d_rays, g_z);
+  }
+  if (pts && (g_pts || g_viewdirs)) {   // explicit-point mode (NeRF++ background network)
+    const float* g_ped = m.use_viewdirs ? G.Gf + W : nullptr;
+    SCNERF_LAUNCH(pe_bwd_pts_kernel, (unsigned)N, 128, 0, stream, pts, m.pts_dim == 4 ? 4 : 3, viewdirs, S,
+                  m.L_pos, m.L_dir, G.Gx5, B.ldx5, g_ped, B.ldf, g_pts, g_viewdirs);
   }
   return 0;
 }

@@ -320,7 +320,7 @@ inline int field_tc_fwd_impl(const scnerf_mlp& m, const float* rays, int ray_col
 inline int field_tc_fwd(const scnerf_mlp& m, int precision, const float* rays, int ray_cols,
                         const float* z, const float* pts, const float* viewdirs, int64_t N, int S,
                         const FieldBufs& B, float* raw, void* stream, const TcFwdImages* imgs = nullptr) {
-  if (!(m.D == 8 && m.W == 256 && m.skip == 4 && m.use_viewdirs && m.L_pos == 10 && m.L_dir == 4))
+  if (!(m.D == 8 && m.W == 256 && m.skip == 4 && m.use_viewdirs && m.L_pos == 10 && m.L_dir == 4 && m.pts_dim != 4))
     return fail(SCNERF_ERR_UNSUPPORTED,
                 "tensor-core field path is specialised for the 8x256, skip-4, use_viewdirs network "
                 "(multires 10/4); use precision fp32 for other shapes");

@@ -1,0 +1,746 @@
+// NeRF++ (inverted-sphere) ray-side kernels: SURVEY.md §8 rows a6, a14 and the non-MLP part of a15.
+//   a6  render_ray_from_camera      nerfplusplus/nerf_sample_ray_split.py:196-258
+//   a14 intersect_sphere / perturb_samples / sample_pdf   nerfplusplus/ddp_train_nerf.py:50-132, 437-467
+//   a15 depth2pts_outside + the two alpha-compositing passes of NerfNet.forward
+//       nerfplusplus/ddp_model.py:16-45, 74-143
+// All of these are per-ray, HBM/latency-bound and tiny next to the MLPs; one thread, warp or CTA per
+// ray, everything recomputed in registers in the backward (no saved intermediates).
+//
+// Depth gradients: in NeRF++ the fg depths are differentiable (they are affine in the sphere depth
+// `far`, ddp_train_nerf.py:437-467), so every depth array carries a `coef` array = d(depth)/d(far),
+// propagated through the jitter, the inverse-CDF lerp and the sort.
+#pragma once
+#include "common.cuh"
+#include "raygen.cuh"
+#include "sampling.cuh"
+#include "composite.cuh"
+
+namespace scnerf {
+namespace pp {
+
+constexpr float TINY = 1e-6f;   // nerfplusplus/utils.py:8
+constexpr float HUGE_ = 1e10f;  // nerfplusplus/utils.py:7
+
+// ---------------------------------------------------------------------------------------------------
+// a6: ray generation
+// ---------------------------------------------------------------------------------------------------
+struct RaygenDev {
+  scnerf_camera cam;
+  const float* dist_initial;   // [2] or NULL (camera without distortion_noise)
+  const float* dist_noise;     // [2]
+  float dist_scale;
+  const int64_t* sel;          // [N] flat pixel index y*W+x
+  int64_t cam_idx;             // >= 0: learnable pose of that camera; < 0: `extrinsic`
+  const float* extrinsic;      // [4,4]
+  int64_t N;
+};
+
+struct Radial { float f, r, dif; };   // factor, normalised radius, (p - c)
+__device__ __forceinline__ float radial_apply(float p, float c, float k0, float k1, Radial& R) {
+  R.dif = p - c;
+  R.r = R.dif / c;
+  float r2 = R.r * R.r;
+  R.f = 1.f + r2 * k0 + r2 * r2 * k1;
+  return R.dif * R.f + c;
+}
+
+__global__ void __launch_bounds__(128) raygen_fwd_kernel(RaygenDev a, float* __restrict__ rays_o,
+                                                         float* __restrict__ rays_d,
+                                                         float* __restrict__ depth) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= a.N) return;
+  const int W = a.cam.W;
+  const int64_t fl = a.sel[i];
+  const int px = (int)(fl % W), py = (int)(fl / W);
+  Pose P;
+  if (a.cam_idx >= 0) pose_from_params(a.cam, a.cam_idx, P); else pose_from_matrix(a.extrinsic, P);
+  Intr K = load_intrinsics(a.cam);
+  float u = (float)px + 0.5f, v = (float)py + 0.5f;
+  if (a.dist_initial) {
+    float k0 = a.dist_initial[0] + a.dist_noise[0] * a.dist_scale;
+    float k1 = a.dist_initial[1] + a.dist_noise[1] * a.dist_scale;
+    Radial R;
+    u = radial_apply(u, K.cx, k0, k1, R);
+    v = radial_apply(v, K.cy, k0, k1, R);
+  }
+  // K^-1 [u v 1]^T with the analytic inverse (:234-243)
+  float dc[3] = {u * (1.f / K.fx) + (-K.cx / K.fx), v * (1.f / K.fy) + (-K.cy / K.fy), 1.f};
+  float o[3], d[3];
+#pragma unroll
+  for (int j = 0; j < 3; ++j) { d[j] = P.x[j] * dc[0] + P.y[j] * dc[1] + P.z[j] * dc[2]; o[j] = P.t[j]; }
+  Tap ty = bilinear_tap(py, a.cam.gh, a.cam.H), tx = bilinear_tap(px, a.cam.gw, a.cam.W);
+  if (a.cam.ray_o_noise) {
+    float r[3];
+    grid_lookup(a.cam.ray_o_noise, a.cam.gw, ty, tx, a.cam.ray_o_noise_scale, r);
+#pragma unroll
+    for (int j = 0; j < 3; ++j) o[j] += r[j];
+  }
+  if (a.cam.ray_d_noise) {
+    float r[3];
+    grid_lookup(a.cam.ray_d_noise, a.cam.gw, ty, tx, a.cam.ray_d_noise_scale, r);
+#pragma unroll
+    for (int j = 0; j < 3; ++j) d[j] += r[j];
+    float inv = 1.f / sqrtf(dot3(d, d));      // :254 (no epsilon)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) d[j] *= inv;
+  }
+#pragma unroll
+  for (int j = 0; j < 3; ++j) { rays_o[i * 3 + j] = o[j]; rays_d[i * 3 + j] = d[j]; }
+  if (depth) depth[i] = a.cam_idx >= 0 ? 0.f : a.extrinsic[14];   // c2w.T[2,3] = c2w[3,2]  (:256)
+}
+
+__global__ void __launch_bounds__(128) raygen_bwd_kernel(RaygenDev a, const float* __restrict__ g_o,
+                                                         const float* __restrict__ g_d,
+                                                         scnerf_camera_grads G, float* g_dist_noise) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  float gp[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};   // d/d(fx, fy, cx, cy, k0, k1)
+  if (i < a.N) {
+    const int W = a.cam.W;
+    const int64_t fl = a.sel[i];
+    const int px = (int)(fl % W), py = (int)(fl / W);
+    Pose P;
+    const bool learn_pose = a.cam_idx >= 0;
+    if (learn_pose) pose_from_params(a.cam, a.cam_idx, P); else pose_from_matrix(a.extrinsic, P);
+    Intr K = load_intrinsics(a.cam);
+    float u0 = (float)px + 0.5f, v0 = (float)py + 0.5f, u = u0, v = v0, k0 = 0.f, k1 = 0.f;
+    Radial Ru{1.f, 0.f, 0.f}, Rv{1.f, 0.f, 0.f};
+    if (a.dist_initial) {
+      k0 = a.dist_initial[0] + a.dist_noise[0] * a.dist_scale;
+      k1 = a.dist_initial[1] + a.dist_noise[1] * a.dist_scale;
+      u = radial_apply(u0, K.cx, k0, k1, Ru);
+      v = radial_apply(v0, K.cy, k0, k1, Rv);
+    }
+    float dc[3] = {(u - K.cx) / K.fx, (v - K.cy) / K.fy, 1.f};
+    float go[3] = {g_o[i * 3], g_o[i * 3 + 1], g_o[i * 3 + 2]};
+    float gd[3] = {g_d[i * 3], g_d[i * 3 + 1], g_d[i * 3 + 2]};
+    Tap ty = bilinear_tap(py, a.cam.gh, a.cam.H), tx = bilinear_tap(px, a.cam.gw, a.cam.W);
+    if (a.cam.ray_d_noise) {
+      float dp[3], r[3];
+      grid_lookup(a.cam.ray_d_noise, a.cam.gw, ty, tx, a.cam.ray_d_noise_scale, r);
+#pragma unroll
+      for (int j = 0; j < 3; ++j) dp[j] = P.x[j] * dc[0] + P.y[j] * dc[1] + P.z[j] * dc[2] + r[j];
+      float n2 = dot3(dp, dp), n = sqrtf(n2);
+      float k = dot3(gd, dp) / (n2 * n);
+#pragma unroll
+      for (int j = 0; j < 3; ++j) gd[j] = gd[j] / n - k * dp[j];
+      if (G.ray_d_noise) grid_scatter(G.ray_d_noise, a.cam.gw, ty, tx, a.cam.ray_d_noise_scale, gd);
+    }
+    if (a.cam.ray_o_noise && G.ray_o_noise)
+      grid_scatter(G.ray_o_noise, a.cam.gw, ty, tx, a.cam.ray_o_noise_scale, go);
+    float g_dc0 = dot3(gd, P.x), g_dc1 = dot3(gd, P.y);
+    if (learn_pose && G.extrinsics_noise) {
+      float gx[3], gy[3], gz[3], g_a[3], g_b[3];
+#pragma unroll
+      for (int j = 0; j < 3; ++j) { gx[j] = gd[j] * dc[0]; gy[j] = gd[j] * dc[1]; gz[j] = gd[j] * dc[2]; }
+      pose_bwd(P, gx, gy, gz, g_a, g_b);
+      float* ge = G.extrinsics_noise + a.cam_idx * 9;
+      float s = a.cam.extrinsics_noise_scale;
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        atomicAdd(ge + j, s * g_a[j]);
+        atomicAdd(ge + 3 + j, s * g_b[j]);
+        atomicAdd(ge + 6 + j, s * go[j]);
+      }
+    }
+    // dc0 = (u - cx)/fx, u = (u0 - cx) f(r) + cx, r = (u0 - cx)/cx, f = 1 + r^2 k0 + r^4 k1
+    float g_u = g_dc0 / K.fx, g_v = g_dc1 / K.fy;
+    gp[0] = -g_dc0 * (u - K.cx) / (K.fx * K.fx);
+    gp[1] = -g_dc1 * (v - K.cy) / (K.fy * K.fy);
+    gp[2] = -g_dc0 / K.fx;
+    gp[3] = -g_dc1 / K.fy;
+    if (a.dist_initial) {
+      float r2 = Ru.r * Ru.r, gf = g_u * Ru.dif;
+      float gr = gf * (2.f * Ru.r * k0 + 4.f * r2 * Ru.r * k1);
+      gp[2] += g_u * (1.f - Ru.f) + gr * (-u0 / (K.cx * K.cx));
+      gp[4] += gf * r2; gp[5] += gf * r2 * r2;
+      r2 = Rv.r * Rv.r; gf = g_v * Rv.dif;
+      gr = gf * (2.f * Rv.r * k0 + 4.f * r2 * Rv.r * k1);
+      gp[3] += g_v * (1.f - Rv.f) + gr * (-v0 / (K.cy * K.cy));
+      gp[4] += gf * r2; gp[5] += gf * r2 * r2;
+    }
+  }
+  __shared__ float red[4][6];
+  int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < 6; ++k) {
+    float v = warp_sum(gp[k]);
+    if (lane == 0) red[w][k] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < 6) {
+    int k = threadIdx.x;
+    float v = red[0][k] + red[1][k] + red[2][k] + red[3][k];
+    if (k < 4) {
+      if (G.intrinsics_noise) {
+        float init = a.cam.intrinsics_initial[k];
+        float s = a.cam.intrinsics_noise_scale * (a.cam.multiplicative_noise ? init : 1.f);
+        atomicAdd(G.intrinsics_noise + k, v * s);
+      }
+    } else if (g_dist_noise && a.dist_initial) {
+      atomicAdd(g_dist_noise + (k - 4), v * a.dist_scale);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// a14: sphere intersection and depth sampling
+// ---------------------------------------------------------------------------------------------------
+// far[r] = d1 + d2 (ddp_train_nerf.py:50-68); *miss counts rays whose closest approach is outside
+// the unit sphere (the reference raises; the host mirror checks the counter and raises too).
+__global__ void __launch_bounds__(128) sphere_fwd_kernel(const float* __restrict__ o,
+                                                         const float* __restrict__ d, int64_t N,
+                                                         float* __restrict__ far, int* miss) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  const float* oo = o + i * 3; const float* dd_ = d + i * 3;
+  float dd = dot3(dd_, dd_), od = dot3(dd_, oo);
+  float d1 = -od / dd;
+  float p[3] = {oo[0] + d1 * dd_[0], oo[1] + d1 * dd_[1], oo[2] + d1 * dd_[2]};
+  float pn2 = dot3(p, p);
+  if (pn2 >= 1.f && miss) atomicAdd(miss, 1);
+  float d2 = sqrtf(1.f - pn2) * (1.f / sqrtf(dd));
+  far[i] = d1 + d2;
+}
+__global__ void __launch_bounds__(128) sphere_bwd_kernel(const float* __restrict__ o,
+                                                         const float* __restrict__ d,
+                                                         const float* __restrict__ g_far, int64_t N,
+                                                         float* __restrict__ g_o, float* __restrict__ g_d) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  const float* oo = o + i * 3; const float* dv = d + i * 3;
+  float dd = dot3(dv, dv), od = dot3(dv, oo);
+  float d1 = -od / dd;
+  float p[3] = {oo[0] + d1 * dv[0], oo[1] + d1 * dv[1], oo[2] + d1 * dv[2]};
+  float pn2 = dot3(p, p), sq = sqrtf(1.f - pn2), cosd = 1.f / sqrtf(dd);
+  float g = g_far[i];
+  float g_pn2 = g * (-0.5f / sq) * cosd;
+  float g_dd = g * sq * (-0.5f) * cosd / dd;
+  float gp[3] = {2.f * p[0] * g_pn2, 2.f * p[1] * g_pn2, 2.f * p[2] * g_pn2};
+  float g_d1 = g + dot3(gp, dv);
+  float g_od = -g_d1 / dd;
+  g_dd += g_d1 * od / (dd * dd);
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+    g_o[i * 3 + j] += gp[j] + g_od * dv[j];
+    g_d[i * 3 + j] += d1 * gp[j] + g_od * oo[j] + 2.f * dv[j] * g_dd;
+  }
+}
+
+// Level-0 depths (ddp_train_nerf.py:437-449): fg[r,i] = near + i*step jittered inside its interval,
+// bg[r,i] = linspace(0,1,S)[i] jittered; coef = d(fg)/d(far).  t_* == NULL: no jitter.
+__global__ void __launch_bounds__(256) level0_depths_kernel(const float* __restrict__ far, float near_,
+                                                            int64_t N, int S, const float* __restrict__ t_fg,
+                                                            const float* __restrict__ t_bg,
+                                                            float* __restrict__ fg, float* __restrict__ coef,
+                                                            float* __restrict__ bg) {
+  int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= N * S) return;
+  int64_t r = g / S;
+  int i = (int)(g % S);
+  float step = (far[r] - near_) / (float)(S - 1);
+  float cstep = 1.f / (float)(S - 1);
+  auto zf = [&](int k) { return __fadd_rn(near_, __fmul_rn((float)k, step)); };   // no FMA: mul then add, as torch
+  auto cf = [&](int k) { return (float)k * cstep; };
+  auto zb = [&](int k) { return linspace01(k, S); };
+  float z = zf(i), c = cf(i);
+  if (t_fg) {
+    float up = i < S - 1 ? 0.5f * (zf(i + 1) + z) : z, lo = i > 0 ? 0.5f * (z + zf(i - 1)) : z;
+    float cu = i < S - 1 ? 0.5f * (cf(i + 1) + c) : c, cl = i > 0 ? 0.5f * (c + cf(i - 1)) : c;
+    float t = t_fg[g];
+    z = __fadd_rn(lo, __fmul_rn(up - lo, t));
+    c = cl + (cu - cl) * t;
+  }
+  fg[g] = z;
+  if (coef) coef[g] = c;
+  if (bg) {
+    float b = zb(i);
+    if (t_bg) {
+      float up = i < S - 1 ? 0.5f * (zb(i + 1) + b) : b, lo = i > 0 ? 0.5f * (b + zb(i - 1)) : b;
+      b = __fadd_rn(lo, __fmul_rn(up - lo, t_bg[g]));
+    }
+    bg[g] = b;
+  }
+}
+
+// sample_pdf (ddp_train_nerf.py:83-132) on bins = depth mid-points, weights[1:-1] (:451-467), fused
+// with sort(cat(depth, samples)).  One CTA per ray.  `coef` (optional) rides along as the sort payload.
+struct SampleArgs {
+  const float* depth;   // [N,S] ascending
+  const float* coef;    // [N,S] or NULL
+  const float* w;       // [N,S]  (uses columns 1..S-2)
+  const float* u;       // [N,Nf] or NULL (det: linspace(0,1,Nf))
+  int S, Nf, sort_n;
+  int direct;           // 1: `depth` holds the bin edges [N,S] themselves and `w` is [N,S-1] (the
+                        //    reference's sample_pdf(bins, weights) signature); 0: mid-points + w[:,1:-1]
+  float* tfrac;         // [N,Nf] optional: the lerp fraction t (for the backward w.r.t. bins)
+  float* samples;       // [N,Nf] optional
+  int64_t* above;       // [N,Nf] optional (count-based index)
+  float* merged;        // [N,S+Nf]
+  float* merged_coef;   // [N,S+Nf] or NULL
+};
+__global__ void __launch_bounds__(128) sample_pdf_kernel(SampleArgs a) {
+  extern __shared__ float pp_smem[];
+  const int M = a.direct ? a.S - 1 : a.S - 2;   // number of pdf bins
+  float* cdf = pp_smem;                   // [M+1]
+  float* bins = cdf + (M + 1);            // [M+1]
+  float* cbin = bins + (M + 1);           // [M+1]
+  float* key = cbin + (M + 1);            // [sort_n]
+  float* pay = key + a.sort_n;            // [sort_n]
+  const int64_t r = blockIdx.x;
+  const float* dep = a.depth + r * a.S;
+  const float* cf = a.coef ? a.coef + r * a.S : nullptr;
+  const float* w = a.direct ? a.w + r * M : a.w + r * a.S + 1;
+  for (int i = threadIdx.x; i <= M; i += blockDim.x) {
+    bins[i] = a.direct ? dep[i] : 0.5f * (dep[i + 1] + dep[i]);
+    cbin[i] = cf ? (a.direct ? cf[i] : 0.5f * (cf[i + 1] + cf[i])) : 0.f;
+  }
+  if (threadIdx.x == 0) {
+    // torch.sum then torch.cumsum over M <= 4094 values: sequential fp32 in index order
+    float tot = 0.f;
+    for (int i = 0; i < M; ++i) tot += w[i] + TINY;
+    float run = 0.f;
+    cdf[0] = 0.f;
+    for (int i = 0; i < M; ++i) { run += (w[i] + TINY) / tot; cdf[i + 1] = run; }
+  }
+  __syncthreads();
+  const int St = a.S + a.Nf;
+  for (int j = threadIdx.x; j < a.Nf; j += blockDim.x) {
+    float u = a.u ? a.u[r * a.Nf + j] : linspace01(j, a.Nf);
+    int above = upper_bound(cdf, M, u);            // #{i < M : cdf[i] <= u}  (:110)
+    int below = max(above - 1, 0);
+    float c0 = cdf[below], c1 = cdf[above];
+    float denom = c1 - c0;
+    if (denom < TINY) denom = 1.f;
+    float t = (u - c0) / denom;
+    float s = __fadd_rn(bins[below], __fmul_rn(t, __fadd_rn(bins[above] - bins[below], TINY)));
+    if (a.samples) a.samples[r * a.Nf + j] = s;
+    if (a.above) a.above[r * a.Nf + j] = above;
+    if (a.tfrac) a.tfrac[r * a.Nf + j] = t;
+    key[a.S + j] = s;
+    pay[a.S + j] = cbin[below] + t * (cbin[above] - cbin[below]);
+  }
+  if (!a.merged) return;
+  for (int i = threadIdx.x; i < a.S; i += blockDim.x) { key[i] = dep[i]; pay[i] = cf ? cf[i] : 0.f; }
+  for (int i = St + threadIdx.x; i < a.sort_n; i += blockDim.x) { key[i] = INFINITY; pay[i] = 0.f; }
+  __syncthreads();
+  for (int k = 2; k <= a.sort_n; k <<= 1)
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = threadIdx.x; i < a.sort_n; i += blockDim.x) {
+        int l = i ^ j;
+        if (l > i) {
+          bool up = (i & k) == 0;
+          float ki = key[i], kl = key[l];
+          if ((ki > kl) == up) {
+            key[i] = kl; key[l] = ki;
+            float t = pay[i]; pay[i] = pay[l]; pay[l] = t;
+          }
+        }
+      }
+      __syncthreads();
+    }
+  for (int i = threadIdx.x; i < St; i += blockDim.x) {
+    a.merged[r * St + i] = key[i];
+    if (a.merged_coef) a.merged_coef[r * St + i] = pay[i];
+  }
+}
+
+// sample_pdf backward w.r.t. the bin edges: samples = b[below] + t (b[above] - b[below] + TINY)
+__global__ void __launch_bounds__(256) sample_pdf_bwd_kernel(const float* __restrict__ g_s,
+                                                             const int64_t* __restrict__ above,
+                                                             const float* __restrict__ tfrac, int64_t N, int Nf,
+                                                             int nb, float* __restrict__ g_bins) {
+  int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= N * Nf) return;
+  int64_t r = g / Nf;
+  int ab = (int)above[g], be = max(ab - 1, 0);
+  float t = tfrac[g], v = g_s[g];
+  atomicAdd(g_bins + r * nb + be, v * (1.f - t));
+  atomicAdd(g_bins + r * nb + ab, v * t);
+}
+
+// perturb_samples (ddp_train_nerf.py:71-80) for arbitrary z_vals[N,S], and its (linear) backward
+__global__ void __launch_bounds__(256) perturb_fwd_kernel(const float* __restrict__ z, const float* __restrict__ t,
+                                                          int64_t N, int S, float* __restrict__ out) {
+  int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= N * S) return;
+  int i = (int)(g % S);
+  float zi = z[g];
+  float up = i < S - 1 ? 0.5f * (z[g + 1] + zi) : zi, lo = i > 0 ? 0.5f * (zi + z[g - 1]) : zi;
+  out[g] = __fadd_rn(lo, __fmul_rn(up - lo, t[g]));
+}
+__global__ void __launch_bounds__(256) perturb_bwd_kernel(const float* __restrict__ g_out, const float* __restrict__ t,
+                                                          int64_t N, int S, float* __restrict__ g_z) {
+  int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= N * S) return;
+  int j = (int)(g % S);
+  float tj = t[g];
+  float v = g_out[g] * ((1.f - tj) * (j > 0 ? 0.5f : 1.f) + tj * (j < S - 1 ? 0.5f : 1.f));
+  if (j + 1 < S) v += g_out[g + 1] * (1.f - t[g + 1]) * 0.5f;   // lower_{j+1} = mid(z_j, z_{j+1})
+  if (j > 0) v += g_out[g - 1] * t[g - 1] * 0.5f;               // upper_{j-1} = mid(z_{j-1}, z_j)
+  g_z[g] = v;
+}
+
+// g_far[r] += sum_s g_z[r,s] * coef[r,s]
+__global__ void __launch_bounds__(128) depth_bwd_kernel(const float* __restrict__ g_z,
+                                                        const float* __restrict__ coef, int64_t N, int S,
+                                                        float* __restrict__ g_far) {
+  const int lane = threadIdx.x & 31;
+  const int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (r >= N) return;
+  float acc = 0.f;
+  for (int s = lane; s < S; s += 32) acc += g_z[r * S + s] * coef[r * S + s];
+  acc = warp_sum(acc);
+  if (lane == 0) g_far[r] += acc;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// a15: background points — depth2pts_outside (ddp_model.py:16-45), written in the FLIPPED sample
+// order NerfNet.forward feeds the bg MLP (:120): out[r, s] uses depth bg_z[r, S-1-s].
+// ---------------------------------------------------------------------------------------------------
+struct SphereRay {   // per-ray quantities of depth2pts_outside
+  float dd, od, d1, pmid[3], pmn, cosd, sq, d2, ps[3], araw[3], an, a[3], phi, k;
+};
+__device__ __forceinline__ void cross3(const float* x, const float* y, float* o) {
+  o[0] = x[1] * y[2] - x[2] * y[1]; o[1] = x[2] * y[0] - x[0] * y[2]; o[2] = x[0] * y[1] - x[1] * y[0];
+}
+__device__ __forceinline__ void sphere_ray(const float* o, const float* d, SphereRay& R) {
+  R.dd = dot3(d, d); R.od = dot3(d, o);
+  R.d1 = -R.od / R.dd;
+#pragma unroll
+  for (int j = 0; j < 3; ++j) R.pmid[j] = o[j] + R.d1 * d[j];
+  R.pmn = sqrtf(dot3(R.pmid, R.pmid));
+  R.cosd = 1.f / sqrtf(R.dd);
+  R.sq = sqrtf(1.f - R.pmn * R.pmn);
+  R.d2 = R.sq * R.cosd;
+#pragma unroll
+  for (int j = 0; j < 3; ++j) R.ps[j] = o[j] + (R.d1 + R.d2) * d[j];
+  cross3(o, R.ps, R.araw);
+  R.an = sqrtf(dot3(R.araw, R.araw));
+#pragma unroll
+  for (int j = 0; j < 3; ++j) R.a[j] = R.araw[j] / R.an;
+  R.phi = asinf(R.pmn);
+  R.k = dot3(R.a, R.ps);
+}
+__device__ __forceinline__ void sphere_point(const SphereRay& R, float q, float* pn_raw, float& nrm,
+                                             float& sn, float& cs) {
+  float theta = asinf(R.pmn * q);
+  sincosf(R.phi - theta, &sn, &cs);
+  float axp[3];
+  cross3(R.a, R.ps, axp);
+#pragma unroll
+  for (int j = 0; j < 3; ++j) pn_raw[j] = R.ps[j] * cs + axp[j] * sn + R.a[j] * R.k * (1.f - cs);
+  nrm = sqrtf(dot3(pn_raw, pn_raw));
+}
+
+__global__ void __launch_bounds__(256) bg_points_fwd_kernel(const float* __restrict__ o,
+                                                            const float* __restrict__ d,
+                                                            const float* __restrict__ bg_z, int64_t N,
+                                                            int S, float* __restrict__ pts4,
+                                                            float* __restrict__ depth_real) {
+  int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= N * S) return;
+  int64_t r = g / S;
+  int s = (int)(g % S);
+  SphereRay R;
+  sphere_ray(o + r * 3, d + r * 3, R);
+  float q = bg_z[r * S + (S - 1 - s)];
+  float pn[3], nrm, sn, cs;
+  sphere_point(R, q, pn, nrm, sn, cs);
+  float* out = pts4 + g * 4;
+  out[0] = pn[0] / nrm; out[1] = pn[1] / nrm; out[2] = pn[2] / nrm; out[3] = q;
+  if (depth_real)   // ddp_model.py:44: 1/(depth + TINY) * cos(theta) * ray_d_cos + d1
+    depth_real[g] = 1.f / (q + TINY) * cosf(asinf(R.pmn * q)) * R.cosd + R.d1;
+}
+
+// one CTA per ray: d(loss)/d(pts4[r,s,0:3]) -> g_o[r], g_d[r] (+=)
+__global__ void __launch_bounds__(128) bg_points_bwd_kernel(const float* __restrict__ o,
+                                                            const float* __restrict__ d,
+                                                            const float* __restrict__ bg_z,
+                                                            const float* __restrict__ g_pts4, int S,
+                                                            float* __restrict__ g_o, float* __restrict__ g_d) {
+  const int64_t r = blockIdx.x;
+  const float* oo = o + r * 3; const float* dv = d + r * 3;
+  SphereRay R;
+  sphere_ray(oo, dv, R);
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};   // g_ps(3), g_a(3), g_phi, g_pmn
+  float axp[3];
+  cross3(R.a, R.ps, axp);
+  for (int s = threadIdx.x; s < S; s += blockDim.x) {
+    float q = bg_z[r * S + (S - 1 - s)];
+    float pn[3], nrm, sn, cs;
+    sphere_point(R, q, pn, nrm, sn, cs);
+    const float* gin = g_pts4 + (r * S + s) * 4;
+    float ph[3] = {pn[0] / nrm, pn[1] / nrm, pn[2] / nrm};
+    float gdot = gin[0] * ph[0] + gin[1] * ph[1] + gin[2] * ph[2];
+    float g[3] = {(gin[0] - ph[0] * gdot) / nrm, (gin[1] - ph[1] * gdot) / nrm, (gin[2] - ph[2] * gdot) / nrm};
+    float ga = dot3(g, R.a);
+    float gxa[3], psxg[3];
+    cross3(g, R.a, gxa);        // d(a x ps)/d(ps): g_ps += (g*sn) x a
+    cross3(R.ps, g, psxg);      // d(a x ps)/d(a) : g_a  += ps x (g*sn)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      acc[j] += g[j] * cs + gxa[j] * sn + R.a[j] * ga * (1.f - cs);
+      acc[3 + j] += psxg[j] * sn + (g[j] * R.k + R.ps[j] * ga) * (1.f - cs);
+    }
+    float g_c = dot3(g, R.ps) - ga * R.k, g_s = dot3(g, axp);
+    float g_ang = -g_c * sn + g_s * cs;
+    acc[6] += g_ang;
+    float x = R.pmn * q;
+    acc[7] += -g_ang * q / sqrtf(1.f - x * x);
+  }
+  __shared__ float red[4][8];
+  int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    float v = warp_sum(acc[k]);
+    if (lane == 0) red[w][k] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t[8];
+    for (int k = 0; k < 8; ++k) t[k] = red[0][k] + red[1][k] + red[2][k] + red[3][k];
+    float g_ps[3] = {t[0], t[1], t[2]}, g_a[3] = {t[3], t[4], t[5]};
+    float g_pmn = t[7] + t[6] / R.sq;                       // phi = asin(pmn)
+    // a = araw/|araw|, araw = o x ps
+    float gaa = dot3(g_a, R.a);
+    float g_ar[3] = {(g_a[0] - R.a[0] * gaa) / R.an, (g_a[1] - R.a[1] * gaa) / R.an, (g_a[2] - R.a[2] * gaa) / R.an};
+    float go[3], tmp[3];
+    cross3(R.ps, g_ar, go);                                 // g_o  = ps x g_araw
+    cross3(g_ar, oo, tmp);                                  // g_ps += g_araw x o
+#pragma unroll
+    for (int j = 0; j < 3; ++j) g_ps[j] += tmp[j];
+    // ps = o + (d1 + d2) d
+    float gd[3], g_d12 = dot3(g_ps, dv);
+#pragma unroll
+    for (int j = 0; j < 3; ++j) { go[j] += g_ps[j]; gd[j] = (R.d1 + R.d2) * g_ps[j]; }
+    float g_d1 = g_d12, g_d2 = g_d12;
+    // d2 = sqrt(1 - pmn^2) * cosd ; cosd = dd^-1/2
+    g_pmn += g_d2 * (-R.pmn / R.sq) * R.cosd;
+    float g_dd = g_d2 * R.sq * (-0.5f) * R.cosd / R.dd;
+    // pmn = |pmid| ; pmid = o + d1 d
+    float gpm[3] = {g_pmn * R.pmid[0] / R.pmn, g_pmn * R.pmid[1] / R.pmn, g_pmn * R.pmid[2] / R.pmn};
+    g_d1 += dot3(gpm, dv);
+#pragma unroll
+    for (int j = 0; j < 3; ++j) { go[j] += gpm[j]; gd[j] += R.d1 * gpm[j]; }
+    // d1 = -od/dd
+    float g_od = -g_d1 / R.dd;
+    g_dd += g_d1 * R.od / (R.dd * R.dd);
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      g_o[r * 3 + j] += go[j] + g_od * dv[j];
+      g_d[r * 3 + j] += gd[j] + g_od * oo[j] + 2.f * dv[j] * g_dd;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// a15: alpha compositing of NerfNet.forward.  One warp per ray.
+//   mode 0 (foreground, ddp_model.py:98-110): dists = |d| * [diff(z), zmax - z_last]
+//   mode 1 (background, ddp_model.py:120-139): raw is in flipped order, z is the UNflipped bg_z,
+//          dists = [zf[s]-zf[s+1], 1e10]; outputs are scaled by bg_lambda and added to fg_rgb.
+// raw[.,0:3] = rgb before the sigmoid, raw[.,3] = sigma before the abs (nerf_network.py:132-139).
+// ---------------------------------------------------------------------------------------------------
+struct CompArgs {
+  int mode;
+  const float* raw;      // [N,S,4]
+  const float* z;        // [N,S]
+  const float* rays_d;   // [N,3]   (mode 0)
+  const float* zmax;     // [N]     (mode 0)
+  const float* lambda_in;   // [N]   (mode 1) bg_lambda from the fg pass
+  const float* fg_rgb;      // [N,3] (mode 1)
+  int64_t N; int S;
+  float* weights;        // [N,S]
+  float* rgb_map;        // [N,3]  mode 0: fg_rgb ; mode 1: bg_rgb (scaled)
+  float* depth_map;      // [N]    mode 0: fg_depth ; mode 1: bg_depth (scaled)
+  float* lambda_out;     // [N]    mode 0
+  float* rgb_total;      // [N,3]  mode 1: fg_rgb + bg_rgb
+};
+__device__ __forceinline__ float comp_z(const CompArgs& a, int64_t r, int s) {
+  return a.mode == 0 ? a.z[r * a.S + s] : a.z[r * a.S + (a.S - 1 - s)];
+}
+__device__ __forceinline__ float comp_delta(const CompArgs& a, int64_t r, int s, float zs) {
+  if (a.mode == 0) return (s + 1 < a.S) ? a.z[r * a.S + s + 1] - zs : a.zmax[r] - zs;
+  return (s + 1 < a.S) ? zs - comp_z(a, r, s + 1) : HUGE_;
+}
+__device__ __forceinline__ float sigmoidf(float x) { return 1.f / (1.f + expf(-x)); }
+
+__global__ void __launch_bounds__(128) composite_fwd_kernel(CompArgs a) {
+  const int lane = threadIdx.x & 31;
+  const int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (r >= a.N) return;
+  float dn = 1.f;
+  if (a.mode == 0) { const float* d = a.rays_d + r * 3; dn = sqrtf(dot3(d, d)); }
+  float carry = 1.f, ar = 0.f, ag = 0.f, ab = 0.f, az = 0.f;
+  for (int s0 = 0; s0 < a.S; s0 += 32) {
+    int s = s0 + lane;
+    float alpha = 0.f, zs = 0.f, cr = 0.f, cg = 0.f, cb = 0.f;
+    if (s < a.S) {
+      zs = comp_z(a, r, s);
+      float dist = dn * comp_delta(a, r, s, zs);
+      const float* rw = a.raw + (r * a.S + s) * 4;
+      alpha = 1.f - expf(-fabsf(rw[3]) * dist);
+      cr = sigmoidf(rw[0]); cg = sigmoidf(rw[1]); cb = sigmoidf(rw[2]);
+    }
+    float f = (s < a.S) ? (1.f - alpha + TINY) : 1.f;
+    float incl = warp_incl_prod(f, lane);
+    float excl = __shfl_up_sync(0xffffffffu, incl, 1);
+    if (lane == 0) excl = 1.f;
+    float w = alpha * carry * excl;
+    carry *= __shfl_sync(0xffffffffu, incl, 31);
+    if (s < a.S) {
+      if (a.weights) a.weights[r * a.S + s] = w;
+      ar += w * cr; ag += w * cg; ab += w * cb; az += w * zs;
+    }
+  }
+  ar = warp_sum(ar); ag = warp_sum(ag); ab = warp_sum(ab); az = warp_sum(az);
+  if (lane == 0) {
+    if (a.mode == 0) {
+      a.rgb_map[r * 3] = ar; a.rgb_map[r * 3 + 1] = ag; a.rgb_map[r * 3 + 2] = ab;
+      if (a.depth_map) a.depth_map[r] = az;
+      a.lambda_out[r] = carry;           // T[..., -1]
+    } else {
+      float lam = a.lambda_in[r];
+      float br = lam * ar, bgc = lam * ag, bb = lam * ab;
+      if (a.rgb_map) { a.rgb_map[r * 3] = br; a.rgb_map[r * 3 + 1] = bgc; a.rgb_map[r * 3 + 2] = bb; }
+      if (a.depth_map) a.depth_map[r] = lam * az;
+      a.rgb_total[r * 3] = a.fg_rgb[r * 3] + br;
+      a.rgb_total[r * 3 + 1] = a.fg_rgb[r * 3 + 1] + bgc;
+      a.rgb_total[r * 3 + 2] = a.fg_rgb[r * 3 + 2] + bb;
+    }
+  }
+}
+
+struct CompBwdArgs {
+  CompArgs f;
+  const float* g_rgb;       // [N,3]  mode 0: d/d(fg_rgb) ; mode 1: d/d(rgb_total)
+  const float* g_lambda;    // [N]    mode 0: d/d(bg_lambda) (from the bg pass) or NULL
+  float* g_raw;             // [N,S,4] overwrite
+  float* g_z;               // [N,S]  mode 0, overwrite
+  float* g_zmax;            // [N]    mode 0, +=
+  float* g_d;               // [N,3]  mode 0, += (through |d|)
+  float* g_lambda_out;      // [N]    mode 1, overwrite
+};
+__global__ void __launch_bounds__(128) composite_bwd_kernel(CompBwdArgs b) {
+  extern __shared__ float pp_smem[];
+  const CompArgs& a = b.f;
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + wib;
+  if (r >= a.N) return;
+  float* T_s = pp_smem + (size_t)wib * 3 * a.S;
+  float* A_s = T_s + a.S;
+  float* Gz = A_s + a.S;      // per-sample d/d(z) accumulator (mode 0)
+  float dn = 1.f;
+  const float* d = nullptr;
+  if (a.mode == 0) { d = a.rays_d + r * 3; dn = sqrtf(dot3(d, d)); }
+  float carry = 1.f, ur = 0.f, ug = 0.f, ub = 0.f;   // unscaled rgb (mode 1 needs it for g_lambda)
+  for (int s0 = 0; s0 < a.S; s0 += 32) {
+    int s = s0 + lane;
+    float alpha = 0.f;
+    const float* rw = a.raw + (r * a.S + s) * 4;
+    if (s < a.S) {
+      float zs = comp_z(a, r, s);
+      alpha = 1.f - expf(-fabsf(rw[3]) * dn * comp_delta(a, r, s, zs));
+    }
+    float f = (s < a.S) ? (1.f - alpha + TINY) : 1.f;
+    float incl = warp_incl_prod(f, lane);
+    float excl = __shfl_up_sync(0xffffffffu, incl, 1);
+    if (lane == 0) excl = 1.f;
+    if (s < a.S) {
+      float T = carry * excl, w = alpha * T;
+      T_s[s] = T; A_s[s] = alpha; Gz[s] = 0.f;
+      ur += w * sigmoidf(rw[0]); ug += w * sigmoidf(rw[1]); ub += w * sigmoidf(rw[2]);
+    }
+    carry *= __shfl_sync(0xffffffffu, incl, 31);
+  }
+  __syncwarp();
+  float gr = b.g_rgb[r * 3], gg = b.g_rgb[r * 3 + 1], gb = b.g_rgb[r * 3 + 2];
+  float lam_term = 0.f;   // g_lambda * lambda (mode 0): d(lambda)/d(alpha_s) = -lambda / f_s
+  if (a.mode == 0) {
+    if (b.g_lambda) lam_term = b.g_lambda[r] * carry;
+  } else {
+    ur = warp_sum(ur); ug = warp_sum(ug); ub = warp_sum(ub);
+    if (lane == 0) b.g_lambda_out[r] = gr * ur + gg * ug + gb * ub;
+    float lam = a.lambda_in[r];
+    gr *= lam; gg *= lam; gb *= lam;
+  }
+  float suffix_carry = 0.f, g_dn = 0.f, g_zmax = 0.f;
+  const int nchunk = (a.S + 31) / 32;
+  for (int c = nchunk - 1; c >= 0; --c) {
+    int s = c * 32 + lane;
+    float gw = 0.f, w = 0.f, alpha = 0.f, T = 0.f, cr = 0.f, cg = 0.f, cb = 0.f;
+    const float* rw = a.raw + (r * a.S + s) * 4;
+    if (s < a.S) {
+      alpha = A_s[s]; T = T_s[s]; w = alpha * T;
+      cr = sigmoidf(rw[0]); cg = sigmoidf(rw[1]); cb = sigmoidf(rw[2]);
+      gw = gr * cr + gg * cg + gb * cb;
+    }
+    float v = gw * w, incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      float n = __shfl_down_sync(0xffffffffu, incl, o);
+      if (lane + o < 32) incl += n;
+    }
+    float suffix = suffix_carry + (incl - v);
+    suffix_carry += __shfl_sync(0xffffffffu, incl, 0);
+    if (s < a.S) {
+      float fs = 1.f - alpha + TINY;
+      float g_alpha = gw * T - (suffix + lam_term) / fs;
+      float zs = comp_z(a, r, s);
+      float delta = comp_delta(a, r, s, zs);
+      float sg = rw[3], as = fabsf(sg);
+      float e = expf(-as * delta * dn);
+      float g_sigma = g_alpha * delta * dn * e;
+      float* go = b.g_raw + (r * a.S + s) * 4;
+      go[0] = w * gr * cr * (1.f - cr);
+      go[1] = w * gg * cg * (1.f - cg);
+      go[2] = w * gb * cb * (1.f - cb);
+      go[3] = sg > 0.f ? g_sigma : (sg < 0.f ? -g_sigma : 0.f);
+      if (a.mode == 0) {
+        float g_dist = g_alpha * as * e;
+        g_dn += g_dist * delta;
+        float g_delta = g_dist * dn;
+        atomicAdd(&Gz[s], -g_delta);
+        if (s + 1 < a.S) atomicAdd(&Gz[s + 1], g_delta); else g_zmax += g_delta;
+      }
+    }
+  }
+  if (a.mode == 0) {
+    __syncwarp();
+    for (int s = lane; s < a.S; s += 32) b.g_z[r * a.S + s] = Gz[s];
+    g_dn = warp_sum(g_dn); g_zmax = warp_sum(g_zmax);
+    if (lane == 0 && b.g_zmax) b.g_zmax[r] += g_zmax;
+    if (lane < 3 && b.g_d) b.g_d[r * 3 + lane] += g_dn * d[lane] / dn;
+  }
+}
+
+// viewdirs = d/|d| (ddp_model.py:83-84): rays[N,11] = [o, d, 0, 0, viewdirs]
+__global__ void __launch_bounds__(128) pack_rays_kernel(const float* __restrict__ o, const float* __restrict__ d,
+                                                        int64_t N, float* __restrict__ rays) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  const float* dv = d + i * 3;
+  float inv = 1.f / sqrtf(dot3(dv, dv));
+  float* out = rays + i * 11;
+#pragma unroll
+  for (int j = 0; j < 3; ++j) { out[j] = o[i * 3 + j]; out[3 + j] = dv[j]; out[8 + j] = dv[j] * inv; }
+  out[6] = 0.f; out[7] = 0.f;
+}
+// d_rays[N,11] -> g_o, g_d (+=), including the viewdirs normalisation
+__global__ void __launch_bounds__(128) unpack_rays_bwd_kernel(const float* __restrict__ d, const float* __restrict__ d_rays,
+                                                              int64_t N, float* __restrict__ g_o, float* __restrict__ g_d) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  const float* dv = d + i * 3;
+  const float* g = d_rays + i * 11;
+  float n2 = dot3(dv, dv), inv = rsqrtf(n2);
+  float gv[3] = {g[8], g[9], g[10]};
+  float k = dot3(gv, dv) * inv / n2;
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+    g_o[i * 3 + j] += g[j];
+    g_d[i * 3 + j] += g[3 + j] + gv[j] * inv - k * dv[j];
+  }
+}
+
+}  // namespace pp
+}  // namespace scnerf

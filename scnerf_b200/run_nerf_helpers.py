@@ -127,22 +127,13 @@ class NeRF(nn.Module):
         return m
 
     def forward(self, x):
-        """Embedded features [P, input_ch(+input_ch_views)] -> raw (run_nerf_helpers.py:105-128).
-        API parity for external callers; the render path evaluates the field with the fused CUDA
-        kernels from (rays, z) directly and never calls this."""
-        import torch.nn.functional as F
-        input_pts, input_views = torch.split(x, [self.input_ch, self.input_ch_views], dim=-1)
-        h = input_pts
-        for i, layer in enumerate(self.pts_linears):
-            h = F.relu(layer(h))
-            if i in self.skips:
-                h = torch.cat([input_pts, h], -1)
-        if not self.use_viewdirs:
-            return self.output_linear(h)
-        alpha = self.alpha_linear(h)
-        h = torch.cat([self.feature_linear(h), input_views], -1)
-        h = F.relu(self.views_linears[0](h))
-        return torch.cat([self.rgb_linear(h), alpha], -1)
+        """The reference's ``NeRF.forward`` (run_nerf_helpers.py:105-128) consumes pre-embedded features and
+        is only ever reached through ``run_network`` (create_nerf.py:18-32).  Here the positional encoding
+        is fused into the CUDA field kernels, which start from points, so there is no embedded-feature
+        entry; evaluating this module with eager PyTorch ops would be a silent library fallback."""
+        raise NotImplementedError(
+            "scnerf_b200.NeRF is evaluated by the CUDA field kernels from points: call "
+            "scnerf_b200.create_nerf.run_network(pts, viewdirs, net, ...) / network_query_fn instead of net(x)")
 
 
 class SingleDeviceParallel(nn.Module):

@@ -23,7 +23,8 @@ def _ensure_built():
 def test_header_symbols_exported():
     _lib = _ensure_built()
     lib = _lib.load()
-    header = open(os.path.join(ROOT, "include", "scnerf_b200.h")).read()
+    header = "".join(open(os.path.join(ROOT, "include", h)).read()
+                     for h in ("scnerf_b200.h", "scnerf_b200_nerfpp.h"))
     declared = set(re.findall(r"\b(scnerf_[a-z0-9_]+)\s*\(", header))
     assert declared, "no declarations parsed"
     for name in sorted(declared):
@@ -38,7 +39,8 @@ def test_struct_sizes_match_header():
     import ctypes as C
     _lib = _ensure_built()
     assert C.sizeof(_lib.Camera) == 6 * 8 + 4 * 4 + 6 * 4
-    assert C.sizeof(_lib.Mlp) == 9 * 4 + 4 + (2 * 16 + 10) * 8          # 9 ints + pad + pointers
+    assert C.sizeof(_lib.Mlp) == 9 * 4 + 4 + (2 * 16 + 10) * 8 + 8      # 9 ints + pad + pointers + pts_dim + pad
+    assert C.sizeof(_lib.PPRaygenArgs) == 8 * 3 + 8 + 8 * 4
     assert C.sizeof(_lib.RenderCfg) == 48
     assert C.sizeof(_lib.RaygenArgs) == 8 + 4 * 3 + 4 + 8 * 4 + 8 + 8
 
