@@ -241,6 +241,21 @@ int scnerf_train_step(const scnerf_camera* cam, const scnerf_camera_grads* g_cam
                       const scnerf_step_io* io, int32_t inputs_on_host, int64_t N, void* workspace,
                       size_t workspace_bytes, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Optimiser step: the reference's CustomAdamOptimizer — NeRF/create_nerf.py:199-336,
+ * nerfplusplus/custom_optim.py:11-147 — as ONE multi-tensor launch per <= 40 tensors.  `tensors_host` is
+ * a HOST array; weight_decay applies only to tensors with decay != 0 (the reference decays by POSITION:
+ * the last ray_o / ray_d / distortion parameters, create_nerf.py:222-230; the host mirror computes that).
+ * step is the tensor's 1-based update count (bias correction).  vmax != NULL selects amsgrad.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct scnerf_adam_tensor {
+  float* param; const float* grad; float* exp_avg; float* exp_avg_sq; float* max_exp_avg_sq;
+  int64_t numel;
+  int32_t step, decay;
+} scnerf_adam_tensor;
+int scnerf_adam_step(const scnerf_adam_tensor* tensors_host, int32_t n_tensors, float lr, float beta1,
+                     float beta2, float eps, float weight_decay, void* stream);
+
 /* Hardware self-test of the tcgen05 building blocks (descriptor encodings, TMEM, bulk copy):
  * D[128,N] = bf16(A[128,K]) * bf16(B[N,K])^T with fp32 accumulation, one CTA.
  * variant bit0 swaps the LBO/SBO descriptor fields (diagnostic), bit1 stages through cp.async.bulk. */

@@ -445,3 +445,33 @@ def searchsorted_rows(a, v, right):
         out[r] = np.searchsorted(a[r if a.shape[0] > 1 else 0], v[r if v.shape[0] > 1 else 0],
                                  side="right" if right else "left")
     return out
+
+
+# --------------------------------------------------------------------------------------
+# optimiser step: NeRF/create_nerf.py:199-258, nerfplusplus/custom_optim.py:11-70
+# --------------------------------------------------------------------------------------
+
+
+def custom_adam_step(params, grads, exp_avgs, exp_avg_sqs, max_exp_avg_sqs, steps, camera_model_name, *,
+                     amsgrad, beta1, beta2, lr, weight_decay, eps):
+    """`f_custom_adam` restated: Adam where only the LAST parameters (ray_o / ray_d / distortion, chosen by
+    substring of the camera-model name, :222-230) receive weight decay.  Updates the lists in place."""
+    decay_from = len(params)
+    if camera_model_name != "none":
+        decay_from -= "rayo" in camera_model_name
+        decay_from -= "rayd" in camera_model_name
+        decay_from -= "dist" in camera_model_name
+    for i, p in enumerate(params):
+        g = grads[i]
+        bc1, bc2 = 1 - beta1 ** steps[i], 1 - beta2 ** steps[i]
+        if weight_decay != 0 and i >= decay_from:
+            g = g + weight_decay * p
+        exp_avgs[i] = exp_avgs[i] * beta1 + (1 - beta1) * g
+        exp_avg_sqs[i] = exp_avg_sqs[i] * beta2 + (1 - beta2) * g * g
+        if amsgrad:
+            max_exp_avg_sqs[i] = torch.maximum(max_exp_avg_sqs[i], exp_avg_sqs[i])
+            denom = max_exp_avg_sqs[i].sqrt() / math.sqrt(bc2) + eps
+        else:
+            denom = exp_avg_sqs[i].sqrt() / math.sqrt(bc2) + eps
+        params[i] = p - (lr / bc1) * exp_avgs[i] / denom
+    return params

@@ -61,6 +61,11 @@ class PPRaygenArgs(C.Structure):          # include/scnerf_b200_nerfpp.h
                 ("extrinsic", vp), ("N", C.c_int64)]
 
 
+class AdamTensor(C.Structure):
+    _fields_ = [("param", vp), ("grad", vp), ("exp_avg", vp), ("exp_avg_sq", vp), ("max_exp_avg_sq", vp),
+                ("numel", C.c_int64), ("step", C.c_int32), ("decay", C.c_int32)]
+
+
 class RenderCfg(C.Structure):
     _fields_ = [("N_samples", C.c_int32), ("N_importance", C.c_int32), ("ray_cols", C.c_int32),
                 ("lindisp", C.c_int32), ("white_bkgd", C.c_int32), ("perturb", C.c_int32),
@@ -121,6 +126,7 @@ SIGNATURES = {
     "scnerf_train_step": (_I, [_P(Camera), _P(CameraGrads), _P(RenderCfg), C.c_int32, C.c_float,
                                C.c_float, _P(Mlp), _P(Mlp), _P(Mlp), _P(Mlp), _P(StepIO), C.c_int32,
                                _I64, vp, _SZ, vp]),
+    "scnerf_adam_step": (_I, [_P(AdamTensor), C.c_int32, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, vp]),
     # ---- include/scnerf_b200_nerfpp.h ----
     "scnerf_pp_raygen_fwd": (_I, [_P(PPRaygenArgs), vp, vp, vp, vp]),
     "scnerf_pp_raygen_bwd": (_I, [_P(PPRaygenArgs), vp, vp, _P(CameraGrads), vp, vp]),

@@ -102,10 +102,12 @@ def create_nerf(args, noisy_focal, noisy_poses, H, W, mode="train", device="cuda
                 intrinsics=intrinsic_init, extrinsics=noisy_poses, args=args, H=H, W=W).to(device)
         grad_vars += list(camera_model.parameters())
 
-    if getattr(args, "use_custom_optim", False):
-        raise NotImplementedError("use_custom_optim: the positional-weight-decay Adam of "
-                                  "NeRF/create_nerf.py:199-336 is a later row of the scope table")
-    optimizer = torch.optim.Adam(params=grad_vars, lr=args.lrate, betas=(0.9, 0.999))
+    if getattr(args, "use_custom_optim", False):        # create_nerf.py:126-130
+        from .custom_optim import CustomAdamOptimizer
+        optimizer = CustomAdamOptimizer(params=grad_vars, lr=args.lrate, betas=(0.9, 0.999),
+                                        weight_decay=args.non_linear_weight_decay, H=H, W=W, args=args)
+    else:
+        optimizer = torch.optim.Adam(params=grad_vars, lr=args.lrate, betas=(0.9, 0.999))
 
     start = 0
     ckpts = []

@@ -3,6 +3,7 @@
 // stream; it never allocates or synchronises.
 #include <algorithm>
 #include <cstring>
+#include <cmath>
 
 #include "common.cuh"
 #include "raygen.cuh"
@@ -12,6 +13,7 @@
 #include "field_simt.cuh"
 #include "field_tc.cuh"
 #include "nerfpp.cuh"
+#include "adam.cuh"
 #include "../../include/scnerf_b200_nerfpp.h"
 
 using namespace scnerf;
@@ -547,5 +549,34 @@ int scnerf_train_step(const scnerf_camera* cam, const scnerf_camera_grads* g_cam
 }
 
 }  // extern "C"
+
+extern "C" int scnerf_adam_step(const scnerf_adam_tensor* tensors_host, int32_t n_tensors, float lr, float beta1,
+                                float beta2, float eps, float weight_decay, void* stream) {
+  SCNERF_CHECK_ARG(tensors_host || n_tensors == 0, "adam_step: null tensor table");
+  SCNERF_CHECK_ARG(beta1 >= 0.f && beta1 < 1.f && beta2 >= 0.f && beta2 < 1.f && eps >= 0.f && lr >= 0.f,
+                   "adam_step: bad hyper-parameters");
+  int i = 0;
+  while (i < n_tensors) {
+    AdamTable tab{};
+    tab.beta1 = beta1; tab.beta2 = beta2; tab.eps = eps;
+    int64_t blocks = 0;
+    for (; i < n_tensors && tab.n < ADAM_MAX_TENSORS; ++i) {
+      const scnerf_adam_tensor& s = tensors_host[i];
+      if (s.numel == 0) continue;
+      SCNERF_CHECK_ARG(s.param && s.grad && s.exp_avg && s.exp_avg_sq && s.step >= 1, "adam_step: tensor %d incomplete", i);
+      AdamTensor& t = tab.t[tab.n++];
+      t.p = s.param; t.g = s.grad; t.m = s.exp_avg; t.v = s.exp_avg_sq; t.vmax = s.max_exp_avg_sq; t.n = s.numel;
+      t.first_block = (int32_t)blocks;
+      const double bc1 = 1.0 - std::pow((double)beta1, (double)s.step), bc2 = 1.0 - std::pow((double)beta2, (double)s.step);
+      t.step_size = (float)((double)lr / bc1);
+      t.inv_sqrt_bc2 = (float)(1.0 / std::sqrt(bc2));
+      t.weight_decay = s.decay ? weight_decay : 0.f;
+      blocks += cdiv(s.numel, ADAM_BLOCK * ADAM_ILP);
+    }
+    if (tab.n == 0) break;
+    SCNERF_LAUNCH(adam_multi_kernel, (unsigned)blocks, ADAM_BLOCK, 0, stream, tab);
+  }
+  return 0;
+}
 
 #include "api_pp.inc"

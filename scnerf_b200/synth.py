@@ -175,3 +175,14 @@ def pp_pixel_batch(seed, N, H=PP_H, W=PP_W, n_cams=PP_NCAM):
     cam_idx = int(rng.integers(0, n_cams))
     target = rng.uniform(0, 1, (N, 3)).astype(np.float32)
     return sel, cam_idx, target
+
+
+def adam_case(seed, n_steps=3):
+    """Parameter shapes (a slice of the real grad_vars order: MLP tensors then the camera's noise tensors) and
+    per-step gradients for the optimiser tests."""
+    rng = np.random.default_rng(seed + 7000)
+    shapes = [(32, 63), (32,), (32, 32), (1, 32), (3, 16), (4,), (17, 9), (7, 10, 3), (7, 10, 3), (2,)]
+    params = [rng.standard_normal(s).astype(np.float32) * 0.1 for s in shapes]
+    grads = [[(rng.standard_normal(s) * 10.0 ** rng.uniform(-4, 0)).astype(np.float32) for s in shapes]
+             for _ in range(n_steps)]
+    return params, grads

@@ -302,3 +302,24 @@ def test_pp_train_step(golden):
             st = nets[m][0] if name.startswith("fg_net.") else nets[m][1]
             ref = g[k]
             close(st[name[7:]].grad[:8], ref, 1e-2, 1e-4 * np.abs(ref).max())
+
+
+ADAM_CASES = (("dist", "pinhole_rot_noise_10k_rayo_rayd_dist", False, 0.1),
+              ("od", "pinhole_rot_noise_10k_rayo_rayd", True, 0.05), ("none", "none", False, 0.1))
+
+
+def test_custom_adam(golden):
+    """oracle restatement of f_custom_adam vs the reference's CustomAdamOptimizer."""
+    g = golden("adam")
+    for tag, cam_name, amsgrad, wd in ADAM_CASES:
+        p0, grads = synth.adam_case(1)
+        params = [T(p.copy()) for p in p0]
+        m = [torch.zeros_like(p) for p in params]
+        v = [torch.zeros_like(p) for p in params]
+        vmax = [torch.zeros_like(p) for p in params]
+        for step, gs in enumerate(grads):
+            lr = 5e-4 * (0.1 ** (step / 250000))
+            params = O.custom_adam_step(params, [T(x) for x in gs], m, v, vmax, [step + 1] * len(params), cam_name,
+                                        amsgrad=amsgrad, beta1=0.9, beta2=0.999, lr=lr, weight_decay=wd, eps=1e-8)
+            for i, p in enumerate(params):
+                close(p, g[f"{tag}_s{step}_p{i}"], 2e-6, 1e-7)
