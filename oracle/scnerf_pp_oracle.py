@@ -242,10 +242,15 @@ def nerfnet_forward(st_fg, st_bg, ray_o, ray_d, fg_z_max, fg_z_vals, bg_z_vals, 
                         ("bg_rgb", bg_rgb_map), ("bg_depth", bg_depth_map), ("bg_lambda", bg_lambda)])
 
 
-def train_step(cam, camera_idx, select_inds, target, nets, cascade_samples, rand, min_depth=1e-4):
+def train_step(cam, camera_idx, select_inds, target, nets, cascade_samples, rand, min_depth=1e-4,
+               level1_override=None):
     """One optimisation step's forward of ddp_train_nerf.py:421-488 (no auto-exposure):
     loss = sum over cascade levels of img2mse(rgb, target).  ``nets`` = [(st_fg, st_bg), ...];
-    ``rand`` = dict(t_fg, t_bg, u_fg, u_bg) of injected draws (None = deterministic)."""
+    ``rand`` = dict(t_fg, t_bg, u_fg, u_bg) of injected draws (None = deterministic).
+    ``level1_override`` = (fg_depth, d(fg_depth)/d(far), bg_depth): evaluate level 1 AT these sample positions
+    (still differentiable w.r.t. the sphere depth through the coefficient).  The parity tests use it to compare
+    gradients at the CUDA path's own samples: inverse-CDF sampling is discontinuous in the weights, so two fp32
+    implementations occasionally put a sample in neighbouring bins."""
     ray_o, ray_d, _ = rays_from_camera(cam, camera_idx, select_inds)
     loss = 0.0
     rets = []
@@ -255,6 +260,10 @@ def train_step(cam, camera_idx, select_inds, target, nets, cascade_samples, rand
         Ns = cascade_samples[m]
         if m == 0:
             fg_depth, bg_depth = level0_depths(fg_near, fg_far, Ns, rand.get("t_fg"), rand.get("t_bg"))
+        elif level1_override is not None:
+            fg1, coef1, bg1 = level1_override
+            fg_depth = fg1 + coef1 * (fg_far - fg_far.detach()).unsqueeze(-1)
+            bg_depth = bg1
         else:
             fg_depth = level1_depths(fg_depth, ret["fg_weights"], Ns, u=rand.get("u_fg"), det=rand.get("u_fg") is None)
             bg_depth = level1_depths(bg_depth, ret["bg_weights"], Ns, u=rand.get("u_bg"), det=rand.get("u_bg") is None)

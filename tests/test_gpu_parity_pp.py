@@ -41,7 +41,7 @@ def oracle64_field(g):
     return grads
 
 
-def oracle64_train_step(g):
+def oracle64_train_step(g, level1_override=None):
     from oracle import scnerf_pp_oracle as OP
     dt = torch.float64
     cam = OP.CameraPP(synth.intrinsic_init(PH, PW, PF), synth.pp_camera_poses(35), synth.pp_camera_args(), PH, PW,
@@ -50,7 +50,8 @@ def oracle64_train_step(g):
     cv = lambda st: {k: T(v).to(dt).requires_grad_(True) for k, v in st.items()}
     nets = [(cv(synth.pp_mlp_state(s, 63)), cv(synth.pp_mlp_state(s + 1, 84))) for s in (50, 52)]
     rand = {k: T(g[k]).to(dt) for k in ("t_fg", "t_bg", "u_fg", "u_bg")}
-    loss, _, _ = OP.train_step(cam, int(g["cam_idx"]), T(g["sel"]), T(g["target"]).to(dt), nets, [24, 48], rand)
+    loss, _, _ = OP.train_step(cam, int(g["cam_idx"]), T(g["sel"]), T(g["target"]).to(dt), nets, [24, 48], rand,
+                               level1_override=level1_override)
     loss.backward()
     grads = {"cam_" + k: getattr(cam, k).grad.numpy() for k in OP.CameraPP.LEARNABLE}
     for m, (fgst, bgst) in enumerate(nets):
@@ -266,14 +267,24 @@ def test_pp_train_step(golden):
     assert (d_rgb > 1e-4).sum() <= 2 and d_rgb.max() <= 5e-3
     assert abs(float(loss) - float(g["loss"])) <= 2e-4 * float(g["loss"]), (float(loss), float(g["loss"]))
     loss.backward()
-    # the cascade resamples: ~1.5 % of the level-1 depths land in a neighbouring pdf bin (cdf round-off, see
-    # test_pp_sampling), which perturbs the gradients by a few 1e-3 of their maximum on top of the fp32 floor
-    g64 = oracle64_train_step(g)
+    # Inverse-CDF sampling is discontinuous in the weights: two fp32 implementations put the odd sample in a
+    # neighbouring bin (rows counted above), which changes that ray's gradient.  So gradients are compared with
+    # the fp64 oracle evaluated AT the CUDA path's own level-1 samples (differentiable through coef); the
+    # reference's fp32-vs-fp64 gap (golden vs the unconstrained fp64 oracle) calibrates the tolerance.
+    g64_free = oracle64_train_step(g)
+    ov = tuple(x.detach().cpu().double() for x in (fg, coef, bg))
+    g64 = oracle64_train_step(g, level1_override=ov)
+
+    def check(what, cuda, golden, free, at_samples):
+        e_cuda, e_ref = relmax(cuda, at_samples), relmax(golden, free)
+        print(f"{what}: err vs fp64-at-own-samples {e_cuda:.2e} (reference fp32 vs fp64 {e_ref:.2e})")
+        assert e_cuda <= max(3.0 * e_ref, 2e-4), (what, e_cuda, e_ref)
+
     for name in CAM_NAMES:
-        floor_check(f"pp_train_step d/d(camera.{name})", getattr(cam, name).grad, g["g_cam_" + name], g64["cam_" + name],
-                    slack=6.0, floor=1e-3)
+        check(f"pp_train_step d/d(camera.{name})", getattr(cam, name).grad, g["g_cam_" + name], g64_free["cam_" + name],
+              g64["cam_" + name])
     for k in list(g):
         if k.startswith("g_net"):
             m, name = int(k[5]), k[7:]
-            floor_check(f"pp_train_step d/d(net{m}.{name})", dict(nets[m].named_parameters())[name].grad[:8], g[k],
-                        g64[f"net{m}_{name}"][:8], slack=6.0, floor=1e-3)
+            check(f"pp_train_step d/d(net{m}.{name})", dict(nets[m].named_parameters())[name].grad[:8], g[k],
+                  g64_free[f"net{m}_{name}"][:8], g64[f"net{m}_{name}"][:8])
