@@ -252,7 +252,7 @@ inline fused::PackSrc make_pack_src(const scnerf_mlp& m) {
 
 // bf16 tile images kept by the tensor-core training path (one set of forward images per pass;
 // the dgrad images and per-sample geometry gradients are shared between passes)
-struct TcFwdImages { eng::ImgDump x, v, h[8], feat, hv; };
+struct TcFwdImages { eng::ImgDump x, v, h[8], feat, hv; uint4* relu_bits = nullptr; };
 struct TcBwdBufs {
   eng::ImgDump dz[8], dfeat, dzv;
   float *g_pts = nullptr, *g_vd = nullptr;
@@ -270,6 +270,7 @@ inline void tc_fwd_images_alloc(Arena& ar, int64_t P, int nsplit, TcFwdImages& I
   I.x = img_alloc(ar, T, 64, nh); I.v = img_alloc(ar, T, 32, nh);
   for (int i = 0; i < 8; ++i) I.h[i] = img_alloc(ar, T, 256, nh);
   I.feat = img_alloc(ar, T, 256, nh); I.hv = img_alloc(ar, T, 128, nh);
+  I.relu_bits = ar.get<uint4>((size_t)T * 9 * 2 * 128);
 }
 inline void tc_bwd_bufs_alloc(Arena& ar, int64_t P, int nsplit, TcBwdBufs& G) {
   const int64_t T = cdiv(P, 128);
@@ -300,6 +301,7 @@ inline int field_tc_fwd_impl(const scnerf_mlp& m, const float* rays, int ray_col
     a.img_x = imgs->x; a.img_v = imgs->v;
     for (int s = 0; s < 8; ++s) a.img_out[s] = imgs->h[s];
     a.img_out[8] = imgs->feat; a.img_out[9] = imgs->hv;
+    a.relu_bits = imgs->relu_bits;
   }
   if (B.keep_all && B.X5) {   // training with the fp32 CUDA-core backward: fp32 row-major layer inputs
     for (int s = 0; s < 8; ++s) {
@@ -379,8 +381,8 @@ inline int field_tc_bwd_impl(const scnerf_mlp& m, const scnerf_mlp& g, const flo
   dgrad::Args a{};
   a.rays = rays; a.ray_cols = ray_cols; a.z = z; a.P = P; a.S = S; a.num_tiles = T;
   a.g_raw = g_raw; a.wimg = G.wimg; a.cbuf = B.tc_cbuf;
-  for (int i = 0; i < 8; ++i) { a.img_h[i] = I.h[i]; a.out_dz[i] = G.dz[i]; }
-  a.img_hv = I.hv; a.out_dfeat = G.dfeat; a.out_dzv = G.dzv; a.g_pts = G.g_pts; a.g_vd = G.g_vd;
+  for (int i = 0; i < 8; ++i) a.out_dz[i] = G.dz[i];
+  a.relu_bits = I.relu_bits; a.out_dfeat = G.dfeat; a.out_dzv = G.dzv; a.g_pts = G.g_pts; a.g_vd = G.g_vd;
   SCNERF_LAUNCH((dgrad::field_fused_dgrad_kernel<NSPLIT>), std::min(device_sm_count(), T), 320,
                 dgrad::Cfg<NSPLIT>::SMEM_BYTES, stream, a);
   if (d_rays)

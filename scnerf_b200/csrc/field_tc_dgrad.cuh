@@ -3,7 +3,7 @@
 // For each 128-sample tile:  d(raw)[4] -> rgb/alpha heads (fp32 in registers) -> views layer ->
 // feature layer -> trunk 7..0, every  g_in = dZ * W  GEMM on the tensor cores with the SAME slab
 // engine as the forward (A = dZ in TMEM, B = transposed bf16 weight slabs streamed by bulk TMA),
-// ReLU masks taken from the forward's bf16 tile images, and every dZ written back as a bf16 (hi[,lo])
+// ReLU masks taken from the forward's 1-bit-per-activation mask buffer, and every dZ written back as a bf16 (hi[,lo])
 // TILE IMAGE that the wgrad kernel consumes directly.  Also produces d(pts) and d(viewdirs) per
 // sample (PE backward in registers), reduced per ray by reduce_pts_grad_kernel.
 //
@@ -105,44 +105,11 @@ struct Args {
   const float* rays; int ray_cols; const float* z; int64_t P; int S; int num_tiles;
   const float* g_raw;                  // [P,4]
   const uint8_t* wimg; const float* cbuf;
-  eng::ImgDump img_h[8], img_hv;       // forward images (masks)          (read, hi half only)
+  const uint4* relu_bits;              // forward ReLU masks, 1 bit per activation (fused::Args::relu_bits)
   eng::ImgDump out_dz[8], out_dfeat, out_dzv;   // produced for the wgrad kernel
   float* g_pts;                        // [P,3] d(loss)/d(point)
   float* g_vd;                         // [P,3] d(loss)/d(viewdir)
 };
-
-// mask 32 values with (h > 0) read from the forward image (hi half), features [c0, c0+32) of sample k
-__device__ __forceinline__ void relu_mask32(const eng::ImgDump& img, int tile, uint32_t k, uint32_t c0,
-                                            float (&f)[32]) {
-#pragma unroll
-  for (int g = 0; g < 4; ++g) {
-    const uint4 h = *reinterpret_cast<const uint4*>(img.chunk(tile, k, c0 + 8 * g, 0));
-    const uint32_t w[4] = {h.x, h.y, h.z, h.w};
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      if ((w[e] & 0x0000ffffu) == 0u) f[8 * g + 2 * e] = 0.f;
-      if ((w[e] & 0xffff0000u) == 0u) f[8 * g + 2 * e + 1] = 0.f;
-    }
-  }
-}
-
-// bit j of the result = (h[c0 + j] > 0): 4 x 16-byte loads from the forward image (hi half) of sample k
-__device__ __forceinline__ uint32_t relu_bits32(const eng::ImgDump& img, int tile, uint32_t k, uint32_t c0,
-                                                uint64_t pol) {
-  const uint8_t* p = img.chunk(tile, k, c0, 0);
-  uint32_t bits = 0;
-#pragma unroll
-  for (int g = 0; g < 4; ++g) {
-    const uint4 h = tc::ld_v4_hint(p + g * 256, pol);
-    const uint32_t w[4] = {h.x, h.y, h.z, h.w};
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      bits |= ((w[e] & 0x0000ffffu) != 0u ? 1u : 0u) << (8 * g + 2 * e);
-      bits |= ((w[e] & 0xffff0000u) != 0u ? 1u : 0u) << (8 * g + 2 * e + 1);
-    }
-  }
-  return bits;
-}
 
 template <int NSPLIT>
 __global__ void __launch_bounds__(320, 1) field_fused_dgrad_kernel(const __grid_constant__ Args a) {
@@ -198,6 +165,8 @@ __global__ void __launch_bounds__(320, 1) field_fused_dgrad_kernel(const __grid_
       // ---- E0: rgb head dgrad (fp32), ReLU mask of the view layer -> dZ_v (this warp's 64 columns)
       {
         if (half == 0) *reinterpret_cast<float4*>(out_s + row * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+        const uint4 mv = tc::ld_v4_hint(a.relu_bits + ((size_t)(tile * 9 + 8) * 2 + half) * 128 + row, ctx.pol_stream);
+        const uint32_t mvw[2] = {mv.x, mv.y};
 #pragma unroll
         for (int cc = 0; cc < 2; ++cc) {
           const int c0 = half * 64 + cc * 32;
@@ -206,7 +175,8 @@ __global__ void __launch_bounds__(320, 1) field_fused_dgrad_kernel(const __grid_
           for (int j = 0; j < 32; ++j)
             f[j] = gr.x * cst[fused::C_WRGB + c0 + j] + gr.y * cst[fused::C_WRGB + 128 + c0 + j] +
                    gr.z * cst[fused::C_WRGB + 256 + c0 + j];
-          relu_mask32(a.img_hv, tile, row, c0, f);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = ((mvw[cc] >> j) & 1u) ? f[j] : 0.f;
           uint32_t hi[16], lo[16];
           eng::split32<SPLIT, false>(f, hi, lo);
           tc::tmem_st16(T_AHI + lane_base + (uint32_t)(c0 >> 1), hi);
@@ -220,19 +190,8 @@ __global__ void __launch_bounds__(320, 1) field_fused_dgrad_kernel(const __grid_
       for (int s = 0; s < NSTAGE; ++s, ++m) {
         // stage -> (mask image, output image); by value: taking the address of a kernel parameter would
         // spill the whole struct to local memory
-        eng::ImgDump mask{}, outd{};
-        switch (s) {
-          case 0: outd = a.out_dfeat; break;                        // g_feat: feature_linear has no ReLU
-          case 1: mask = a.img_h[7]; outd = a.out_dz[7]; break;
-          case 2: mask = a.img_h[6]; outd = a.out_dz[6]; break;
-          case 3: mask = a.img_h[5]; outd = a.out_dz[5]; break;
-          case 5: mask = a.img_h[4]; outd = a.out_dz[4]; break;
-          case 6: mask = a.img_h[3]; outd = a.out_dz[3]; break;
-          case 7: mask = a.img_h[2]; outd = a.out_dz[2]; break;
-          case 8: mask = a.img_h[1]; outd = a.out_dz[1]; break;
-          case 9: mask = a.img_h[0]; outd = a.out_dz[0]; break;
-          default: break;                                            // 4, 10: d(PE) stages
-        }
+        // stage -> trunk layer whose ReLU is differentiated here (-1: none: feature_linear / d(PE) stages)
+        const int mlayer = (s >= 1 && s <= 3) ? 8 - s : ((s >= 5 && s <= 9) ? 9 - s : -1);
         // this stage's A operand (TMEM) is a dZ the wgrad kernel needs: write its tile image now, under
         // the MMA phase (off the critical path)
         switch (s) {
@@ -251,9 +210,9 @@ __global__ void __launch_bounds__(320, 1) field_fused_dgrad_kernel(const __grid_
         // ReLU masks of this warp's 128 columns are fetched BEFORE waiting for the accumulator, i.e.
         // under the MMA phase of this stage
         uint32_t mk[4] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};
-        if (mask.base) {
-#pragma unroll
-          for (int cc = 0; cc < 4; ++cc) mk[cc] = relu_bits32(mask, tile, row, half * 128 + cc * 32, ctx.pol_stream);
+        if (mlayer >= 0) {
+          const uint4 mb = tc::ld_v4_hint(a.relu_bits + ((size_t)(tile * 9 + mlayer) * 2 + half) * 128 + row, ctx.pol_stream);
+          mk[0] = mb.x; mk[1] = mb.y; mk[2] = mb.z; mk[3] = mb.w;
         }
         tc::mbar_wait(acc_full, m & 1);
         tc::tc_fence_after();

@@ -207,6 +207,9 @@ struct Args {
   int num_tiles;
   // training (tensor-core backward): bf16 tile images of every layer input
   eng::ImgDump img_x, img_v, img_out[NSTAGE];
+  // ReLU masks for the tensor-core dgrad: 1 bit per activation, [tile][9 layers][2 halves][128 rows] x 16 B
+  // (layers 0..7 = trunk, 8 = view layer; a warp's 32 rows store 512 contiguous bytes)
+  uint4* relu_bits;
   // training (fp32 CUDA-core backward): fp32 row-major copies
   float* dump[NSTAGE]; int dump_ld[NSTAGE];
   float* dump_pe; int dump_pe_ld;
@@ -353,6 +356,21 @@ __device__ __forceinline__ void epi_stage(const Args& a, const float* cst, uint3
     tc::tmem_st_wait();
     tc::tc_fence_before();
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(a_ready_addr) : "memory");
+  }
+  if constexpr (d.relu != 0) {
+    if (a.relu_bits != nullptr) {      // after the hand-off: off the MMA's critical path
+      constexpr int L = S == 9 ? 8 : S;
+      uint4 mb = make_uint4(0u, 0u, 0u, 0u);
+      uint32_t* mw = reinterpret_cast<uint32_t*>(&mb);
+#pragma unroll
+      for (int cc = 0; cc < nchunk; ++cc) {
+        uint32_t bits = 0;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) bits |= (__uint_as_float(v[cc][j]) > 0.f ? 1u : 0u) << j;
+        mw[cc] = bits;
+      }
+      tc::st_v4_hint(a.relu_bits + ((size_t)(tile * 9 + L) * 2 + half) * 128 + row, mb, ctx.pol_stream);
+    }
   }
   if (threadIdx.x == 64) eng::dbg_stamp(ctx, tile_iter, S, NSTAGE, 3);
 }
