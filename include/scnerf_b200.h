@@ -98,6 +98,14 @@ int scnerf_raygen_fwd(const scnerf_raygen_args* a, float* rays_o, float* rays_d,
 int scnerf_raygen_bwd(const scnerf_raygen_args* a, const float* d_rays_o, const float* d_rays_d,
                       const scnerf_camera_grads* g, void* stream);
 
+/* Per-step ray batch — NeRF/run_nerf.py:368-398 (batching mode with a camera model):
+ * shuffled_ray_idx[N] are global ray ids in [0, n_train*H*W); outputs kps[N,2] = (x, y), image_idx[N] =
+ * id / (H*W) (index into the train cameras) and target[N,3] = images[i_train[image_idx], y, x].
+ * images: [n_images, H, W, 3] fp32 on the device. */
+int scnerf_ray_batch(const int64_t* shuffled_ray_idx, int64_t N, const float* images, const int64_t* i_train,
+                     int64_t n_train, int32_t H, int32_t W, int64_t* kps, int64_t* image_idx, float* target,
+                     void* stream);
+
 /* render()'s ray packing — NeRF/render.py:105-130 (+ ndc_rays :357-374 / ndc_rays_camera :376-396):
  * viewdirs = d/|d|, optional NDC (near plane 1), rays[N, 8|11] = [o, d, near, far, viewdirs].
  * fx,fy come from `cam` (learnable, differentiable) when cam != NULL, else from `focal`. */

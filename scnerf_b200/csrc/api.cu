@@ -118,6 +118,17 @@ int scnerf_raygen_bwd(const scnerf_raygen_args* a, const float* d_rays_o, const 
   return 0;
 }
 
+int scnerf_ray_batch(const int64_t* shuffled_ray_idx, int64_t N, const float* images, const int64_t* i_train,
+                     int64_t n_train, int32_t H, int32_t W, int64_t* kps, int64_t* image_idx, float* target,
+                     void* stream) {
+  SCNERF_CHECK_ARG(shuffled_ray_idx && images && i_train && kps && image_idx && target, "ray_batch: null pointer");
+  SCNERF_CHECK_ARG(H > 0 && W > 0 && n_train > 0, "ray_batch: bad sizes");
+  if (N == 0) return 0;
+  SCNERF_LAUNCH(ray_batch_kernel, (unsigned)cdiv(N, 256), 256, 0, stream, shuffled_ray_idx, N, images, i_train, H, W,
+                kps, image_idx, target);
+  return 0;
+}
+
 static int make_rayprep_dev(const scnerf_rayprep_args* a, RayprepDev& d) {
   SCNERF_CHECK_ARG(a, "rayprep: null args");
   std::memset(&d, 0, sizeof(d));

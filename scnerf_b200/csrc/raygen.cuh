@@ -307,6 +307,24 @@ __global__ void camera_matrices_kernel(scnerf_camera c, float* K_out, float* E_o
   }
 }
 
+// ---- per-step ray batch: NeRF/run_nerf.py:368-398 — from a slice of the shuffled global
+// ray indices to pixel coordinates (x, y), per-ray train-image index and target colours, in one pass.
+// The reference does this with numpy on the host and three H2D copies every step.
+__global__ void __launch_bounds__(256) ray_batch_kernel(const int64_t* __restrict__ shuffled, int64_t N,
+                                                        const float* __restrict__ images,
+                                                        const int64_t* __restrict__ i_train, int H, int W,
+                                                        int64_t* __restrict__ kps, int64_t* __restrict__ img_idx,
+                                                        float* __restrict__ target) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  const int64_t hw = (int64_t)H * W, g = shuffled[i];
+  const int64_t t = g / hw, rem = g % hw, y = rem / W, x = rem % W;      // :372-374
+  kps[2 * i] = x; kps[2 * i + 1] = y;
+  img_idx[i] = t;                                                        // index into the TRAIN cameras
+  const float* px = images + ((i_train[t] * H + y) * W + x) * 3;         // images[i_train[t], y, x]  (:392-395)
+  target[3 * i] = px[0]; target[3 * i + 1] = px[1]; target[3 * i + 2] = px[2];
+}
+
 // ---- render()'s ray packing: viewdirs + NDC + [o d near far viewdirs] (render.py:105-130) -------
 struct RayprepDev {
   scnerf_camera cam;

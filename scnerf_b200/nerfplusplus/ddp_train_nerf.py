@@ -164,3 +164,60 @@ def level1_depths(depth, weights, N_samples, fg_far_depth=None, coef=None, u=Non
     if coef is None:
         return merged, None
     return _DepthsOfFar.apply(fg_far_depth, merged, mcoef), mcoef
+
+
+# ---- full-image inference: ddp_train_nerf.py:135-256 ---------------------------------
+def render_single_image(rank, world_size, models, ray_sampler, chunk_size, camera_model, camera_idx=None,
+                        min_depth=1e-4):
+    """Render every pixel of one image through the cascade (deterministic sampling), each rank taking a
+    contiguous slice of the pixels.  ``models`` = {'cascade_level', 'cascade_samples', 'net_0', ...} as in the
+    reference; ``ray_sampler`` only needs ``.H``, ``.W`` and, when ``camera_idx`` is None, ``.c2w_mat``.
+
+    Returns (rank 0 only, like the reference) a list over cascade levels of OrderedDicts of [H, W(, 3)] tensors.
+    Deviation: results stay on the device and ranks are merged with one NCCL all_gather per
+    key instead of per-chunk ``.cpu()`` copies and a Gloo gather."""
+    from collections import OrderedDict
+    from .nerf_sample_ray_split import render_ray_from_camera
+    H, W = ray_sampler.H, ray_sampler.W
+    n_pix = H * W
+    if (n_pix // world_size) * world_size != n_pix:
+        raise Exception('Number of pixels in the image is not divisible by the number of GPUs!\n\t# pixels: {}\n\t# GPUs: {}'
+                        .format(n_pix, world_size))
+    per = n_pix // world_size
+    dev = camera_model.intrinsics_initial.device
+    all_idx = torch.arange(rank * per, (rank + 1) * per, device=dev, dtype=torch.int64)
+    levels = models['cascade_level']
+    merged = [OrderedDict() for _ in range(levels)]
+    with torch.no_grad():
+        for s0 in range(0, per, chunk_size):
+            sel = all_idx[s0:s0 + chunk_size]
+            if camera_idx is not None:
+                ray_o, ray_d, _ = render_ray_from_camera(camera_model, camera_idx, sel, rank)
+            else:
+                ray_o, ray_d, _ = render_ray_from_camera(camera_model, None, sel, rank, ray_sampler.c2w_mat)
+            for m in range(levels):
+                net = models['net_{}'.format(m)]
+                Ns = models['cascade_samples'][m]
+                if m == 0:
+                    fg_far_depth = intersect_sphere(ray_o, ray_d)
+                    fg_depth, _, bg_depth = level0_depths(fg_far_depth, Ns, min_depth, perturb=False)
+                else:
+                    fg_depth, _ = level1_depths(fg_depth, ret['fg_weights'], Ns, det=True)
+                    bg_depth, _ = level1_depths(bg_depth, ret['bg_weights'], Ns, det=True)
+                ret = net(ray_o, ray_d, fg_far_depth, fg_depth, bg_depth)
+                for key in ret:
+                    if key not in ('fg_weights', 'bg_weights') and torch.is_tensor(ret[key]):
+                        merged[m].setdefault(key, []).append(ret[key])
+    for m in range(levels):
+        for key in merged[m]:
+            merged[m][key] = torch.cat(merged[m][key], dim=0)
+    if world_size > 1:
+        import torch.distributed as dist
+        for m in range(levels):
+            for key in merged[m]:
+                parts = [torch.empty_like(merged[m][key]) for _ in range(world_size)]
+                dist.all_gather(parts, merged[m][key].contiguous())
+                merged[m][key] = torch.cat(parts, dim=0)
+    if rank != 0:
+        return None
+    return [OrderedDict((k, v.reshape(H, W, -1).squeeze()) for k, v in merged[m].items()) for m in range(levels)]

@@ -547,3 +547,23 @@ def test_custom_adam_fused(lib, golden):
             for i, p in enumerate(params):
                 np.testing.assert_allclose(p.detach().cpu().numpy(), g[f"{tag}_s{step}_p{i}"], rtol=2e-5, atol=2e-7)
         assert lib.scnerf_launch_count(0) == len(grads)          # one launch per step for all 10 tensors
+
+
+def test_ray_batch_sampler(lib):
+    """device-side per-step batch == the reference's numpy bookkeeping (run_nerf.py:368-398)."""
+    from scnerf_b200.ray_batch import RayBatchSampler
+    rng = np.random.default_rng(3)
+    n_img, Hh, Ww, N = 5, 12, 20, 64
+    images = rng.uniform(0, 1, (n_img, Hh, Ww, 3)).astype(np.float32)
+    i_train = np.array([0, 2, 3, 4])
+    perm = rng.permutation(len(i_train) * Hh * Ww)
+    sm = RayBatchSampler(T(images).cuda(), i_train, Hh, Ww, N)
+    sm.shuffle(T(perm).cuda())
+    for step in range(3):
+        kps, idx, target = sm.next()
+        sl = perm[step * N:(step + 1) * N]
+        img = sl // (Hh * Ww)
+        h, w = sl % (Hh * Ww) // Ww, sl % (Hh * Ww) % Ww
+        assert (kps.cpu().numpy() == np.stack([w, h], -1)).all()
+        assert (idx.cpu().numpy() == img).all()
+        assert (target.cpu().numpy() == images[i_train[img], h, w]).all()

@@ -323,3 +323,30 @@ def test_pp_train_step(golden):
             m, name = int(k[5]), k[7:]
             check(f"pp_train_step d/d(net{m}.{name})", dict(nets[m].named_parameters())[name].grad[:8], g[k],
                   g64_free[f"net{m}_{name}"][:8], g64[f"net{m}_{name}"][:8])
+
+
+def test_pp_render_single_image():
+    """full-image cascade inference (ddp_train_nerf.py:135-256) vs the oracle on a pixel subset."""
+    import types
+    from oracle import scnerf_pp_oracle as OP
+    from scnerf_b200.nerfplusplus.ddp_train_nerf import render_single_image
+    cam = make_cam(36, requires_grad=False)
+    nets = [make_net(60), make_net(62)]
+    models = {"cascade_level": 2, "cascade_samples": [16, 16], "net_0": nets[0], "net_1": nets[1]}
+    sampler = types.SimpleNamespace(H=PH, W=PW, c2w_mat=None)
+    out = render_single_image(0, 1, models, sampler, 8192, cam, camera_idx=3)
+    assert len(out) == 2 and out[1]["rgb"].shape == (PH, PW, 3) and out[1]["fg_depth"].shape == (PH, PW)
+    # oracle on 256 scattered pixels
+    sel = torch.arange(0, PH * PW, (PH * PW) // 256)[:256]
+    cam_o = OP.CameraPP(synth.intrinsic_init(PH, PW, PF), synth.pp_camera_poses(36), synth.pp_camera_args(), PH, PW,
+                        k=(-0.05, 0.01))
+    cam_o.load(synth.camera_noise_state(36, n_cams=PN, H=PH, W=PW, with_distortion=True))
+    cv = lambda st: {k: T(v) for k, v in st.items()}
+    nets_o = [(cv(synth.pp_mlp_state(s, 63)), cv(synth.pp_mlp_state(s + 1, 84))) for s in (60, 62)]
+    with torch.no_grad():
+        _, rets, _ = OP.train_step(cam_o, 3, sel, torch.zeros(256, 3), nets_o, [16, 16], {})
+    for m in range(2):
+        got = out[m]["rgb"].reshape(-1, 3)[sel.to(DEV)].cpu().numpy()
+        d = np.abs(got - rets[m]["rgb"].numpy()).max(1)
+        print(f"render_single_image level {m}: {(d > 1e-4).sum()} of 256 pixels off by > 1e-4 (max {d.max():.2e})")
+        assert (d > 1e-4).sum() <= 3 and d.max() <= 2e-2          # det sampling: the u = 1.0 knot (test_pp_sampling)

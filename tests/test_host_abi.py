@@ -135,3 +135,20 @@ def test_synth_is_deterministic():
     k2, i2, t2 = synth.pixel_batch(9, 64)
     assert np.array_equal(k1, k2) and np.array_equal(i1, i2) and np.array_equal(t1, t2)
     assert k1[:, 0].max() < synth.FERN_W and k1[:, 1].max() < synth.FERN_H
+
+
+def test_checkpoint_layout(tmp_path):
+    """checkpoints use the reference's dict keys and state-dict keys (run_nerf.py:626-641)."""
+    import types
+    from scnerf_b200.ray_batch import save_checkpoint
+    from scnerf_b200.run_nerf_helpers import NeRF, SingleDeviceParallel
+    mk = lambda: SingleDeviceParallel(NeRF(D=8, W=256, input_ch=63, output_ch=5, skips=[4], input_ch_views=27,
+                                           use_viewdirs=True))
+    kw = {"network_fn": mk(), "network_fine": mk()}
+    opt = torch.optim.Adam(list(kw["network_fn"].parameters()) + list(kw["network_fine"].parameters()), lr=5e-4)
+    path = save_checkpoint(str(tmp_path / "000100.tar"), 100, kw, opt)
+    ck = torch.load(path, weights_only=False)
+    assert set(ck) == {"global_step", "network_fn_state_dict", "network_fine_state_dict", "optimizer_state_dict"}
+    assert "module.pts_linears.0.weight" in ck["network_fn_state_dict"]          # nn.DataParallel prefix kept
+    fresh = mk()
+    fresh.load_state_dict(ck["network_fine_state_dict"])
