@@ -264,6 +264,24 @@ typedef struct scnerf_adam_tensor {
 int scnerf_adam_step(const scnerf_adam_tensor* tensors_host, int32_t n_tensors, float lr, float beta1,
                      float beta2, float eps, float weight_decay, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Projected ray distance loss — model/ray_dist_loss.py:22-246 `proj_ray_dist_loss_single`
+ * for N matched keypoint pairs: rays of image 0 / image 1 ([N,3] each, un-normalised directions), matched
+ * keypoints kps0 / kps1 ([N,2] float (x, y)), K4 = [fx, fy, cx, cy] (fx NEGATED by the caller for method
+ * "NeRF", :116-118), E2 = [2,3,4] camera-to-world of the two images.  acc5 is 5 floats of scratch that the
+ * backward re-reads; loss[1] and n_match[1] are device scalars.  train != 0: mean over errors that are finite
+ * and below `threshold`; train == 0: errors clamped to `threshold`, mean over the chirality-valid matches.
+ * Backward (train): ray gradients overwrite, d_K4[4] and d_E2[2,3,4] accumulate (either may be NULL).
+ * ---------------------------------------------------------------------------------------------- */
+int scnerf_prd_loss_fwd(const float* rays0_o, const float* rays0_d, const float* rays1_o, const float* rays1_d,
+                        const float* kps0, const float* kps1, const float* K4, const float* E2, float eps,
+                        float threshold, int32_t train, int64_t N, float* acc5, float* loss, float* n_match,
+                        void* stream);
+int scnerf_prd_loss_bwd(const float* rays0_o, const float* rays0_d, const float* rays1_o, const float* rays1_d,
+                        const float* kps0, const float* kps1, const float* K4, const float* E2, float eps,
+                        float threshold, int64_t N, const float* acc5, const float* d_loss, float* d_rays0_o,
+                        float* d_rays0_d, float* d_rays1_o, float* d_rays1_d, float* d_K4, float* d_E2, void* stream);
+
 /* Hardware self-test of the tcgen05 building blocks (descriptor encodings, TMEM, bulk copy):
  * D[128,N] = bf16(A[128,K]) * bf16(B[N,K])^T with fp32 accumulation, one CTA.
  * variant bit0 swaps the LBO/SBO descriptor fields (diagnostic), bit1 stages through cp.async.bulk. */

@@ -475,3 +475,46 @@ def custom_adam_step(params, grads, exp_avgs, exp_avg_sqs, max_exp_avg_sqs, step
             denom = exp_avg_sqs[i].sqrt() / math.sqrt(bc2) + eps
         params[i] = p - (lr / bc1) * exp_avgs[i] / denom
     return params
+
+
+# --------------------------------------------------------------------------------------
+# projected ray distance loss: model/ray_dist_loss.py:96-246
+# --------------------------------------------------------------------------------------
+
+
+def proj_ray_dist_loss(kps0, kps1, rays0, rays1, K4x4, E2, threshold, train=True, method="NeRF", eps=1e-10):
+    """Restatement of `proj_ray_dist_loss_single` after its mode/camera dispatch: K4x4 is the 4x4 intrinsic,
+    E2 = [2,4,4] camera-to-world of image 0 and image 1.  -> (loss, n_matches or None)."""
+    (o0, d0), (o1, d1) = rays0, rays1
+    K = K4x4.clone()
+    if method == "NeRF":
+        K = torch.cat([torch.cat([-K[0:1, 0:1], K[0:1, 1:]], 1), K[1:]], 0)     # :116-118
+    Rt = E2[:, :3, :3].transpose(1, 2)
+    tinv = -(Rt @ E2[:, :3, 3, None]).squeeze(-1)                                # :120-126
+    d0 = d0 / (d0.norm(p=2, dim=-1, keepdim=True) + eps)                        # :128-129
+    d1 = d1 / (d1.norm(p=2, dim=-1, keepdim=True) + eps)
+    c = (d0 * d1).sum(-1)
+    den = c ** 2 - 1 + eps
+    t0 = ((d0 * (o0 - o1)).sum(-1) - c * (d1 * (o0 - o1)).sum(-1)) / den        # :145-157
+    t1 = ((d1 * (o1 - o0)).sum(-1) - c * (d0 * (o1 - o0)).sum(-1)) / den        # :159-171
+    p0 = t0[:, None] * d0 + o0
+    p1 = t1[:, None] * d1 + o1
+
+    def project(p, cam):                                                         # :176-186
+        q = p @ Rt[cam].T + tinv[cam]
+        x = q @ K[:3, :3].T
+        return x[:, :2] / (x[:, 2:3] + eps)
+
+    uv0, uv1 = project(p0, 1), project(p1, 0)
+    valid = (t0 > 0) & (t1 > 0)                                                  # :188-190
+    loss0 = ((uv1[valid] - kps0[valid]) ** 2).sum(-1)                            # :207-212
+    loss1 = ((uv0[valid] - kps1[valid]) ** 2).sum(-1)
+    if train:
+        k0 = (loss0 < threshold) & torch.isfinite(loss0)
+        k1 = (loss1 < threshold) & torch.isfinite(loss1)
+        return 0.5 * (loss0[k0].mean() + loss1[k1].mean()), float((k0 & k1).sum())
+    bad0 = (loss0 > threshold) | ~torch.isfinite(loss0)
+    bad1 = (loss1 > threshold) | ~torch.isfinite(loss1)
+    loss0 = torch.where(bad0, torch.full_like(loss0, threshold), loss0)
+    loss1 = torch.where(bad1, torch.full_like(loss1, threshold), loss1)
+    return 0.5 * (loss0.mean() + loss1.mean()), None

@@ -126,6 +126,8 @@ SIGNATURES = {
     "scnerf_train_step": (_I, [_P(Camera), _P(CameraGrads), _P(RenderCfg), C.c_int32, C.c_float,
                                C.c_float, _P(Mlp), _P(Mlp), _P(Mlp), _P(Mlp), _P(StepIO), C.c_int32,
                                _I64, vp, _SZ, vp]),
+    "scnerf_prd_loss_fwd": (_I, [vp] * 8 + [C.c_float, C.c_float, C.c_int32, _I64, vp, vp, vp, vp]),
+    "scnerf_prd_loss_bwd": (_I, [vp] * 8 + [C.c_float, C.c_float, _I64, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
     "scnerf_ray_batch": (_I, [vp, _I64, vp, vp, _I64, C.c_int32, C.c_int32, vp, vp, vp, vp]),
     "scnerf_adam_step": (_I, [_P(AdamTensor), C.c_int32, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, vp]),
     # ---- include/scnerf_b200_nerfpp.h ----

@@ -14,6 +14,7 @@
 #include "field_tc.cuh"
 #include "nerfpp.cuh"
 #include "adam.cuh"
+#include "prd_loss.cuh"
 #include "../../include/scnerf_b200_nerfpp.h"
 
 using namespace scnerf;
@@ -589,5 +590,42 @@ extern "C" int scnerf_adam_step(const scnerf_adam_tensor* tensors_host, int32_t 
   }
   return 0;
 }
+
+extern "C" {
+static int make_prd_args(const float* o0, const float* d0, const float* o1, const float* d1, const float* kps0,
+                         const float* kps1, const float* K4, const float* E2, float eps, float threshold, int train,
+                         int64_t N, prd::Args& a) {
+  SCNERF_CHECK_ARG(o0 && d0 && o1 && d1 && kps0 && kps1 && K4 && E2, "prd_loss: null pointer");
+  a.o0 = o0; a.d0 = d0; a.o1 = o1; a.d1 = d1; a.kps0 = kps0; a.kps1 = kps1; a.K = K4; a.E = E2;
+  a.eps = eps; a.threshold = threshold; a.train = train; a.N = N;
+  return 0;
+}
+int scnerf_prd_loss_fwd(const float* rays0_o, const float* rays0_d, const float* rays1_o, const float* rays1_d,
+                        const float* kps0, const float* kps1, const float* K4, const float* E2, float eps,
+                        float threshold, int32_t train, int64_t N, float* acc5, float* loss, float* n_match,
+                        void* stream) {
+  prd::Args a;
+  int rc = make_prd_args(rays0_o, rays0_d, rays1_o, rays1_d, kps0, kps1, K4, E2, eps, threshold, train, N, a);
+  if (rc) return rc;
+  SCNERF_CHECK_ARG(acc5 && loss, "prd_loss_fwd: null outputs");
+  SCNERF_CUDA(cudaMemsetAsync(acc5, 0, 5 * sizeof(float), (cudaStream_t)stream));
+  if (N > 0) SCNERF_LAUNCH(prd::fwd_kernel, (unsigned)cdiv(N, 128), 128, 0, stream, a, acc5);
+  SCNERF_LAUNCH(prd::finalize_kernel, 1, 32, 0, stream, acc5, loss, n_match);
+  return 0;
+}
+int scnerf_prd_loss_bwd(const float* rays0_o, const float* rays0_d, const float* rays1_o, const float* rays1_d,
+                        const float* kps0, const float* kps1, const float* K4, const float* E2, float eps,
+                        float threshold, int64_t N, const float* acc5, const float* d_loss, float* d_rays0_o,
+                        float* d_rays0_d, float* d_rays1_o, float* d_rays1_d, float* d_K4, float* d_E2, void* stream) {
+  prd::Args a;
+  int rc = make_prd_args(rays0_o, rays0_d, rays1_o, rays1_d, kps0, kps1, K4, E2, eps, threshold, 1, N, a);
+  if (rc) return rc;
+  SCNERF_CHECK_ARG(acc5 && d_loss && d_rays0_o && d_rays0_d && d_rays1_o && d_rays1_d, "prd_loss_bwd: null pointer");
+  if (N == 0) return 0;
+  SCNERF_LAUNCH(prd::bwd_kernel, (unsigned)cdiv(N, 128), 128, 0, stream, a, acc5, d_loss, d_rays0_o, d_rays0_d,
+                d_rays1_o, d_rays1_d, d_K4, d_E2);
+  return 0;
+}
+}  // extern "C"
 
 #include "api_pp.inc"

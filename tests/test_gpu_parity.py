@@ -567,3 +567,51 @@ def test_ray_batch_sampler(lib):
         assert (kps.cpu().numpy() == np.stack([w, h], -1)).all()
         assert (idx.cpu().numpy() == img).all()
         assert (target.cpu().numpy() == images[i_train[img], h, w]).all()
+
+
+def test_prd_loss(lib, golden):
+    """fused PRD loss (forward + backward kernels) through the reference's own signature, against
+    the live reference's outputs: train mode with the learnable camera (gradients to every camera parameter),
+    train mode with fixed K / poses (gradients to the rays), val mode, NeRF and NeRF++ conventions."""
+    import types
+    from scnerf_b200.get_rays import get_rays_kps_use_camera
+    from scnerf_b200.ray_dist_loss import proj_ray_dist_loss_single
+    g = golden("prd_loss")
+    args = types.SimpleNamespace(proj_ray_dist_threshold=5.0)
+    i, j = int(g["i"]), int(g["j"])
+    kps0, kps1 = T(g["kps0"]).cuda(), T(g["kps1"]).cuda()
+    mods = build_modules(7, "cuda:0")
+    cam = mods["cam"]
+    r0 = get_rays_kps_use_camera(H, W, cam, kps0, idx_in_camera_param=i)
+    r1 = get_rays_kps_use_camera(H, W, cam, kps1, idx_in_camera_param=j)
+    loss, n_match = proj_ray_dist_loss_single(kps0, kps1, i, j, r0, r1, "train", "cuda:0", H, W, args, camera_model=cam,
+                                              i_map=np.arange(synth.FERN_NCAM), method="NeRF")
+    assert abs(float(loss) - float(g["train_loss"])) <= 1e-4 * float(g["train_loss"]), (float(loss), float(g["train_loss"]))
+    assert n_match == float(g["train_n_match"])
+    loss.backward()
+    for k in ("intrinsics_noise", "extrinsics_noise", "ray_o_noise", "ray_d_noise"):
+        ref = g["train_g_" + k]
+        e = float(np.abs(getattr(cam, k).grad.cpu().numpy() - ref).max() / np.abs(ref).max())
+        print(f"prd_loss d/d(camera.{k}): rel-to-max err {e:.2e}")
+        assert e <= 1e-3, (k, e)
+    # fixed K / poses: gradient w.r.t. the rays
+    rays = [T(g["rays_" + k]).cuda().requires_grad_(True) for k in ("o0", "d0", "o1", "d1")]
+    K, E = T(g["K"]).cuda(), T(g["E"]).cuda()
+    loss, n_match = proj_ray_dist_loss_single(kps0, kps1, i, j, (rays[0], rays[1]), (rays[2], rays[3]), "train", "cuda:0",
+                                              H, W, args, intrinsic=K, extrinsic=E, method="NeRF")
+    assert abs(float(loss) - float(g["nocam_loss"])) <= 1e-4 * float(g["nocam_loss"])
+    loss.backward()
+    for name, t in zip(("o0", "d0", "o1", "d1"), rays):
+        ref = g["nocam_g_" + name]
+        e = float(np.abs(t.grad.cpu().numpy() - ref).max() / np.abs(ref).max())
+        print(f"prd_loss d/d(rays_{name}): rel-to-max err {e:.2e}")
+        assert e <= 1e-3, (name, e)
+    with torch.no_grad():
+        r = [t.detach() for t in rays]
+        lv, none = proj_ray_dist_loss_single(kps0, kps1, i, j, (r[0], r[1]), (r[2], r[3]), "val", "cuda:0", H, W, args,
+                                             intrinsic=K, extrinsic=E, method="NeRF")
+        lpp, _ = proj_ray_dist_loss_single(kps0, kps1, i, j, (r[0], r[1]), (r[2], r[3]), "val", "cuda:0", H, W, args,
+                                           intrinsic=K, extrinsic=E, method="NeRF++")
+    assert none is None
+    assert abs(float(lv) - float(g["val_loss"])) <= 1e-4 * float(g["val_loss"])
+    assert abs(float(lpp) - float(g["val_loss_pp"])) <= 1e-4 * float(g["val_loss_pp"])

@@ -323,3 +323,26 @@ def test_custom_adam(golden):
                                         amsgrad=amsgrad, beta1=0.9, beta2=0.999, lr=lr, weight_decay=wd, eps=1e-8)
             for i, p in enumerate(params):
                 close(p, g[f"{tag}_s{step}_p{i}"], 2e-6, 1e-7)
+
+
+def test_prd_loss(golden):
+    """oracle restatement of proj_ray_dist_loss_single vs the live reference."""
+    g = golden("prd_loss")
+    rays = [T(g["rays_" + k]).requires_grad_(True) for k in ("o0", "d0", "o1", "d1")]
+    K, E = T(g["K"]), T(g["E"])
+    E2 = E[[int(g["i"]), int(g["j"])]]
+    kps0, kps1 = T(g["kps0"]).float(), T(g["kps1"]).float()
+    loss, n = O.proj_ray_dist_loss(kps0, kps1, (rays[0], rays[1]), (rays[2], rays[3]), K, E2, 5.0, train=True)
+    close(loss, g["nocam_loss"], 1e-5, 0)
+    assert n == float(g["nocam_n_match"])
+    loss.backward()
+    for name, t in zip(("o0", "d0", "o1", "d1"), rays):
+        ref = g["nocam_g_" + name]
+        close(t.grad, ref, 1e-3, 1e-5 * np.abs(ref).max())
+    with torch.no_grad():
+        r = [t.detach() for t in rays]
+        lv, none = O.proj_ray_dist_loss(kps0, kps1, (r[0], r[1]), (r[2], r[3]), K, E2, 5.0, train=False)
+        lpp, _ = O.proj_ray_dist_loss(kps0, kps1, (r[0], r[1]), (r[2], r[3]), K, E2, 5.0, train=False, method="NeRF++")
+    assert none is None
+    close(lv, g["val_loss"], 1e-5, 0)
+    close(lpp, g["val_loss_pp"], 1e-5, 0)
