@@ -224,26 +224,39 @@ inline int fwd_plan_init() {
   SCNERF_CUDA(cudaGetDevice(&dev));
   if (dev < 64 && done[dev]) return 0;
   static eng::Plan P = fused::make_fwd_plan<3>();   // (image offsets and sources do not depend on NSPLIT)
-  static fused::PlanSrc S;
-  fused::build_fwd_plansrc(S);
-  if (fused::plan_image_bytes(P, 3) > TC_IMG_BYTES) return fail(SCNERF_ERR_WORKSPACE, "TC_IMG_BYTES too small");
+  static eng::Plan P6 = fused::make_fwd_plan<3, 6>();
+  static fused::PlanSrc S, S6;
+  fused::build_fwd_plansrc<4>(S);
+  fused::build_fwd_plansrc<6>(S6);
+  if (fused::plan_image_bytes(P, 3) > TC_IMG_BYTES || fused::plan_image_bytes(P6, 3) > TC_IMG_BYTES)
+    return fail(SCNERF_ERR_WORKSPACE, "TC_IMG_BYTES too small");
   SCNERF_CUDA(cudaMemcpyToSymbol(fused::d_plan_fwd, &P, sizeof(P)));
   SCNERF_CUDA(cudaMemcpyToSymbol(fused::d_plansrc_fwd, &S, sizeof(S)));
-  SCNERF_CUDA(cudaFuncSetAttribute(fused::field_fused_fwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   fused::Cfg<1>::SMEM_BYTES));
-  SCNERF_CUDA(cudaFuncSetAttribute(fused::field_fused_fwd_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   fused::Cfg<3>::SMEM_BYTES));
+  SCNERF_CUDA(cudaMemcpyToSymbol(fused::d_plan_fwd6, &P6, sizeof(P6)));
+  SCNERF_CUDA(cudaMemcpyToSymbol(fused::d_plansrc_fwd6, &S6, sizeof(S6)));
+  SCNERF_CUDA(cudaFuncSetAttribute((fused::field_fused_fwd_kernel<1, 4>), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   fused::Cfg<1, 4>::SMEM_BYTES));
+  SCNERF_CUDA(cudaFuncSetAttribute((fused::field_fused_fwd_kernel<3, 4>), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   fused::Cfg<3, 4>::SMEM_BYTES));
+  SCNERF_CUDA(cudaFuncSetAttribute((fused::field_fused_fwd_kernel<1, 6>), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   fused::Cfg<1, 6>::SMEM_BYTES));
+  SCNERF_CUDA(cudaFuncSetAttribute((fused::field_fused_fwd_kernel<3, 6>), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   fused::Cfg<3, 6>::SMEM_BYTES));
   if (dev < 64) done[dev] = true;
   return 0;
 }
+template <int XS = 4>
 inline const eng::Plan& fwd_plan_host() {
-  static eng::Plan P = fused::make_fwd_plan<3>();
+  static eng::Plan P = fused::make_fwd_plan<3, XS>();
   return P;
 }
 
 inline fused::PackSrc make_pack_src(const scnerf_mlp& m) {
   fused::PackSrc src{};
-  for (int i = 0; i < 8; ++i) { src.w[i] = m.pts_w[i]; src.b[i] = m.pts_b[i]; src.ld[i] = (i == 0) ? 63 : (i == 5 ? 319 : 256); }
+  for (int i = 0; i < 8; ++i) {
+    src.w[i] = m.pts_w[i]; src.b[i] = m.pts_b[i];
+    src.ld[i] = (i == 0) ? m.input_ch : (i == 5 ? m.input_ch + 256 : 256);      // 63 / 319, or 84 / 340 (4-D points)
+  }
   src.w[8] = m.feature_w; src.b[8] = m.feature_b; src.ld[8] = 256;
   src.w[9] = m.views_w; src.b[9] = m.views_b; src.ld[9] = 283;
   src.alpha_w = m.alpha_w; src.alpha_b = m.alpha_b; src.rgb_w = m.rgb_w; src.rgb_b = m.rgb_b;
@@ -264,10 +277,10 @@ inline eng::ImgDump img_alloc(Arena& ar, int64_t tiles, uint32_t F, uint32_t nh)
   d.base = ar.get<uint8_t>((size_t)tiles * F * 256u * nh);
   return d;
 }
-inline void tc_fwd_images_alloc(Arena& ar, int64_t P, int nsplit, TcFwdImages& I) {
+inline void tc_fwd_images_alloc(Arena& ar, int64_t P, int nsplit, TcFwdImages& I, int pts_dim = 3) {
   const int64_t T = cdiv(P, 128);
   const uint32_t nh = nsplit == 3 ? 2 : 1;
-  I.x = img_alloc(ar, T, 64, nh); I.v = img_alloc(ar, T, 32, nh);
+  I.x = img_alloc(ar, T, pts_dim == 4 ? 96 : 64, nh); I.v = img_alloc(ar, T, 32, nh);
   for (int i = 0; i < 8; ++i) I.h[i] = img_alloc(ar, T, 256, nh);
   I.feat = img_alloc(ar, T, 256, nh); I.hv = img_alloc(ar, T, 128, nh);
   I.relu_bits = ar.get<uint4>((size_t)T * 9 * 2 * 128);
@@ -281,7 +294,7 @@ inline void tc_bwd_bufs_alloc(Arena& ar, int64_t P, int nsplit, TcBwdBufs& G) {
   G.wimg = ar.get<uint8_t>(TC_IMG_BYTES);
 }
 
-template <int NSPLIT>
+template <int NSPLIT, int XS = 4>
 inline int field_tc_fwd_impl(const scnerf_mlp& m, const float* rays, int ray_cols, const float* z,
                              const float* pts, const float* viewdirs, int64_t N, int S,
                              const FieldBufs& B, float* raw, void* stream, const TcFwdImages* imgs = nullptr) {
@@ -289,9 +302,9 @@ inline int field_tc_fwd_impl(const scnerf_mlp& m, const float* rays, int ray_col
   static_assert(C_TOTAL <= (int)TC_CBUF_FLOATS, "TC_CBUF_FLOATS too small");
   int rc = fwd_plan_init();
   if (rc) return rc;
-  const eng::Plan& P = fwd_plan_host();
+  const eng::Plan& P = fwd_plan_host<XS>();
   PackSrc src = make_pack_src(m);
-  SCNERF_LAUNCH((pack_fwd_kernel<NSPLIT>), dim3(2, (unsigned)P.n_slabs), 256, 0, stream, src, B.tc_img);
+  SCNERF_LAUNCH((pack_fwd_kernel<NSPLIT, XS>), dim3(2, (unsigned)P.n_slabs), 256, 0, stream, src, B.tc_img);
   SCNERF_LAUNCH(pack_consts_kernel, (unsigned)cdiv(C_TOTAL, 256), 256, 0, stream, src, B.tc_cbuf);
   Args a{};
   a.rays = rays; a.ray_cols = ray_cols; a.z = z; a.pts = pts; a.viewdirs = viewdirs;
@@ -303,7 +316,7 @@ inline int field_tc_fwd_impl(const scnerf_mlp& m, const float* rays, int ray_col
     a.img_out[8] = imgs->feat; a.img_out[9] = imgs->hv;
     a.relu_bits = imgs->relu_bits;
   }
-  if (B.keep_all && B.X5) {   // training with the fp32 CUDA-core backward: fp32 row-major layer inputs
+  if (XS == 4 && B.keep_all && B.X5) {   // training with the fp32 CUDA-core backward: fp32 row-major layer inputs
     for (int s = 0; s < 8; ++s) {
       a.dump[s] = (s == 4) ? B.X5 + 63 : B.H[s];
       a.dump_ld[s] = (s == 4) ? (int)B.ldx5 : 256;
@@ -315,18 +328,24 @@ inline int field_tc_fwd_impl(const scnerf_mlp& m, const float* rays, int ray_col
   }
   a.dbg = tc_dbg_ptr(); a.dbg_tiles = tc_dbg_tiles();
   int grid = std::min(device_sm_count(), a.num_tiles);
-  SCNERF_LAUNCH((field_fused_fwd_kernel<NSPLIT>), grid, 320, Cfg<NSPLIT>::SMEM_BYTES, stream, a);
+  SCNERF_LAUNCH((field_fused_fwd_kernel<NSPLIT, XS>), grid, 320, (Cfg<NSPLIT, XS>::SMEM_BYTES), stream, a);
   return 0;
 }
 
 inline int field_tc_fwd(const scnerf_mlp& m, int precision, const float* rays, int ray_cols,
                         const float* z, const float* pts, const float* viewdirs, int64_t N, int S,
                         const FieldBufs& B, float* raw, void* stream, const TcFwdImages* imgs = nullptr) {
-  if (!(m.D == 8 && m.W == 256 && m.skip == 4 && m.use_viewdirs && m.L_pos == 10 && m.L_dir == 4 && m.pts_dim != 4))
+  if (!(m.D == 8 && m.W == 256 && m.skip == 4 && m.use_viewdirs && m.L_pos == 10 && m.L_dir == 4))
     return fail(SCNERF_ERR_UNSUPPORTED,
                 "tensor-core field path is specialised for the 8x256, skip-4, use_viewdirs network "
                 "(multires 10/4); use precision fp32 for other shapes");
   if (rays && ray_cols != 11) return fail(SCNERF_ERR_ARG, "tensor-core field path needs 11-column rays");
+  if (m.pts_dim == 4) {    // NeRF++ background network: explicit (x, y, z, 1/r) points, 84-channel encoding
+    if (!pts || !viewdirs) return fail(SCNERF_ERR_ARG, "tensor-core field path: 4-D points must be given explicitly");
+    if (precision == SCNERF_PRECISION_BF16X3)
+      return field_tc_fwd_impl<3, 6>(m, nullptr, 0, nullptr, pts, viewdirs, N, S, B, raw, stream, imgs);
+    return field_tc_fwd_impl<1, 6>(m, nullptr, 0, nullptr, pts, viewdirs, N, S, B, raw, stream, imgs);
+  }
   if (precision == SCNERF_PRECISION_BF16X3)
     return field_tc_fwd_impl<3>(m, rays, ray_cols, z, pts, viewdirs, N, S, B, raw, stream, imgs);
   return field_tc_fwd_impl<1>(m, rays, ray_cols, z, pts, viewdirs, N, S, B, raw, stream, imgs);

@@ -35,21 +35,23 @@ using eng::TILE_M;
 constexpr int NSTAGE = 10;
 // per stage: output width N, k16 slabs taken from X (PE pts, smem), H (hidden, TMEM), V (PE dir, smem)
 struct StageDef { int N, kx, kh, kv, relu; };
+// XS = k16 slabs of PE(pts): 4 (63 channels, 3-D points) or 6 (84 channels, NeRF++ background (x,y,z,1/r))
+template <int XS = 4>
 __host__ __device__ constexpr StageDef stage_def(int s) {
-  return s == 0 ? StageDef{256, 4, 0, 0, 1}
-       : s == 5 ? StageDef{256, 4, 16, 0, 1}
+  return s == 0 ? StageDef{256, XS, 0, 0, 1}
+       : s == 5 ? StageDef{256, XS, 16, 0, 1}
        : s == 8 ? StageDef{256, 0, 16, 0, 0}      // feature_linear: no activation
        : s == 9 ? StageDef{128, 0, 16, 2, 1}      // views_linears[0]
                 : StageDef{256, 0, 16, 0, 1};
 }
 
 // smem A area (byte offsets from its base); the lo images exist only in the split-bf16 build
-template <int NSPLIT> struct ALay {
+template <int NSPLIT, int XS = 4> struct ALay {
   static constexpr int XHI = 0;
-  static constexpr int XLO = 16384;
-  static constexpr int VHI = NSPLIT == 3 ? 32768 : 16384;
+  static constexpr int XLO = XS * 4096;
+  static constexpr int VHI = (NSPLIT == 3 ? 2 : 1) * XS * 4096;
   static constexpr int VLO = VHI + 8192;
-  static constexpr int ONES = NSPLIT == 3 ? 49152 : 24576;
+  static constexpr int ONES = VHI + (NSPLIT == 3 ? 16384 : 8192);
   static constexpr int BYTES = ONES + 4096;
 };
 
@@ -67,16 +69,18 @@ struct PackSrc {
   const float *alpha_w, *alpha_b, *rgb_w, *rgb_b;
 };
 
-constexpr int N_PAD_SLABS = 4;
-template <int NSPLIT>
+// real slabs: XS = 4 -> 164, padded to 168; XS = 6 -> 168 exactly (both = 8 x 21 = 2 x 12 x 7)
+__host__ __device__ constexpr int n_pad_slabs(int xs) { return xs == 4 ? 4 : 0; }
+template <int NSPLIT, int XS = 4>
 __host__ __device__ constexpr eng::Plan make_fwd_plan() {
-  constexpr int A_XHI = ALay<NSPLIT>::XHI, A_XLO = ALay<NSPLIT>::XLO, A_VHI = ALay<NSPLIT>::VHI,
-                A_VLO = ALay<NSPLIT>::VLO, A_ONES = ALay<NSPLIT>::ONES;
+  constexpr int A_XHI = ALay<NSPLIT, XS>::XHI, A_XLO = ALay<NSPLIT, XS>::XLO, A_VHI = ALay<NSPLIT, XS>::VHI,
+                A_VLO = ALay<NSPLIT, XS>::VLO, A_ONES = ALay<NSPLIT, XS>::ONES;
+  constexpr int N_PAD_SLABS = n_pad_slabs(XS);
   eng::Plan P{};
   int n = 0;
   uint32_t off = 0;
   for (int s = 0; s < NSTAGE; ++s) {
-    const StageDef d = stage_def(s);
+    const StageDef d = stage_def<XS>(s);
     const int nk = d.kx + d.kh + d.kv;
     for (int j = 0; j <= nk; ++j, ++n) {
       eng::SlabDef e{};
@@ -92,7 +96,7 @@ __host__ __device__ constexpr eng::Plan make_fwd_plan() {
         e.a_kind = eng::A_SMEM; e.a_off = (uint16_t)((A_VHI + (j - d.kx - d.kh) * 4096) / 16);
         e.a_lo_delta = (A_VLO - A_VHI) / 16;
       }
-      if (s == NSTAGE - 1 && j == nk) e.flags = (uint8_t)(e.flags & ~eng::F_STAGE_END);   // padding follows
+      if (N_PAD_SLABS > 0 && s == NSTAGE - 1 && j == nk) e.flags = (uint8_t)(e.flags & ~eng::F_STAGE_END);   // padding follows
       P.slab[n] = e;
       off += (uint32_t)d.N * 32u;
     }
@@ -110,17 +114,20 @@ __host__ __device__ constexpr eng::Plan make_fwd_plan() {
   P.n_slabs = n; P.n_stages = NSTAGE;
   return P;
 }
+template <int XS = 4>
 inline void build_fwd_plansrc(PlanSrc& S) {
+  constexpr int N_PAD_SLABS = n_pad_slabs(XS);
+  constexpr int IN_CH = XS == 4 ? 63 : 84;
   int n = 0;
   for (int s = 0; s < NSTAGE; ++s) {
-    const StageDef d = stage_def(s);
+    const StageDef d = stage_def<XS>(s);
     const int nk = d.kx + d.kh + d.kv;
     for (int j = 0; j <= nk; ++j, ++n) {
       SrcDef q{};
       q.wsel = (uint8_t)s; q.valid_n = (uint16_t)d.N;
       if (j == nk) q.kind = 2;
-      else if (j < d.kx) { q.col0 = (uint16_t)(16 * j); q.valid_k = (uint16_t)std::min(16, 63 - 16 * j); }
-      else if (j < d.kx + d.kh) { q.col0 = (uint16_t)((d.kx ? 63 : 0) + 16 * (j - d.kx)); q.valid_k = 16; }
+      else if (j < d.kx) { q.col0 = (uint16_t)(16 * j); q.valid_k = (uint16_t)std::max(0, std::min(16, IN_CH - 16 * j)); }
+      else if (j < d.kx + d.kh) { q.col0 = (uint16_t)((d.kx ? IN_CH : 0) + 16 * (j - d.kx)); q.valid_k = 16; }
       else { const int jv = j - d.kx - d.kh; q.col0 = (uint16_t)(256 + 16 * jv); q.valid_k = (uint16_t)std::min(16, 27 - 16 * jv); }
       S.s[n] = q;
     }
@@ -179,16 +186,18 @@ __global__ void pack_consts_kernel(PackSrc src, float* __restrict__ cbuf) {
   cbuf[g] = v;
 }
 
-template <int NSPLIT_> struct Cfg {
+template <int NSPLIT_, int XS_ = 4> struct Cfg {
   static constexpr int NSPLIT = NSPLIT_;
-  static constexpr eng::Plan PLAN = make_fwd_plan<NSPLIT_>();
+  static constexpr int XS = XS_;
+  static constexpr eng::Plan PLAN = make_fwd_plan<NSPLIT_, XS_>();
   static constexpr int GROUP = NSPLIT_ == 1 ? 2 : 1;         // slabs per ring slot
-  static constexpr int NSLOT = NSPLIT_ == 1 ? 12 : 8;        // 168 slabs per tile = 84 pairs = 12*7 = 8*21
+  static constexpr int NSLOT = NSPLIT_ == 1 ? (XS_ == 4 ? 12 : 7) : 8;   // 168 slabs per tile = 84 pairs = 12*7 = 8*21
+                                                                         // (XS = 6, bf16: 7 slots, the X slabs need the room)
   static constexpr int SLOT_BYTES = 16384;
   static_assert((PLAN.n_slabs / GROUP) % NSLOT == 0 && PLAN.n_slabs % GROUP == 0, "ring size must divide the slab-group count");
   static constexpr int OFF_RING = 0;
   static constexpr int OFF_A = NSLOT * SLOT_BYTES;
-  static constexpr int OFF_C = OFF_A + ALay<NSPLIT_>::BYTES;
+  static constexpr int OFF_C = OFF_A + ALay<NSPLIT_, XS_>::BYTES;
   static constexpr int OFF_OUT = OFF_C + ((C_TOTAL * 4 + 127) / 128) * 128;   // [128][4] head partial sums
   static constexpr int OFF_BAR = OFF_OUT + 128 * 4 * 4;
   static constexpr int SMEM_BYTES = OFF_BAR + (2 * NSLOT + 2) * 8 + 16;
@@ -219,10 +228,14 @@ struct Args {
 
 __device__ eng::Plan d_plan_fwd;       // runtime copy of the constexpr plan, for the pack kernel
 __device__ PlanSrc d_plansrc_fwd;
-template <int NSPLIT>
+__device__ eng::Plan d_plan_fwd6;      // ... of the XS = 6 (4-D points) plan
+__device__ PlanSrc d_plansrc_fwd6;
+template <int NSPLIT, int XS = 4>
 __global__ void __launch_bounds__(256) pack_fwd_kernel(PackSrc src, uint8_t* __restrict__ img) {
   const int i = blockIdx.y;
-  if (i < d_plan_fwd.n_slabs) pack_slab_impl<NSPLIT>(d_plan_fwd.slab[i], d_plansrc_fwd.s[i], src, img);
+  const eng::Plan& P = XS == 4 ? d_plan_fwd : d_plan_fwd6;
+  const PlanSrc& S = XS == 4 ? d_plansrc_fwd : d_plansrc_fwd6;
+  if (i < P.n_slabs) pack_slab_impl<NSPLIT>(P.slab[i], S.s[i], src, img);
 }
 
 // sin/cos with 3-term Cody-Waite reduction by pi/2 and the usual degree-7/8 minimax kernels: <= 7e-8
@@ -251,16 +264,16 @@ __device__ __forceinline__ void sincos_cw(float a, float& sv, float& cv) {
 
 // PE columns [LO, LO+32) of a 3-vector with L frequencies ([x, sin(2^0 x), cos(2^0 x), ...], zero padded):
 // one sin/cos evaluation per (frequency, component) pair that touches the range; indices are compile-time.
-template <int L, int LO>
-__device__ __forceinline__ void pe_fill32(const float (&x)[3], bool valid, float (&e)[32]) {
+template <int L, int LO, int DIM = 3>
+__device__ __forceinline__ void pe_fill32(const float (&x)[DIM], bool valid, float (&e)[32]) {
 #pragma unroll
-  for (int i = 0; i < 32; ++i) e[i] = (valid && LO + i < 3) ? x[(LO + i) % 3] : 0.f;
+  for (int i = 0; i < 32; ++i) e[i] = (valid && LO + i < DIM) ? x[(LO + i) % DIM] : 0.f;
   if (!valid) return;
 #pragma unroll
   for (int f = 0; f < L; ++f) {
 #pragma unroll
-    for (int c = 0; c < 3; ++c) {
-      const int is = 3 + 6 * f + c, ic = is + 3;
+    for (int c = 0; c < DIM; ++c) {
+      const int is = DIM + 2 * DIM * f + c, ic = is + DIM;
       const bool need_s = is >= LO && is < LO + 32, need_c = ic >= LO && ic < LO + 32;
       if (need_s || need_c) {
         float sv, cv;
@@ -384,12 +397,12 @@ __device__ __forceinline__ void epi_tile(const Args& a, const float* cst, uint32
                               a_ready_addr, alpha, rgb, ctx, tile_iter), ...);
 }
 
-template <int NSPLIT>
+template <int NSPLIT, int XS = 4>
 __global__ void __launch_bounds__(320, 1) field_fused_fwd_kernel(const __grid_constant__ Args a) {
-  using C = Cfg<NSPLIT>;
+  using C = Cfg<NSPLIT, XS>;
   constexpr bool SPLIT = NSPLIT == 3;
-  constexpr int A_XHI = ALay<NSPLIT>::XHI, A_XLO = ALay<NSPLIT>::XLO, A_VHI = ALay<NSPLIT>::VHI,
-                A_VLO = ALay<NSPLIT>::VLO, A_ONES = ALay<NSPLIT>::ONES;
+  constexpr int A_XHI = ALay<NSPLIT, XS>::XHI, A_XLO = ALay<NSPLIT, XS>::XLO, A_VHI = ALay<NSPLIT, XS>::VHI,
+                A_VLO = ALay<NSPLIT, XS>::VLO, A_ONES = ALay<NSPLIT, XS>::ONES;
   extern __shared__ __align__(128) uint8_t fsm[];
   uint8_t* ringp = fsm + C::OFF_RING;
   uint8_t* areg = fsm + C::OFF_A;
@@ -443,7 +456,35 @@ __global__ void __launch_bounds__(320, 1) field_fused_fwd_kernel(const __grid_co
       const int64_t p = (int64_t)tile * TILE_M + row;
       const bool valid = p < a.P;
       // ---- positional encodings -> smem A slabs (half 0: X chunks 0-3; half 1: X 4-7 and V 0-3)
-      {
+      if constexpr (XS == 6) {
+        // NeRF++ background: explicit 4-D points (x, y, z, 1/r), 84-channel encoding in 6 slabs
+        // (half 0: X columns 0..31 + PE(dir); half 1: X columns 32..95)
+        float x[4] = {0.f, 0.f, 0.f, 0.f}, vd[3] = {0.f, 0.f, 0.f};
+        if (valid) {
+          const int64_t r = p / a.S;
+          const float4 q = *reinterpret_cast<const float4*>(a.pts + p * 4);
+          x[0] = q.x; x[1] = q.y; x[2] = q.z; x[3] = q.w;
+#pragma unroll
+          for (int c = 0; c < 3; ++c) vd[c] = a.viewdirs[r * 3 + c];
+        }
+        float* dpe = a.dump_pe ? a.dump_pe + p * a.dump_pe_ld : nullptr;
+        float* dped = a.dump_ped ? a.dump_ped + p * a.dump_ped_ld : nullptr;
+        float e[32];
+        if (half == 0) {
+          pe_fill32<10, 0, 4>(x, valid, e);
+          pe_store32<SPLIT>(e, 0, 84, areg + A_XHI, areg + A_XLO, row, a.img_x, tile, dpe, valid, ctx.pol_stream);
+          pe_fill32<4, 0>(vd, valid, e);
+          pe_store32<SPLIT>(e, 0, 27, areg + A_VHI, areg + A_VLO, row, a.img_v, tile, dped, valid, ctx.pol_stream);
+          *reinterpret_cast<float4*>(out_s + row * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+        } else {
+          pe_fill32<10, 32, 4>(x, valid, e);
+          pe_store32<SPLIT>(e, 32, 84, areg + A_XHI, areg + A_XLO, row, a.img_x, tile, dpe, valid, ctx.pol_stream);
+          pe_fill32<10, 64, 4>(x, valid, e);
+          pe_store32<SPLIT>(e, 64, 84, areg + A_XHI, areg + A_XLO, row, a.img_x, tile, dpe, valid, ctx.pol_stream);
+        }
+        tc::fence_proxy_async();
+        tc::mbar_arrive(a_ready);
+      } else {
         float x[3] = {0.f, 0.f, 0.f}, vd[3] = {0.f, 0.f, 0.f};
         if (valid) {
           const int64_t r = p / a.S;

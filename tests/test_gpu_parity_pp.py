@@ -350,3 +350,35 @@ def test_pp_render_single_image():
         d = np.abs(got - rets[m]["rgb"].numpy()).max(1)
         print(f"render_single_image level {m}: {(d > 1e-4).sum()} of 256 pixels off by > 1e-4 (max {d.max():.2e})")
         assert (d > 1e-4).sum() <= 3 and d.max() <= 2e-2          # det sampling: the u = 1.0 knot (test_pp_sampling)
+
+
+def _bg_field_fwd(net, pts4, vd, precision):
+    """raw[N,S,4] of the background MLP through scnerf_field_fwd (inference entry point)."""
+    from scnerf_b200 import _lib
+    lib = _lib.load()
+    m = net.bg_net.c_struct(pts_dim=4)
+    N, S = pts4.shape[:2]
+    nb = lib.scnerf_field_workspace_bytes(m, N * S, 0)
+    ws = torch.empty(nb, device=DEV, dtype=torch.uint8)
+    raw = torch.empty(N, S, 4, device=DEV)
+    _lib.check(lib.scnerf_field_fwd(m, _lib.ptr(pts4), _lib.ptr(vd), N, S, _lib.ptr(raw), _lib.PRECISION[precision],
+                                    _lib.ptr(ws), nb, _lib.stream()), "field_fwd(bg)")
+    return raw
+
+
+def test_pp_bg_field_tensor_core_forward():
+    """The 84-channel (4-D point) variant of the fused tcgen05 forward against the fp32 CUDA-core kernels."""
+    net = make_net(40)
+    rng = np.random.default_rng(2)
+    for N, S in ((1, 1), (3, 100), (64, 192)):
+        p = rng.standard_normal((N, S, 3)).astype(np.float32)
+        p /= np.linalg.norm(p, axis=-1, keepdims=True)
+        pts4 = T(np.concatenate([p, rng.uniform(0, 1, (N, S, 1)).astype(np.float32)], -1)).to(DEV).contiguous()
+        v = rng.standard_normal((N, 3)).astype(np.float32)
+        vd = T(v / np.linalg.norm(v, axis=-1, keepdims=True)).to(DEV).contiguous()
+        ref = _bg_field_fwd(net, pts4, vd, "fp32")
+        for prec, tol in (("bf16x3", 1e-4), ("bf16", 3e-2)):
+            got = _bg_field_fwd(net, pts4, vd, prec)
+            e = relmax(got, ref.cpu().numpy())
+            print(f"bg field {prec} N={N} S={S}: rel-to-max err {e:.2e}")
+            assert e <= tol, (prec, N, S, e)
