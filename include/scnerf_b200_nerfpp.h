@@ -82,12 +82,13 @@ int scnerf_pp_depth_bwd(const float* d_depth, const float* coef, int64_t N, int6
  * scnerf_mlp carries it with base_layers -> pts_*, sigma_layers -> alpha_*, base_remap_layers ->
  * feature_*, rgb_layers.0 -> views_*, rgb_layers.2 -> rgb_*; raw[.,0:3] is rgb BEFORE the sigmoid and
  * raw[.,3] sigma BEFORE the abs (both applied in scnerf_pp_composite_*).  The background network sets
- * pts_dim = 4, input_ch = 84.
+ * pts_dim = 4, input_ch = 84 (its own tensor-core slab plans: 6 PE slabs, 96-wide d(PE) stages).
  *
  * Generic field evaluation that keeps what the backward needs in the caller's workspace.
  *   points: (rays[N,ray_cols], z[N,S]) -> pts = o + z d, viewdirs = rays[:,8:11]     (pts == NULL)
  *       or  explicit pts[N,S,pts_dim] + viewdirs[N,3]                                (rays == NULL)
- * precision: SCNERF_PRECISION_* (tensor-core paths need pts_dim == 3 and the (rays, z) form).
+ * precision: SCNERF_PRECISION_*; the tensor-core paths take the (rays, z) form for 3-D points and the explicit
+ * form for 4-D points (the two network shapes of the reference).
  * Backward outputs (any may be NULL): d_rays[N,ray_cols] += (columns o, d, viewdirs), d_z[N,S]
  * overwrite (d_pts . d), d_pts[N,S,pts_dim] overwrite, d_viewdirs[N,3] +=.
  * ---------------------------------------------------------------------------------------------- */

@@ -290,7 +290,7 @@ inline void tc_bwd_bufs_alloc(Arena& ar, int64_t P, int nsplit, TcBwdBufs& G) {
   const uint32_t nh = nsplit == 3 ? 2 : 1;
   for (int i = 0; i < 8; ++i) G.dz[i] = img_alloc(ar, T, 256, nh);
   G.dfeat = img_alloc(ar, T, 256, nh); G.dzv = img_alloc(ar, T, 128, nh);
-  G.g_pts = ar.get<float>(P * 3); G.g_vd = ar.get<float>(P * 3);
+  G.g_pts = ar.get<float>(P * 4); G.g_vd = ar.get<float>(P * 3);     // g_pts: [P,3], or [P,4] for 4-D points
   G.wimg = ar.get<uint8_t>(TC_IMG_BYTES);
 }
 
@@ -357,16 +357,25 @@ inline int bwd_plan_init() {
   int dev = 0;
   SCNERF_CUDA(cudaGetDevice(&dev));
   if (dev < 64 && done[dev]) return 0;
-  static eng::Plan P = dgrad::make_plan();
-  static fused::PlanSrc S;
-  dgrad::build_plansrc(S);
-  if (fused::plan_image_bytes(P, 3) > TC_IMG_BYTES) return fail(SCNERF_ERR_WORKSPACE, "TC_IMG_BYTES too small (dgrad)");
+  static eng::Plan P = dgrad::make_plan<64>();
+  static eng::Plan P96 = dgrad::make_plan<96>();
+  static fused::PlanSrc S, S96;
+  dgrad::build_plansrc<64>(S);
+  dgrad::build_plansrc<96>(S96);
+  if (fused::plan_image_bytes(P, 3) > TC_IMG_BYTES || fused::plan_image_bytes(P96, 3) > TC_IMG_BYTES)
+    return fail(SCNERF_ERR_WORKSPACE, "TC_IMG_BYTES too small (dgrad)");
   SCNERF_CUDA(cudaMemcpyToSymbol(dgrad::d_plan_dgrad, &P, sizeof(P)));
   SCNERF_CUDA(cudaMemcpyToSymbol(dgrad::d_plansrc_dgrad, &S, sizeof(S)));
-  SCNERF_CUDA(cudaFuncSetAttribute(dgrad::field_fused_dgrad_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   dgrad::Cfg<1>::SMEM_BYTES));
-  SCNERF_CUDA(cudaFuncSetAttribute(dgrad::field_fused_dgrad_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   dgrad::Cfg<3>::SMEM_BYTES));
+  SCNERF_CUDA(cudaMemcpyToSymbol(dgrad::d_plan_dgrad96, &P96, sizeof(P96)));
+  SCNERF_CUDA(cudaMemcpyToSymbol(dgrad::d_plansrc_dgrad96, &S96, sizeof(S96)));
+  SCNERF_CUDA(cudaFuncSetAttribute((dgrad::field_fused_dgrad_kernel<1, 64>), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   dgrad::Cfg<1, 64>::SMEM_BYTES));
+  SCNERF_CUDA(cudaFuncSetAttribute((dgrad::field_fused_dgrad_kernel<3, 64>), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   dgrad::Cfg<3, 64>::SMEM_BYTES));
+  SCNERF_CUDA(cudaFuncSetAttribute((dgrad::field_fused_dgrad_kernel<1, 96>), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   dgrad::Cfg<1, 96>::SMEM_BYTES));
+  SCNERF_CUDA(cudaFuncSetAttribute((dgrad::field_fused_dgrad_kernel<3, 96>), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   dgrad::Cfg<3, 96>::SMEM_BYTES));
   SCNERF_CUDA(cudaFuncSetAttribute(wgrad::field_wgrad_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    wgrad::Cfg<1>::SMEM_BYTES));
   SCNERF_CUDA(cudaFuncSetAttribute(wgrad::field_wgrad_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -374,9 +383,9 @@ inline int bwd_plan_init() {
   if (dev < 64) done[dev] = true;
   return 0;
 }
-inline int dgrad_n_slabs() {
+inline int dgrad_n_slabs() {      // the same for both d(PE) widths (only N of two stages differs)
   static int n = -1;
-  if (n < 0) { static eng::Plan P = dgrad::make_plan(); n = P.n_slabs; }
+  if (n < 0) { static eng::Plan P = dgrad::make_plan<64>(); n = P.n_slabs; }
   return n;
 }
 
@@ -386,25 +395,34 @@ inline void wgrad_unit(wgrad::Unit& u, int a_img, int a_half, int b_img, int n, 
   u.rows_valid = rows_valid; u.cols_valid = cols_valid;
 }
 
-template <int NSPLIT>
+// XN = 64: 3-D points formed from (rays, z), d_rays reduced per ray.
+// XN = 96: explicit 4-D points (NeRF++ background): d_pts = G.g_pts [P,4] stays per sample, d_viewdirs[N,3] +=.
+template <int NSPLIT, int XN = 64>
 inline int field_tc_bwd_impl(const scnerf_mlp& m, const scnerf_mlp& g, const float* rays, int ray_cols,
                              const float* z, int64_t N, int S, const FieldBufs& B, const TcFwdImages& I,
-                             const TcBwdBufs& G, const float* g_raw, float* d_rays, void* stream) {
+                             const TcBwdBufs& G, const float* g_raw, float* d_rays, void* stream,
+                             const float* pts = nullptr, const float* viewdirs = nullptr,
+                             float* d_viewdirs = nullptr) {
+  constexpr int IN_CH = XN == 64 ? 63 : 84;
   int rc = bwd_plan_init();
   if (rc) return rc;
   const int64_t P = N * S;
   const int T = (int)cdiv(P, 128);
   fused::PackSrc src = make_pack_src(m);
-  SCNERF_LAUNCH((dgrad::pack_dgrad_kernel<NSPLIT>), dim3(2, (unsigned)dgrad_n_slabs()), 256, 0, stream, src, G.wimg);
+  SCNERF_LAUNCH((dgrad::pack_dgrad_kernel<NSPLIT, XN>), dim3(2, (unsigned)dgrad_n_slabs()), 256, 0, stream, src, G.wimg);
   SCNERF_LAUNCH(fused::pack_consts_kernel, (unsigned)cdiv(fused::C_TOTAL, 256), 256, 0, stream, src, B.tc_cbuf);
   dgrad::Args a{};
   a.rays = rays; a.ray_cols = ray_cols; a.z = z; a.P = P; a.S = S; a.num_tiles = T;
+  a.pts = pts; a.viewdirs = viewdirs;
   a.g_raw = g_raw; a.wimg = G.wimg; a.cbuf = B.tc_cbuf;
   for (int i = 0; i < 8; ++i) a.out_dz[i] = G.dz[i];
   a.relu_bits = I.relu_bits; a.out_dfeat = G.dfeat; a.out_dzv = G.dzv; a.g_pts = G.g_pts; a.g_vd = G.g_vd;
-  SCNERF_LAUNCH((dgrad::field_fused_dgrad_kernel<NSPLIT>), std::min(device_sm_count(), T), 320,
-                dgrad::Cfg<NSPLIT>::SMEM_BYTES, stream, a);
-  if (d_rays)
+  SCNERF_LAUNCH((dgrad::field_fused_dgrad_kernel<NSPLIT, XN>), std::min(device_sm_count(), T), 320,
+                (dgrad::Cfg<NSPLIT, XN>::SMEM_BYTES), stream, a);
+  if (XN == 96) {
+    if (d_viewdirs)
+      SCNERF_LAUNCH(dgrad::reduce_vd_grad_kernel, (unsigned)cdiv(N, 4), 128, 0, stream, G.g_vd, N, S, d_viewdirs);
+  } else if (d_rays)
     SCNERF_LAUNCH(dgrad::reduce_pts_grad_kernel, (unsigned)cdiv(N, 4), 128, 0, stream, G.g_pts, G.g_vd, z, N, S,
                   ray_cols, d_rays);
   // ---- wgrad jobs --------------------------------------------------------------------------------------
@@ -444,13 +462,13 @@ inline int field_tc_bwd_impl(const scnerf_mlp& m, const scnerf_mlp& g, const flo
   {   // J0: layer 0 (dZ0 x X) and the skip columns of layer 5 (dZ5 x X)
     wgrad::Job& J = w.job[0];
     J.a[0] = G.dz[0]; J.a[1] = G.dz[5]; J.na = 2; J.b[0] = I.x; J.nb = 1; J.nu = 4; J.db = g.pts_b[0];
-    wgrad_unit(J.u[0], 0, 0, 0, 64, 0, g.pts_w[0], 63, 128, 63);
-    wgrad_unit(J.u[1], 0, 1, 0, 64, 64, g.pts_w[0] + 128 * 63, 63, 128, 63);
-    wgrad_unit(J.u[2], 1, 0, 0, 64, 128, g.pts_w[5], 319, 128, 63);
-    wgrad_unit(J.u[3], 1, 1, 0, 64, 192, g.pts_w[5] + 128 * 319, 319, 128, 63);
+    wgrad_unit(J.u[0], 0, 0, 0, XN, 0, g.pts_w[0], IN_CH, 128, IN_CH);
+    wgrad_unit(J.u[1], 0, 1, 0, XN, XN, g.pts_w[0] + 128 * IN_CH, IN_CH, 128, IN_CH);
+    wgrad_unit(J.u[2], 1, 0, 0, XN, 2 * XN, g.pts_w[5], IN_CH + 256, 128, IN_CH);
+    wgrad_unit(J.u[3], 1, 1, 0, XN, 3 * XN, g.pts_w[5] + 128 * (IN_CH + 256), IN_CH + 256, 128, IN_CH);
   }
   for (int l = 1; l <= 4; ++l) std_job(w.job[l], G.dz[l], I.h[l - 1], g.pts_w[l], 256, 0, 256, g.pts_b[l]);
-  std_job(w.job[5], G.dz[5], I.h[4], g.pts_w[5], 319, 63, 256, g.pts_b[5]);
+  std_job(w.job[5], G.dz[5], I.h[4], g.pts_w[5], IN_CH + 256, IN_CH, 256, g.pts_b[5]);
   std_job(w.job[6], G.dz[6], I.h[5], g.pts_w[6], 256, 0, 256, g.pts_b[6]);
   std_job(w.job[7], G.dz[7], I.h[6], g.pts_w[7], 256, 0, 256, g.pts_b[7]);
   std_job(w.job[8], G.dfeat, I.h[7], g.feature_w, 256, 0, 256, g.feature_b);
@@ -469,7 +487,13 @@ inline int field_tc_bwd_impl(const scnerf_mlp& m, const scnerf_mlp& g, const flo
 }
 inline int field_tc_bwd(const scnerf_mlp& m, const scnerf_mlp& g, int precision, const float* rays, int ray_cols,
                         const float* z, int64_t N, int S, const FieldBufs& B, const TcFwdImages& I,
-                        const TcBwdBufs& G, const float* g_raw, float* d_rays, void* stream) {
+                        const TcBwdBufs& G, const float* g_raw, float* d_rays, void* stream,
+                        const float* pts = nullptr, const float* viewdirs = nullptr, float* d_viewdirs = nullptr) {
+  if (m.pts_dim == 4) {
+    if (precision == SCNERF_PRECISION_BF16X3)
+      return field_tc_bwd_impl<3, 96>(m, g, nullptr, 0, nullptr, N, S, B, I, G, g_raw, nullptr, stream, pts, viewdirs, d_viewdirs);
+    return field_tc_bwd_impl<1, 96>(m, g, nullptr, 0, nullptr, N, S, B, I, G, g_raw, nullptr, stream, pts, viewdirs, d_viewdirs);
+  }
   if (precision == SCNERF_PRECISION_BF16X3)
     return field_tc_bwd_impl<3>(m, g, rays, ray_cols, z, N, S, B, I, G, g_raw, d_rays, stream);
   return field_tc_bwd_impl<1>(m, g, rays, ray_cols, z, N, S, B, I, G, g_raw, d_rays, stream);

@@ -26,8 +26,9 @@ constexpr int ACC2_COL = 320;
 // one k16 slab of a transposed-weight GEMM stage
 struct SlabSpec { int N, acc_col, j, first, last, stage_begin, wsel, col0, valid_n, stage; };
 // enumerate the slab sequence (shared by the constexpr plan and the host-side pack table)
-template <class F>
+template <int XN = 64, class F>
 __host__ __device__ constexpr void for_each_slab(F&& f) {
+  constexpr int IN_CH = XN == 64 ? 63 : 84;
   // S1 (stage 0): [g_feat | g_V] = dZ_v (K=128) * W_views
   for (int j = 0; j < 8; ++j) {
     f(SlabSpec{256, 0, j, j == 0, 0, j == 0, 9, 0, 256, 0});
@@ -37,13 +38,13 @@ __host__ __device__ constexpr void for_each_slab(F&& f) {
   const int spec[10][4] = {{8, 256, 0, 256},   // S2 : g_h7 = g_feat * W_feature
                            {7, 256, 0, 256},   // S3 : g_h6 = dZ7 * W7
                            {6, 256, 0, 256},   // S4 : g_h5 = dZ6 * W6
-                           {5, 64, 0, 63},     // S5a: g_X (skip branch) = dZ5 * W5[:, :63]
-                           {5, 256, 63, 256},  // S5b: g_h4 = dZ5 * W5[:, 63:]
+                           {5, XN, 0, IN_CH},  // S5a: g_X (skip branch) = dZ5 * W5[:, :63]
+                           {5, 256, IN_CH, 256},  // S5b: g_h4 = dZ5 * W5[:, 63:]
                            {4, 256, 0, 256},   // S6 : g_h3
                            {3, 256, 0, 256},   // S7 : g_h2
                            {2, 256, 0, 256},   // S8 : g_h1
                            {1, 256, 0, 256},   // S9 : g_h0
-                           {0, 64, 0, 63}};    // S10: g_X (layer 0) = dZ0 * W0
+                           {0, XN, 0, IN_CH}}; // S10: g_X (layer 0) = dZ0 * W0
   for (int t = 0; t < 10; ++t)
     for (int j = 0; j < 16; ++j)
       f(SlabSpec{spec[t][1], 0, j, j == 0, j == 15, j == 0, spec[t][0], spec[t][2], spec[t][3], t + 1});
@@ -62,15 +63,17 @@ struct PlanFiller {
     off += (uint32_t)q.N * 32u;
   }
 };
+template <int XN = 64>
 __host__ __device__ constexpr eng::Plan make_plan() {
   PlanFiller f{};
-  for_each_slab(f);
+  for_each_slab<XN>(f);
   f.P.n_slabs = f.n; f.P.n_stages = NSTAGE;
   return f.P;
 }
+template <int XN = 64>
 inline void build_plansrc(PlanSrc& S) {
   int n = 0;
-  for_each_slab([&](const SlabSpec& q) {
+  for_each_slab<XN>([&](const SlabSpec& q) {
     SrcDef d{};
     d.wsel = (uint8_t)q.wsel; d.kind = 1; d.row0 = (uint16_t)(16 * q.j); d.col0 = (uint16_t)q.col0;
     d.valid_k = 16; d.valid_n = (uint16_t)q.valid_n;
@@ -80,40 +83,48 @@ inline void build_plansrc(PlanSrc& S) {
 
 __device__ eng::Plan d_plan_dgrad;
 __device__ PlanSrc d_plansrc_dgrad;
-template <int NSPLIT>
+__device__ eng::Plan d_plan_dgrad96;      // 4-D points: 96-wide d(PE) stages
+__device__ PlanSrc d_plansrc_dgrad96;
+template <int NSPLIT, int XN = 64>
 __global__ void __launch_bounds__(256) pack_dgrad_kernel(fused::PackSrc src, uint8_t* __restrict__ img) {
   const int i = blockIdx.y;
-  if (i < d_plan_dgrad.n_slabs) fused::pack_slab_impl<NSPLIT>(d_plan_dgrad.slab[i], d_plansrc_dgrad.s[i], src, img);
+  const eng::Plan& P = XN == 64 ? d_plan_dgrad : d_plan_dgrad96;
+  const PlanSrc& S = XN == 64 ? d_plansrc_dgrad : d_plansrc_dgrad96;
+  if (i < P.n_slabs) fused::pack_slab_impl<NSPLIT>(P.slab[i], S.s[i], src, img);
 }
 
-template <int NSPLIT_> struct Cfg {
+template <int NSPLIT_, int XN_ = 64> struct Cfg {
   static constexpr int NSPLIT = NSPLIT_;
-  static constexpr eng::Plan PLAN = make_plan();
+  static constexpr int XN = XN_;
+  static constexpr eng::Plan PLAN = make_plan<XN_>();
   static constexpr int GROUP = NSPLIT_ == 1 ? 2 : 1;          // slabs per ring slot
-  static constexpr int NSLOT = 11;                            // 176 slabs per tile = 88 pairs = 11*8 = 11*16
+  static constexpr int NSLOT = XN_ == 64 ? 11 : 8;            // 176 slabs per tile = 88 pairs = 11*8 = 11*16 = 8*22
+                                                              // (XN = 96: the [96][128] fp32 d(PE) buffer needs the room)
   static constexpr int SLOT_BYTES = 16384;
   static_assert((PLAN.n_slabs / GROUP) % NSLOT == 0 && PLAN.n_slabs % GROUP == 0, "ring size must divide the slab-group count");
   static constexpr int OFF_RING = 0;
   static constexpr int OFF_C = NSLOT * SLOT_BYTES;
   static constexpr int OFF_GX = OFF_C + ((fused::C_TOTAL * 4 + 127) / 128) * 128;   // [64][128] fp32 skip-branch d(PE)
-  static constexpr int OFF_OUT = OFF_GX + 64 * 128 * 4;                               // [128][4]
+  static constexpr int OFF_OUT = OFF_GX + XN_ * 128 * 4;                              // [128][4]
   static constexpr int OFF_BAR = OFF_OUT + 128 * 4 * 4;
   static constexpr int SMEM_BYTES = OFF_BAR + (2 * NSLOT + 2) * 8 + 16;
+  static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB shared-memory limit");
 };
 
 struct Args {
   const float* rays; int ray_cols; const float* z; int64_t P; int S; int num_tiles;
+  const float* pts; const float* viewdirs;   // explicit 4-D points [P,4] + per-ray directions [N,3] (XN = 96)
   const float* g_raw;                  // [P,4]
   const uint8_t* wimg; const float* cbuf;
   const uint4* relu_bits;              // forward ReLU masks, 1 bit per activation (fused::Args::relu_bits)
   eng::ImgDump out_dz[8], out_dfeat, out_dzv;   // produced for the wgrad kernel
-  float* g_pts;                        // [P,3] d(loss)/d(point)
+  float* g_pts;                        // [P,3] d(loss)/d(point)   ([P,4] for 4-D points)
   float* g_vd;                         // [P,3] d(loss)/d(viewdir)
 };
 
-template <int NSPLIT>
+template <int NSPLIT, int XN = 64>
 __global__ void __launch_bounds__(320, 1) field_fused_dgrad_kernel(const __grid_constant__ Args a) {
-  using C = Cfg<NSPLIT>;
+  using C = Cfg<NSPLIT, XN>;
   constexpr bool SPLIT = NSPLIT == 3;
   extern __shared__ __align__(128) uint8_t dsm[];
   uint8_t* ringp = dsm + C::OFF_RING;
@@ -216,6 +227,47 @@ __global__ void __launch_bounds__(320, 1) field_fused_dgrad_kernel(const __grid_
         }
         tc::mbar_wait(acc_full, m & 1);
         tc::tc_fence_after();
+        if constexpr (XN == 96) {
+          if (s == 4 || s == 10) {
+            // ---- 96-wide d(PE) stages (4-D points): this warp owns columns [32 half, +32) and [64 + 16 half, +16)
+            uint32_t va[32], vb[16];
+            const int ca = half * 32, cb = 64 + half * 16;
+            tc::tmem_ld32(T_ACC + lane_base + ca, va);
+            tc::tmem_ld16(T_ACC + lane_base + cb, vb);
+            tc::tmem_ld_wait();
+            if (s == 4) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) gx_s[(ca + j) * TILE_M + row] = __uint_as_float(va[j]);
+#pragma unroll
+              for (int j = 0; j < 16; ++j) gx_s[(cb + j) * TILE_M + row] = __uint_as_float(vb[j]);
+              tc::tc_fence_before();
+              tc::mbar_arrive(a_ready);
+            } else {
+              float x[4] = {0.f, 0.f, 0.f, 0.f};
+              if (valid) {
+                const float4 q = *reinterpret_cast<const float4*>(a.pts + p * 4);
+                x[0] = q.x; x[1] = q.y; x[2] = q.z; x[3] = q.w;
+              }
+              float gx[4] = {0.f, 0.f, 0.f, 0.f};
+              auto contract = [&](int i, float gacc) {      // PE column i of [x(4), sin(2^f x)(4), cos(2^f x)(4), ...]
+                const float g = gacc + gx_s[i * TILE_M + row];
+                if (i < 4) gx[i] += g;
+                else if (i < 84) {
+                  const int f = (i - 4) >> 3, r = (i - 4) & 7, c = r & 3;
+                  const float fr = (float)(1 << f), arg = x[c] * fr;
+                  gx[c] += (r < 4) ? fr * cosf(arg) * g : -fr * sinf(arg) * g;
+                }
+              };
+#pragma unroll
+              for (int j = 0; j < 32; ++j) contract(ca + j, __uint_as_float(va[j]));
+#pragma unroll
+              for (int j = 0; j < 16; ++j) contract(cb + j, __uint_as_float(vb[j]));
+#pragma unroll
+              for (int c = 0; c < 4; ++c) atomicAdd(out_s + row * 4 + c, gx[c]);
+            }
+            continue;
+          }
+        }
         if (s == 4 || s == 10) {
           // ---- 64-wide d(PE) stages: this warp owns 32 columns
           uint32_t v[32];
@@ -262,8 +314,13 @@ __global__ void __launch_bounds__(320, 1) field_fused_dgrad_kernel(const __grid_
           tc::tmem_ld_wait();
           float vd[3] = {0.f, 0.f, 0.f}, gv[3] = {0.f, 0.f, 0.f};
           if (valid) {
-            const float* ry = a.rays + (p / a.S) * a.ray_cols;
-            vd[0] = ry[8]; vd[1] = ry[9]; vd[2] = ry[10];
+            if (XN == 96) {
+              const float* vv = a.viewdirs + (p / a.S) * 3;
+              vd[0] = vv[0]; vd[1] = vv[1]; vd[2] = vv[2];
+            } else {
+              const float* ry = a.rays + (p / a.S) * a.ray_cols;
+              vd[0] = ry[8]; vd[1] = ry[9]; vd[2] = ry[10];
+            }
           }
 #pragma unroll
           for (int i = 0; i < 27; ++i) {
@@ -305,7 +362,8 @@ __global__ void __launch_bounds__(320, 1) field_fused_dgrad_kernel(const __grid_
       tc::tc_fence_before();
       asm volatile("bar.sync 1, 256;" ::: "memory");
       if (half == 0 && valid) {
-        a.g_pts[p * 3] = out_s[row * 4]; a.g_pts[p * 3 + 1] = out_s[row * 4 + 1]; a.g_pts[p * 3 + 2] = out_s[row * 4 + 2];
+        if (XN == 96) *reinterpret_cast<float4*>(a.g_pts + p * 4) = *reinterpret_cast<const float4*>(out_s + row * 4);
+        else { a.g_pts[p * 3] = out_s[row * 4]; a.g_pts[p * 3 + 1] = out_s[row * 4 + 1]; a.g_pts[p * 3 + 2] = out_s[row * 4 + 2]; }
       }
       asm volatile("bar.sync 1, 256;" ::: "memory");
     }
@@ -342,6 +400,22 @@ __global__ void __launch_bounds__(128) reduce_pts_grad_kernel(const float* __res
       if (col < ray_cols) d_rays[r * ray_cols + col] += acc[k];
     }
   }
+}
+
+// g_viewdirs[r, 0:3] += sum_s g_vd[r*S + s]   (explicit-point form: d(pts) stays per sample)
+__global__ void __launch_bounds__(128) reduce_vd_grad_kernel(const float* __restrict__ g_vd, int64_t N, int S,
+                                                             float* __restrict__ g_viewdirs) {
+  const int lane = threadIdx.x & 31;
+  const int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (r >= N) return;
+  float acc[3] = {0.f, 0.f, 0.f};
+  for (int s = lane; s < S; s += 32) {
+    const int64_t p = r * S + s;
+    acc[0] += g_vd[p * 3]; acc[1] += g_vd[p * 3 + 1]; acc[2] += g_vd[p * 3 + 2];
+  }
+#pragma unroll
+  for (int k = 0; k < 3; ++k) acc[k] = warp_sum(acc[k]);
+  if (lane == 0) { g_viewdirs[r * 3] += acc[0]; g_viewdirs[r * 3 + 1] += acc[1]; g_viewdirs[r * 3 + 2] += acc[2]; }
 }
 
 }  // namespace dgrad

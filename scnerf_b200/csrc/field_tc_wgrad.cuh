@@ -50,7 +50,7 @@ struct Args {
 
 template <int NSPLIT> struct Cfg {
   static constexpr int NH = NSPLIT == 3 ? 2 : 1;
-  static constexpr int SLOT_BYTES = 36864 / (NSPLIT == 3 ? 1 : 2);   // worst job: 2 x 256 + 64 features
+  static constexpr int SLOT_BYTES = 38912 / (NSPLIT == 3 ? 1 : 2);   // worst job: 2 x 256 + 96 features (4-D points; 64 for 3-D)
   static constexpr int NSLOT = NSPLIT == 3 ? 5 : 10;
   static constexpr int OFF_BAR = NSLOT * SLOT_BYTES;
   static constexpr int SMEM_BYTES = OFF_BAR + (2 * NSLOT + 1) * 8 + 16;

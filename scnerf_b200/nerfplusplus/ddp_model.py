@@ -81,15 +81,15 @@ class _NerfNetFn(torch.autograd.Function):
         _lib.check(lib.scnerf_pp_composite_fg_fwd(_lib.ptr(raw_fg), _lib.ptr(fz), _lib.ptr(zmax), _lib.ptr(d), N, Sf,
                                                   _lib.ptr(fg_w), _lib.ptr(fg_rgb), _lib.ptr(fg_depth), _lib.ptr(lam), st),
                    "pp_composite_fg")
-        # ---- background (fp32 CUDA-core field: 4-D points)
+        # ---- background (4-D points: its own tensor-core slab plans, or the fp32 CUDA-core kernels)
         pts4 = E(N, Sb, 4)
         _lib.check(lib.scnerf_pp_bg_points_fwd(_lib.ptr(o), _lib.ptr(d), _lib.ptr(bz), N, Sb, _lib.ptr(pts4), None, st),
                    "pp_bg_points")
         vd = rays[:, 8:11].contiguous()
-        nbb = lib.scnerf_field_train_workspace_bytes(m_bg, N, Sb, 0)
+        nbb = lib.scnerf_field_train_workspace_bytes(m_bg, N, Sb, prec)
         ws_bg = torch.empty(nbb, device=dev, dtype=torch.uint8)
         raw_bg = E(N, Sb, 4)
-        _lib.check(lib.scnerf_field_train_fwd(m_bg, None, 0, None, _lib.ptr(pts4), _lib.ptr(vd), N, Sb, _lib.ptr(raw_bg), 0,
+        _lib.check(lib.scnerf_field_train_fwd(m_bg, None, 0, None, _lib.ptr(pts4), _lib.ptr(vd), N, Sb, _lib.ptr(raw_bg), prec,
                                               _lib.ptr(ws_bg), nbb, st), "field_train_fwd(bg)")
         bg_w, bg_rgb, bg_depth, rgb = E(N, Sb), E(N, 3), E(N), E(N, 3)
         _lib.check(lib.scnerf_pp_composite_bg_fwd(_lib.ptr(raw_bg), _lib.ptr(bz), _lib.ptr(lam), _lib.ptr(fg_rgb), N, Sb,
@@ -125,7 +125,7 @@ class _NerfNetFn(torch.autograd.Function):
                                                   _lib.ptr(d_raw_bg), _lib.ptr(d_lam), st), "pp_composite_bg_bwd")
         d_pts4, d_vd = E(N, Sb, 4), Z(N, 3)
         _lib.check(lib.scnerf_field_train_bwd(m_bg, gm_bg, None, 0, None, _lib.ptr(pts4), _lib.ptr(vd), N, Sb,
-                                              _lib.ptr(d_raw_bg), None, None, _lib.ptr(d_pts4), _lib.ptr(d_vd), 0,
+                                              _lib.ptr(d_raw_bg), None, None, _lib.ptr(d_pts4), _lib.ptr(d_vd), prec,
                                               _lib.ptr(ws_bg), ws_bg.numel(), st), "field_train_bwd(bg)")
         g_o, g_d = Z(N, 3), Z(N, 3)
         _lib.check(lib.scnerf_pp_bg_points_bwd(_lib.ptr(o), _lib.ptr(d), _lib.ptr(bz), _lib.ptr(d_pts4), N, Sb,
@@ -161,8 +161,7 @@ class NerfNet(nn.Module):
         self.bg_embedder_viewdir = Embedder(3, args.max_freq_log2_viewdirs - 1, args.max_freq_log2_viewdirs)
         self.bg_net = MLPNet(D=args.netdepth, W=args.netwidth, input_ch=self.bg_embedder_position.out_dim,
                              input_ch_viewdirs=self.bg_embedder_viewdir.out_dim, use_viewdirs=args.use_viewdirs)
-        # precision of the FOREGROUND field ("fp32" | "bf16x3" | "bf16"); the background field (4-D points)
-        # runs on the fp32 CUDA-core kernels
+        # "fp32" (CUDA cores) | "bf16x3" (tcgen05, split-bf16, parity-grade) | "bf16" (tcgen05, single pass)
         self.precision = precision or DEFAULT_PRECISION
 
     def forward(self, ray_o, ray_d, fg_z_max, fg_z_vals, bg_z_vals):
