@@ -9,6 +9,7 @@
 #include "field_simt.cuh"
 #include "tc_prims.cuh"
 #include "field_tc_fused.cuh"
+#include "field_tc_fwd_pipe.cuh"
 #include "field_tc_dgrad.cuh"
 #include "field_tc_wgrad.cuh"
 
@@ -139,6 +140,84 @@ __global__ void __launch_bounds__(128) tc_selftest_kernel(const uint8_t* __restr
 __global__ void __launch_bounds__(128) tc_mma_bench_kernel(int mode, int iters, long long* out) {
   extern __shared__ __align__(1024) uint8_t tc_smem[];
   __shared__ __align__(8) uint64_t bar;
+  __shared__ __align__(8) uint64_t fbar[8];
+  __shared__ uint32_t tmem_base_s;
+  __shared__ volatile int done_flag;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  if (tid == 0) {
+    tc::mbar_init(&bar, 1);
+    for (int i = 0; i < 8; ++i) tc::mbar_init(&fbar[i], 1);
+    done_flag = 0;
+    tc::fence_mbar_init();
+  }
+  for (int i = tid; i < 32768 / 4; i += 128) reinterpret_cast<uint32_t*>(tc_smem)[i] = 0x3c003c00u;
+  tc::fence_proxy_async();
+  __syncthreads();
+  if (warp == 0) tc::tmem_alloc(&tmem_base_s, 512);
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem = tmem_base_s;
+  // modes 4..7: N = 128 half-slabs (the N-split pipeline's MMA shape).  4: TS only.  5: the split-bf16
+  // triple TS(hi,Bhi) / SS(lo in smem,Bhi) / TS(hi,Blo).  6: 5 + a concurrent bulk-copy refill stream of
+  // 8 KB per triple (8 copies in flight) from the global scratch behind out[gridDim.x].  7: 4 + refill 4 KB/MMA.
+  if (tid == 32 && (mode == 6 || mode == 7)) {
+    const uint8_t* gsrc = reinterpret_cast<const uint8_t*>(out + ((gridDim.x + 1) & ~1u));
+    uint32_t ph = 0;
+    const uint32_t bytes = 8192;
+    for (int i = 0; i < 8; ++i) {
+      tc::mbar_arrive_expect_tx(&fbar[i], bytes);
+      tc::bulk_g2s(tc_smem + 32768 + i * 8192, gsrc + i * 8192, bytes, &fbar[i]);
+    }
+    while (!done_flag) {
+      for (int i = 0; i < 8; ++i) {
+        tc::mbar_wait(&fbar[i], ph);
+        tc::mbar_arrive_expect_tx(&fbar[i], bytes);
+        tc::bulk_g2s(tc_smem + 32768 + i * 8192, gsrc + i * 8192, bytes, &fbar[i]);
+      }
+      ph ^= 1u;
+    }
+    for (int i = 0; i < 8; ++i) tc::mbar_wait(&fbar[i], ph);
+  }
+  if (tid == 0) {
+    const uint32_t sa = tc::smem_u32(tc_smem), sb = sa + 16384;
+    const uint32_t idk = tc::idesc_bf16_f32(128, 256);
+    const uint32_t idh = tc::idesc_bf16_f32(128, 128);
+    const uint32_t idmn = idk | (1u << 15) | (1u << 16), idamn = idk | (1u << 15);
+    const long long t0 = clock64();
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        if (mode == 0) tc::mma_ss(tmem, eng::desc_at<2048, 128>(sa), eng::desc_at<4096, 128>(sb), idk, 1);
+        else if (mode == 1) tc::mma_ts(tmem, tmem + 256 + (j & 7) * 8, eng::desc_at<4096, 128>(sb), idk, 1);
+        else if (mode == 2) tc::mma_ss(tmem, eng::desc_at<128, 256>(sa), eng::desc_at<128, 256>(sb), idmn, 1);
+        else if (mode == 3) tc::mma_ss(tmem, eng::desc_at<128, 256>(sa), eng::desc_at<4096, 128>(sb), idamn, 1);
+        else if (mode == 4 || mode == 7) tc::mma_ts(tmem + (j & 1) * 128, tmem + 256 + (j & 7) * 8, eng::desc_at<2048, 128>(sb), idh, 1);
+        else {
+          const int r = j % 3;
+          if (r == 1) tc::mma_ss(tmem, eng::desc_at<2048, 128>(sa + (j & 3) * 4096), eng::desc_at<2048, 128>(sb), idh, 1);
+          else tc::mma_ts(tmem, tmem + 256 + (j & 7) * 8, eng::desc_at<2048, 128>(sb + (r == 2 ? 4096 : 0)), idh, 1);
+        }
+      }
+    }
+    tc::tc_commit(&bar);
+    tc::mbar_wait(&bar, 0);
+    const long long t1 = clock64();
+    out[blockIdx.x] = t1 - t0;
+    done_flag = 1;
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tc::tmem_dealloc(tmem, 512);
+}
+
+// Compile-time MMA-shape probe (the loop body is nothing but the MMAs): N = B rows, PAT 0: TS same accumulator,
+// 1: TS alternating accumulator halves, 2: SS, 3: TS/SS/TS triple (split-bf16 with the lo operand in smem),
+// 4: SS/TS alternating, 5: TS/TS/TS triple.
+template <int N, int PAT>
+__global__ void __launch_bounds__(128) tc_mma_probe_kernel(int iters, long long* out) {
+  extern __shared__ __align__(1024) uint8_t tc_smem[];
+  __shared__ __align__(8) uint64_t bar;
   __shared__ uint32_t tmem_base_s;
   const int tid = threadIdx.x, warp = tid >> 5;
   if (tid == 0) { tc::mbar_init(&bar, 1); tc::fence_mbar_init(); }
@@ -152,16 +231,19 @@ __global__ void __launch_bounds__(128) tc_mma_bench_kernel(int mode, int iters, 
   const uint32_t tmem = tmem_base_s;
   if (tid == 0) {
     const uint32_t sa = tc::smem_u32(tc_smem), sb = sa + 16384;
-    const uint32_t idk = tc::idesc_bf16_f32(128, 256);
-    const uint32_t idmn = idk | (1u << 15) | (1u << 16), idamn = idk | (1u << 15);
+    constexpr uint32_t idn = tc::idesc_bf16_f32(128, N);
     const long long t0 = clock64();
     for (int it = 0; it < iters; ++it) {
 #pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        if (mode == 0) tc::mma_ss(tmem, eng::desc_at<2048, 128>(sa), eng::desc_at<4096, 128>(sb), idk, 1);
-        else if (mode == 1) tc::mma_ts(tmem, tmem + 256 + (j & 7) * 8, eng::desc_at<4096, 128>(sb), idk, 1);
-        else if (mode == 2) tc::mma_ss(tmem, eng::desc_at<128, 256>(sa), eng::desc_at<128, 256>(sb), idmn, 1);
-        else tc::mma_ss(tmem, eng::desc_at<128, 256>(sa), eng::desc_at<4096, 128>(sb), idamn, 1);
+      for (int j = 0; j < 24; ++j) {
+        const uint64_t bd = eng::desc_at<N * 16, 128>(sb + (j & 1) * 8192);
+        const uint64_t ad = eng::desc_at<2048, 128>(sa + (j & 3) * 4096);
+        const uint32_t ta = tmem + 256 + (j & 7) * 8;
+        const uint32_t acc = tmem + ((PAT == 1 && (j & 1)) ? 128 : 0);
+        constexpr bool dummy = false; (void)dummy;
+        const bool ss = PAT == 2 || (PAT == 3 && j % 3 == 1) || (PAT == 4 && (j & 1) == 0);
+        if (ss) tc::mma_ss(acc, ad, bd, idn, 1);
+        else tc::mma_ts(acc, ta, bd, idn, 1);
       }
     }
     tc::tc_commit(&bar);
@@ -173,9 +255,36 @@ __global__ void __launch_bounds__(128) tc_mma_bench_kernel(int mode, int iters, 
   __syncthreads();
   if (warp == 0) tc::tmem_dealloc(tmem, 512);
 }
+template <int N, int PAT>
+inline int tc_mma_probe_launch(int iters, long long* out, int nblocks, void* stream) {
+  SCNERF_LAUNCH((tc_mma_probe_kernel<N, PAT>), nblocks, 128, 32768, stream, iters, out);
+  return 0;
+}
+template <int N>
+inline int tc_mma_probe_n(int pat, int iters, long long* out, int nblocks, void* stream) {
+  switch (pat) {
+    case 0: return tc_mma_probe_launch<N, 0>(iters, out, nblocks, stream);
+    case 1: return tc_mma_probe_launch<N, 1>(iters, out, nblocks, stream);
+    case 2: return tc_mma_probe_launch<N, 2>(iters, out, nblocks, stream);
+    case 3: return tc_mma_probe_launch<N, 3>(iters, out, nblocks, stream);
+    case 4: return tc_mma_probe_launch<N, 4>(iters, out, nblocks, stream);
+    default: return tc_mma_probe_launch<N, 5>(iters, out, nblocks, stream);
+  }
+}
+
 inline int tc_mma_bench(int mode, int iters, long long* out, int nblocks, void* stream) {
-  SCNERF_CUDA(cudaFuncSetAttribute(tc_mma_bench_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 32768));
-  SCNERF_LAUNCH(tc_mma_bench_kernel, nblocks, 128, 32768, stream, mode, iters, out);
+  if (mode >= 256) {      // mode = 256 + (N/8 << 4) + pattern  (24 MMAs per iteration)
+    const int n = ((mode - 256) >> 4) * 8, pat = mode & 15;
+    switch (n) {
+      case 256: return tc_mma_probe_n<256>(pat, iters, out, nblocks, stream);
+      case 128: return tc_mma_probe_n<128>(pat, iters, out, nblocks, stream);
+      case 64: return tc_mma_probe_n<64>(pat, iters, out, nblocks, stream);
+      case 32: return tc_mma_probe_n<32>(pat, iters, out, nblocks, stream);
+      default: return fail(SCNERF_ERR_ARG, "mma probe: N must be 256/128/64/32");
+    }
+  }
+  SCNERF_CUDA(cudaFuncSetAttribute(tc_mma_bench_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 32768 + 65536));
+  SCNERF_LAUNCH(tc_mma_bench_kernel, nblocks, 128, 32768 + 65536, stream, mode, iters, out);
   return 0;
 }
 
@@ -245,6 +354,44 @@ inline int fwd_plan_init() {
   if (dev < 64) done[dev] = true;
   return 0;
 }
+// N-half pipelined forward (field_tc_fwd_pipe.cuh): on by default, SCNERF_FWD_PIPE=0 selects the serial kernel
+inline bool fwd_pipe_enabled() {
+  static int on = -1;
+  if (on < 0) { const char* e = getenv("SCNERF_FWD_PIPE"); on = e ? (atoi(e) != 0) : 1; }
+  return on != 0;
+}
+template <int XS = 4>
+inline const eng::Plan& pipe_plan_host() {
+  static eng::Plan P = fpipe::make_plan<3, XS>();   // (slab order, sizes and image offsets do not depend on NSPLIT)
+  return P;
+}
+inline int pipe_plan_init() {
+  static bool done[64] = {};
+  int dev = 0;
+  SCNERF_CUDA(cudaGetDevice(&dev));
+  if (dev < 64 && done[dev]) return 0;
+  const eng::Plan& P = pipe_plan_host<4>();
+  const eng::Plan& P6 = pipe_plan_host<6>();
+  static fused::PlanSrc S, S6;
+  fpipe::build_plansrc<4>(S);
+  fpipe::build_plansrc<6>(S6);
+  if (fused::plan_image_bytes(P, 3) > TC_IMG_BYTES || fused::plan_image_bytes(P6, 3) > TC_IMG_BYTES)
+    return fail(SCNERF_ERR_WORKSPACE, "TC_IMG_BYTES too small (pipelined forward)");
+  SCNERF_CUDA(cudaMemcpyToSymbol(fpipe::d_plan_pipe, &P, sizeof(P)));
+  SCNERF_CUDA(cudaMemcpyToSymbol(fpipe::d_plansrc_pipe, &S, sizeof(S)));
+  SCNERF_CUDA(cudaMemcpyToSymbol(fpipe::d_plan_pipe6, &P6, sizeof(P6)));
+  SCNERF_CUDA(cudaMemcpyToSymbol(fpipe::d_plansrc_pipe6, &S6, sizeof(S6)));
+  SCNERF_CUDA(cudaFuncSetAttribute((fpipe::field_fwd_pipe_kernel<1, 4>), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   fpipe::Cfg<1, 4>::SMEM_BYTES));
+  SCNERF_CUDA(cudaFuncSetAttribute((fpipe::field_fwd_pipe_kernel<3, 4>), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   fpipe::Cfg<3, 4>::SMEM_BYTES));
+  SCNERF_CUDA(cudaFuncSetAttribute((fpipe::field_fwd_pipe_kernel<1, 6>), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   fpipe::Cfg<1, 6>::SMEM_BYTES));
+  SCNERF_CUDA(cudaFuncSetAttribute((fpipe::field_fwd_pipe_kernel<3, 6>), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   fpipe::Cfg<3, 6>::SMEM_BYTES));
+  if (dev < 64) done[dev] = true;
+  return 0;
+}
 template <int XS = 4>
 inline const eng::Plan& fwd_plan_host() {
   static eng::Plan P = fused::make_fwd_plan<3, XS>();
@@ -300,11 +447,15 @@ inline int field_tc_fwd_impl(const scnerf_mlp& m, const float* rays, int ray_col
                              const FieldBufs& B, float* raw, void* stream, const TcFwdImages* imgs = nullptr) {
   using namespace fused;
   static_assert(C_TOTAL <= (int)TC_CBUF_FLOATS, "TC_CBUF_FLOATS too small");
-  int rc = fwd_plan_init();
+  const bool pipe = fwd_pipe_enabled();
+  int rc = pipe ? pipe_plan_init() : fwd_plan_init();
   if (rc) return rc;
-  const eng::Plan& P = fwd_plan_host<XS>();
   PackSrc src = make_pack_src(m);
-  SCNERF_LAUNCH((pack_fwd_kernel<NSPLIT, XS>), dim3(2, (unsigned)P.n_slabs), 256, 0, stream, src, B.tc_img);
+  if (pipe) {
+    SCNERF_LAUNCH((fpipe::pack_pipe_kernel<NSPLIT, XS>), dim3(1, (unsigned)pipe_plan_host<XS>().n_slabs), 256, 0, stream, src, B.tc_img);
+  } else {
+    SCNERF_LAUNCH((pack_fwd_kernel<NSPLIT, XS>), dim3(2, (unsigned)fwd_plan_host<XS>().n_slabs), 256, 0, stream, src, B.tc_img);
+  }
   SCNERF_LAUNCH(pack_consts_kernel, (unsigned)cdiv(C_TOTAL, 256), 256, 0, stream, src, B.tc_cbuf);
   Args a{};
   a.rays = rays; a.ray_cols = ray_cols; a.z = z; a.pts = pts; a.viewdirs = viewdirs;
@@ -328,7 +479,8 @@ inline int field_tc_fwd_impl(const scnerf_mlp& m, const float* rays, int ray_col
   }
   a.dbg = tc_dbg_ptr(); a.dbg_tiles = tc_dbg_tiles();
   int grid = std::min(device_sm_count(), a.num_tiles);
-  SCNERF_LAUNCH((field_fused_fwd_kernel<NSPLIT, XS>), grid, 320, (Cfg<NSPLIT, XS>::SMEM_BYTES), stream, a);
+  if (pipe) SCNERF_LAUNCH((fpipe::field_fwd_pipe_kernel<NSPLIT, XS>), grid, 320, (fpipe::Cfg<NSPLIT, XS>::SMEM_BYTES), stream, a);
+  else SCNERF_LAUNCH((field_fused_fwd_kernel<NSPLIT, XS>), grid, 320, (Cfg<NSPLIT, XS>::SMEM_BYTES), stream, a);
   return 0;
 }
 

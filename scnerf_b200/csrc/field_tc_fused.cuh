@@ -60,7 +60,7 @@ struct SrcDef {
   uint8_t wsel;      // index into PackSrc.w / .b
   uint8_t kind;      // 0: B[n][k] = W[n][col0+k]   1: B[n][k] = W[row0+k][col0+n]   2: B[n][0] = b[n]
   uint16_t row0, col0, valid_k, valid_n;
-  uint16_t pad;
+  uint16_t pad;      // kinds 0 and 2: first output row (N-half plans), 0 otherwise
 };
 struct PlanSrc { SrcDef s[eng::MAX_SLABS]; };
 struct PackSrc {
@@ -152,9 +152,9 @@ __device__ __forceinline__ void pack_slab_impl(const eng::SlabDef& d, const SrcD
   for (int e = 0; e < 8; ++e) {
     const int k = chunk * 8 + e;
     float x = 0.f;
-    if (q.kind == 0) { if (k < q.valid_k && row < q.valid_n) x = src.w[q.wsel][(int64_t)row * src.ld[q.wsel] + q.col0 + k]; }
+    if (q.kind == 0) { if (k < q.valid_k && row < q.valid_n) x = src.w[q.wsel][(int64_t)(q.pad + row) * src.ld[q.wsel] + q.col0 + k]; }
     else if (q.kind == 1) { if (k < q.valid_k && row < q.valid_n) x = src.w[q.wsel][(int64_t)(q.row0 + k) * src.ld[q.wsel] + q.col0 + row]; }
-    else if (q.kind == 2) { if (k == 0 && row < q.valid_n) x = src.b[q.wsel][row]; }
+    else if (q.kind == 2) { if (k == 0 && row < q.valid_n) x = src.b[q.wsel][q.pad + row]; }
     v[e] = x;
   }
   uint32_t h[4], l[4];

@@ -19,10 +19,10 @@ namespace scnerf {
 namespace eng {
 
 constexpr int TILE_M = 128;
-constexpr int MAX_SLABS = 192;
+constexpr int MAX_SLABS = 352;   // the N-half pipelined forward issues 336 half-slabs per tile
 
-enum : uint8_t { A_TMEM = 0, A_SMEM = 1 };
-enum : uint8_t { F_ZERO_ACC = 1, F_STAGE_END = 2, F_HI_ONLY_A = 4, F_STAGE_BEGIN = 8 };
+enum : uint8_t { A_TMEM = 0, A_SMEM = 1, A_MIX = 2 };   // A_MIX: hi in TMEM (a_off), lo in shared memory (a_lo_delta)
+enum : uint8_t { F_ZERO_ACC = 1, F_STAGE_END = 2, F_HI_ONLY_A = 4, F_STAGE_BEGIN = 8, F_WAIT_A2 = 16 };
 
 struct SlabDef {
   uint16_t n;          // rows of the B slab (= GEMM N), multiple of 16
@@ -33,7 +33,7 @@ struct SlabDef {
   uint8_t a_kind;
   uint8_t flags;
   uint8_t stage;
-  uint8_t pad;
+  uint8_t pad;         // pipelined plans: which accumulator-half barrier F_STAGE_END commits to
   uint32_t img_off;    // byte offset of the slab in the NSPLIT==1 weight image (x2 for NSPLIT==3)
 };
 

@@ -1,5 +1,6 @@
 """Print the in-kernel timeline of the fused forward (CTA 0, first tiles)."""
 import sys, os
+os.environ.setdefault("SCNERF_FWD_PIPE", "0")   # this tool reads the serial kernel's 4-stamp layout
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch, numpy as np
 from tests.util import build_modules

@@ -1,0 +1,33 @@
+"""In-kernel timeline of the N-half pipelined fused forward (CTA 0, first tiles): [tile][stage][8] clock64 stamps
+0 MMA passed a1, 1 MMA passed a2, 2 MMA committed h0, 3 MMA committed h1,
+4 epilogue saw accf0, 5 epilogue arrived a1, 6 epilogue saw accf1, 7 epilogue arrived a2."""
+import sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch, numpy as np
+from tests.util import build_modules
+from scnerf_b200.create_nerf import run_network
+from scnerf_b200 import _lib
+prec = sys.argv[1] if len(sys.argv) > 1 else "bf16x3"
+lib = _lib.load()
+mods = build_modules(0, "cuda:0")
+N = 4096
+pts = torch.rand(N, 192, 3, device="cuda") * 2 - 1
+vd = torch.nn.functional.normalize(torch.randn(N, 3, device="cuda"), dim=-1)
+run_network(pts, vd, mods["fine"], None, None, precision=prec)
+T = 4
+buf = torch.zeros(T, 10, 16, dtype=torch.int64, device="cuda")
+lib.scnerf_debug_timeline(_lib.ptr(buf), T)
+run_network(pts, vd, mods["fine"], None, None, precision=prec)
+torch.cuda.synchronize()
+lib.scnerf_debug_timeline(None, 0)
+b = buf.cpu().numpy()
+t0 = b[b > 0].min()
+print(prec, "stage: mma_a1 mma_a2 commit0 commit1 | epi_accf0 epi_a1 epi_accf1 epi_a2   (cycles from the first stamp)")
+for t in range(1, 3):
+    for s in range(10):
+        r = b[t, s] - t0
+        print(f"tile {t} stage {s}: " + " ".join(f"{int(x):8d}" for x in r[:4]) + " | " + " ".join(f"{int(x):8d}" for x in r[4:]) +
+              f" | mma h0 {int(r[2] - r[0]):6d} h1 {int(r[3] - r[2]):6d} epi0 {int(r[5] - r[4]):6d} epi1 {int(r[7] - r[6]):6d}"
+              f" | epi0: ld {int(r[8] - r[4]):5d} cvt+st {int(r[9] - r[8]):5d} fence {int(r[10] - r[9]):5d}"
+              f" | epi1: ld {int(r[12] - r[6]):5d} cvt+st {int(r[13] - r[12]):5d} fence {int(r[14] - r[13]):5d}")
+    print(f"tile {t} total cycles: {b[t + 1, 0, 0] - b[t, 0, 0]}")

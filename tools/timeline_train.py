@@ -1,5 +1,6 @@
 """In-kernel timeline of the fused forward in TRAINING mode (image dumps on): last fwd launch of a step = fine pass."""
 import sys, os
+os.environ.setdefault("SCNERF_FWD_PIPE", "0")   # this tool reads the serial kernel's 4-stamp layout
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from tests.util import build_modules
