@@ -11,6 +11,7 @@
 #include "field_tc_fused.cuh"
 #include "field_tc_fwd_pipe.cuh"
 #include "field_tc_dgrad.cuh"
+#include "field_tc_dgrad_pipe.cuh"
 #include "field_tc_wgrad.cuh"
 
 namespace scnerf {
@@ -535,6 +536,34 @@ inline int bwd_plan_init() {
   if (dev < 64) done[dev] = true;
   return 0;
 }
+// N-half pipelined dgrad (field_tc_dgrad_pipe.cuh, 3-D points): on by default, SCNERF_DGRAD_PIPE=0 selects the serial kernel
+inline bool dgrad_pipe_enabled() {
+  static int on = -1;
+  if (on < 0) { const char* e = getenv("SCNERF_DGRAD_PIPE"); on = e ? (atoi(e) != 0) : 1; }
+  return on != 0;
+}
+inline const eng::Plan& dpipe_plan_host() {
+  static eng::Plan P = dpipe::make_plan();
+  return P;
+}
+inline int dpipe_plan_init() {
+  static bool done[64] = {};
+  int dev = 0;
+  SCNERF_CUDA(cudaGetDevice(&dev));
+  if (dev < 64 && done[dev]) return 0;
+  const eng::Plan& P = dpipe_plan_host();
+  static fused::PlanSrc S;
+  dpipe::build_plansrc(S);
+  if (fused::plan_image_bytes(P, 3) > TC_IMG_BYTES) return fail(SCNERF_ERR_WORKSPACE, "TC_IMG_BYTES too small (pipelined dgrad)");
+  SCNERF_CUDA(cudaMemcpyToSymbol(dpipe::d_plan_dpipe, &P, sizeof(P)));
+  SCNERF_CUDA(cudaMemcpyToSymbol(dpipe::d_plansrc_dpipe, &S, sizeof(S)));
+  SCNERF_CUDA(cudaFuncSetAttribute(dpipe::field_dgrad_pipe_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   dpipe::Cfg<1>::SMEM_BYTES));
+  SCNERF_CUDA(cudaFuncSetAttribute(dpipe::field_dgrad_pipe_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   dpipe::Cfg<3>::SMEM_BYTES));
+  if (dev < 64) done[dev] = true;
+  return 0;
+}
 inline int dgrad_n_slabs() {      // the same for both d(PE) widths (only N of two stages differs)
   static int n = -1;
   if (n < 0) { static eng::Plan P = dgrad::make_plan<64>(); n = P.n_slabs; }
@@ -561,7 +590,14 @@ inline int field_tc_bwd_impl(const scnerf_mlp& m, const scnerf_mlp& g, const flo
   const int64_t P = N * S;
   const int T = (int)cdiv(P, 128);
   fused::PackSrc src = make_pack_src(m);
-  SCNERF_LAUNCH((dgrad::pack_dgrad_kernel<NSPLIT, XN>), dim3(2, (unsigned)dgrad_n_slabs()), 256, 0, stream, src, G.wimg);
+  const bool dp = XN == 64 && dgrad_pipe_enabled();
+  if (dp) {
+    rc = dpipe_plan_init();
+    if (rc) return rc;
+    SCNERF_LAUNCH((dpipe::pack_dpipe_kernel<NSPLIT>), dim3(1, (unsigned)dpipe_plan_host().n_slabs), 256, 0, stream, src, G.wimg);
+  } else {
+    SCNERF_LAUNCH((dgrad::pack_dgrad_kernel<NSPLIT, XN>), dim3(2, (unsigned)dgrad_n_slabs()), 256, 0, stream, src, G.wimg);
+  }
   SCNERF_LAUNCH(fused::pack_consts_kernel, (unsigned)cdiv(fused::C_TOTAL, 256), 256, 0, stream, src, B.tc_cbuf);
   dgrad::Args a{};
   a.rays = rays; a.ray_cols = ray_cols; a.z = z; a.P = P; a.S = S; a.num_tiles = T;
@@ -569,8 +605,10 @@ inline int field_tc_bwd_impl(const scnerf_mlp& m, const scnerf_mlp& g, const flo
   a.g_raw = g_raw; a.wimg = G.wimg; a.cbuf = B.tc_cbuf;
   for (int i = 0; i < 8; ++i) a.out_dz[i] = G.dz[i];
   a.relu_bits = I.relu_bits; a.out_dfeat = G.dfeat; a.out_dzv = G.dzv; a.g_pts = G.g_pts; a.g_vd = G.g_vd;
-  SCNERF_LAUNCH((dgrad::field_fused_dgrad_kernel<NSPLIT, XN>), std::min(device_sm_count(), T), 320,
-                (dgrad::Cfg<NSPLIT, XN>::SMEM_BYTES), stream, a);
+  if (dp) SCNERF_LAUNCH((dpipe::field_dgrad_pipe_kernel<NSPLIT>), std::min(device_sm_count(), T), 320,
+                        (dpipe::Cfg<NSPLIT>::SMEM_BYTES), stream, a);
+  else SCNERF_LAUNCH((dgrad::field_fused_dgrad_kernel<NSPLIT, XN>), std::min(device_sm_count(), T), 320,
+                     (dgrad::Cfg<NSPLIT, XN>::SMEM_BYTES), stream, a);
   if (XN == 96) {
     if (d_viewdirs)
       SCNERF_LAUNCH(dgrad::reduce_vd_grad_kernel, (unsigned)cdiv(N, 4), 128, 0, stream, G.g_vd, N, S, d_viewdirs);

@@ -254,8 +254,10 @@ __global__ void __launch_bounds__(320, 1) field_fused_dgrad_kernel(const __grid_
                 if (i < 4) gx[i] += g;
                 else if (i < 84) {
                   const int f = (i - 4) >> 3, r = (i - 4) & 7, c = r & 3;
-                  const float fr = (float)(1 << f), arg = x[c] * fr;
-                  gx[c] += (r < 4) ? fr * cosf(arg) * g : -fr * sinf(arg) * g;
+                  const float fr = (float)(1 << f);
+                  float sv, cv;
+                  fused::sincos_cw(x[c] * fr, sv, cv);     // same evaluation as the forward's PE
+                  gx[c] += (r < 4) ? fr * cv * g : -fr * sv * g;
                 }
               };
 #pragma unroll
@@ -296,8 +298,10 @@ __global__ void __launch_bounds__(320, 1) field_fused_dgrad_kernel(const __grid_
               if (i < 3) gx[i] += g;
               else if (i < 63) {
                 const int f = (i - 3) / 6, r = (i - 3) % 6, c = r % 3;
-                const float fr = (float)(1 << f), arg = x[c] * fr;
-                gx[c] += (r < 3) ? fr * cosf(arg) * g : -fr * sinf(arg) * g;
+                const float fr = (float)(1 << f);
+                float sv, cv;
+                fused::sincos_cw(x[c] * fr, sv, cv);       // same evaluation as the forward's PE
+                gx[c] += (r < 3) ? fr * cv * g : -fr * sv * g;
               }
             }
             atomicAdd(out_s + row * 4 + 0, gx[0]);
@@ -328,8 +332,10 @@ __global__ void __launch_bounds__(320, 1) field_fused_dgrad_kernel(const __grid_
             if (i < 3) gv[i] += g;
             else {
               const int f = (i - 3) / 6, r = (i - 3) % 6, c = r % 3;
-              const float fr = (float)(1 << f), arg = vd[c] * fr;
-              gv[c] += (r < 3) ? fr * cosf(arg) * g : -fr * sinf(arg) * g;
+              const float fr = (float)(1 << f);
+              float sv, cv;
+              fused::sincos_cw(vd[c] * fr, sv, cv);
+              gv[c] += (r < 3) ? fr * cv * g : -fr * sv * g;
             }
           }
           if (valid) { a.g_vd[p * 3] = gv[0]; a.g_vd[p * 3 + 1] = gv[1]; a.g_vd[p * 3 + 2] = gv[2]; }

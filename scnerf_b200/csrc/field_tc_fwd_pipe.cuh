@@ -20,8 +20,10 @@
 //
 // Barriers (all count their phases per stage, 10 per tile, so parity = stage & 1):
 //   accf[h]  MMA -> epilogue : N-half h of the stage is complete          (tcgen05.commit)
-//   a1       epilogue -> MMA : acc0 drained, A columns 0..127 written     (256 arrivals)
-//   a2       epilogue -> MMA : acc1 drained, A columns 128..255 written   (256 arrivals)
+//   aq[0..3] epilogue -> MMA : the accumulator half is drained and A columns [64q, 64q+64) are written
+//                              (256 arrivals each).  The epilogue hands the next layer's operand over in
+//                              64-column quarters, so the K-slabs that read quarter q start while the
+//                              quarters behind it are still being converted.
 //
 // Reference: NeRF/run_nerf_helpers.py:24-72,105-128, NeRF/create_nerf.py:18-32.
 #pragma once
@@ -83,8 +85,10 @@ struct PlanFiller {
     e.n = (uint16_t)nh; e.acc_col = (uint16_t)(h * 128); e.stage = (uint8_t)s; e.pad = (uint8_t)h; e.img_off = off;
     uint8_t fl = 0;
     if (first) fl |= eng::F_ZERO_ACC;
-    if (first && h == 0) fl |= eng::F_STAGE_BEGIN;                       // wait a1
-    if (h == 0 && ((s == 0 && first) || (kind == 3 && j == 8))) fl |= eng::F_WAIT_A2;
+    if (first && h == 0) fl |= eng::F_STAGE_BEGIN;                       // wait aq[0] (acc0 drained)
+    if (h == 0 && ((s == 0 && first) || (kind == 3 && j == 4))) fl |= eng::F_WAIT_Q1;
+    if (h == 0 && ((s == 0 && first) || (kind == 3 && j == 8))) fl |= eng::F_WAIT_Q2;    // (acc1 drained)
+    if (h == 0 && ((s == 0 && first) || (kind == 3 && j == 12))) fl |= eng::F_WAIT_Q3;
     if (last) fl |= eng::F_STAGE_END;                                    // commit accf[h]
     if (kind == 0) { e.a_kind = eng::A_SMEM; e.a_off = L::ONES / 16; fl |= eng::F_HI_ONLY_A; }
     else if (kind == 1) { e.a_kind = eng::A_SMEM; e.a_off = (uint16_t)((L::XHI + j * 4096) / 16); e.a_lo_delta = (L::XLO - L::XHI) / 16; }
@@ -150,18 +154,18 @@ template <int NSPLIT_, int XS_ = 4> struct Cfg {
   static constexpr int OFF_C = OFF_LO + LO_BYTES;
   static constexpr int OFF_OUT = OFF_C + ((C_TOTAL * 4 + 127) / 128) * 128;   // [128][4] head partial sums
   static constexpr int OFF_BAR = OFF_OUT + 128 * 4 * 4;
-  static constexpr int SMEM_BYTES = OFF_BAR + (2 * NSLOT + 4) * 8 + 16;
+  static constexpr int SMEM_BYTES = OFF_BAR + (2 * NSLOT + 6) * 8 + 16;
   static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB shared-memory limit");
 };
 
 struct PCtx {
   eng::Ctx e;                  // ring / full / empty / tmem_acc / tmem_ahi (= A base) / smem_a / policies
   uint32_t accf_addr;          // accf[0], accf[1] 8 bytes apart
-  uint32_t a1_addr, a2_addr;
+  uint32_t aq_addr;            // aq[0..3] 8 bytes apart
   uint32_t smem_lo;            // shared address of the lo area
   long long* dbg; int dbg_tiles;
 };
-// timeline: [tile][stage][16] (8 + 4h + {0 loads done, 1 converted + stores issued, 2 fences done}; rest unused): 0 MMA passed a1, 1 MMA passed a2, 2 MMA committed h0, 3 MMA committed h1,
+// timeline: [tile][stage][16] (8 + 4h + {0 loads done, 1 quarter 2h handed over, 2 quarter 2h+1 handed over}; rest unused): 0 MMA passed a1, 1 MMA passed a2, 2 MMA committed h0, 3 MMA committed h1,
 //                             4 epilogue saw accf0, 5 epilogue arrived a1, 6 epilogue saw accf1, 7 epilogue arrived a2
 __device__ __forceinline__ void stamp(const PCtx& c, int tile_iter, int stage, int slot) {
   if (c.dbg != nullptr && blockIdx.x == 0 && tile_iter < c.dbg_tiles)
@@ -176,16 +180,24 @@ __device__ __forceinline__ void mma_step(const PCtx& c, uint32_t tp, int tile_it
   constexpr int idx = G % K::NSLOT, wrap = G / K::NSLOT;
   constexpr bool wraps_odd = (((K::PLAN.n_slabs / K::GROUP) / K::NSLOT) & 1) != 0;
   constexpr uint32_t in_slot = eng::group_bytes<K>(G * K::GROUP, I);
-  static_assert((NSTAGE & 1) == 0, "stage parity assumes an even number of stages per tile");
+  static_assert((K::PLAN.n_stages & 1) == 0, "stage parity assumes an even number of stages per tile");
   if constexpr ((d.flags & eng::F_STAGE_BEGIN) != 0) {
-    eng::mbar_wait_a(c.a1_addr, (uint32_t)(d.stage & 1));
+    eng::mbar_wait_a(c.aq_addr, (uint32_t)(d.stage & 1));
     tc::tc_fence_after();
     stamp(c, tile_iter, d.stage, 0);
   }
-  if constexpr ((d.flags & eng::F_WAIT_A2) != 0) {
-    eng::mbar_wait_a(c.a2_addr, (uint32_t)(d.stage & 1));
+  if constexpr ((d.flags & eng::F_WAIT_Q1) != 0) {
+    eng::mbar_wait_a(c.aq_addr + 8, (uint32_t)(d.stage & 1));
+    tc::tc_fence_after();
+  }
+  if constexpr ((d.flags & eng::F_WAIT_Q2) != 0) {
+    eng::mbar_wait_a(c.aq_addr + 16, (uint32_t)(d.stage & 1));
     tc::tc_fence_after();
     stamp(c, tile_iter, d.stage, 1);
+  }
+  if constexpr ((d.flags & eng::F_WAIT_Q3) != 0) {
+    eng::mbar_wait_a(c.aq_addr + 24, (uint32_t)(d.stage & 1));
+    tc::tc_fence_after();
   }
   if constexpr (I % K::GROUP == 0) {
     eng::mbar_wait_a(c.e.full_addr + idx * 8, (uint32_t)(wrap & 1) ^ (wraps_odd ? tp : 0u));
@@ -217,6 +229,7 @@ __device__ __forceinline__ void mma_step(const PCtx& c, uint32_t tp, int tile_it
   if constexpr (I % K::GROUP == K::GROUP - 1) eng::commit_a(c.e.empty_addr + idx * 8);
   if constexpr ((d.flags & eng::F_STAGE_END) != 0) {
     eng::commit_a(c.accf_addr + d.pad * 8);
+    if constexpr ((d.flags & eng::F_COMMIT_BOTH) != 0) eng::commit_a(c.accf_addr + (d.pad ^ 1) * 8);   // stage without a second N-half
     stamp(c, tile_iter, d.stage, 2 + d.pad);
   }
 }
@@ -233,7 +246,8 @@ __device__ __forceinline__ void mma_loop(const PCtx& c, int num_tiles) {
 }
 
 // Epilogue of N-half H of stage S for this warp's columns (compile-time stage parameters).
-// Warp `half` (0/1) owns columns [H*NH + half*NH/2, +NH/2) of the layer output, NH = N/2.
+// 256-wide stages: the N-half is handed over as two 64-column quarters; chunk cc of warp `half` (0/1) is
+// columns [H*128 + cc*64 + half*32, +32).  View layer (N-halves of 64): one chunk, [H*64 + half*32, +32).
 template <int NSPLIT, int S, int H>
 __device__ __forceinline__ void epi_half(const Args& a, const float* cst, const PCtx& c, uint8_t* lo_area,
                                          uint32_t lane_base, int half, int row, int tile, int64_t p, bool valid,
@@ -241,19 +255,20 @@ __device__ __forceinline__ void epi_half(const Args& a, const float* cst, const 
   constexpr bool SPLIT = NSPLIT == 3;
   constexpr StageDef d = stage_def(S);
   constexpr int NH = d.N / 2, NW = NH / 2, nchunk = NW / 32;   // 128/64/2 (256-wide) or 64/32/1 (view layer)
-  const int cw = half * NW;                 // first column inside the N-half
+  constexpr int CSTEP = nchunk == 2 ? 64 : 32;   // column distance between this warp's chunks
+  const int cw = half * 32;                 // first column inside the N-half (chunk 0)
   const int cbase = H * NH + cw;            // first layer-output column
   eng::mbar_wait_a(c.accf_addr + H * 8, (uint32_t)(S & 1));
   tc::tc_fence_after();
   if (threadIdx.x == 64) stamp(c, tile_iter, S, 4 + 2 * H);
   uint32_t v[nchunk][32];
 #pragma unroll
-  for (int cc = 0; cc < nchunk; ++cc) tc::tmem_ld32(c.e.tmem_acc + lane_base + H * 128 + cw + cc * 32, v[cc]);
+  for (int cc = 0; cc < nchunk; ++cc) tc::tmem_ld32(c.e.tmem_acc + lane_base + H * 128 + cw + cc * CSTEP, v[cc]);
   tc::tmem_ld_wait();
   if (threadIdx.x == 64) stamp(c, tile_iter, S, 8 + 4 * H);
 #pragma unroll
   for (int cc = 0; cc < nchunk; ++cc) {
-    const int cu = cbase + cc * 32;         // layer-output column of v[cc][0]
+    const int cu = cbase + cc * CSTEP;      // layer-output column of v[cc][0]
     float f[32];
 #pragma unroll
     for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[cc][j]);
@@ -280,7 +295,7 @@ __device__ __forceinline__ void epi_half(const Args& a, const float* cst, const 
       eng::split32<SPLIT, d.relu != 0>(f, hi, lo);
       if constexpr (S != 9) {
         // next stage's A operand: columns [0,128) -> P[(S+1)&1], [128,256) -> Q
-        const int cb = cw + cc * 32;        // column inside the 128-wide buffer
+        const int cb = cw + cc * CSTEP;     // column inside the 128-wide buffer
         constexpr int buf_col = H == 0 ? ((S + 1) & 1) * 64 : 128;
         constexpr int buf_lo = H == 0 ? ((S + 1) & 1) * 32768 : 65536;
         tc::tmem_st16(c.e.tmem_ahi + lane_base + (uint32_t)(buf_col + (cb >> 1)), hi);
@@ -291,16 +306,16 @@ __device__ __forceinline__ void epi_half(const Args& a, const float* cst, const 
                 make_uint4(lo[4 * g], lo[4 * g + 1], lo[4 * g + 2], lo[4 * g + 3]);
         }
       }
+      if constexpr (S < 9) {
+        // hand this quarter over before converting the next one
+        if constexpr (SPLIT) tc::fence_proxy_async();
+        tc::tmem_st_wait();
+        tc::tc_fence_before();
+        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(c.aq_addr + (uint32_t)(H * 2 + cc) * 8u) : "memory");
+        if (threadIdx.x == 64) stamp(c, tile_iter, S, 9 + 4 * H + cc);
+      }
       if (a.img_out[S].base != nullptr) eng::dump32<SPLIT>(a.img_out[S], tile, row, cu, hi, lo, c.e.pol_stream);
     }
-  }
-  if (threadIdx.x == 64) stamp(c, tile_iter, S, 9 + 4 * H);
-  if constexpr (S < 9) {
-    if constexpr (SPLIT) tc::fence_proxy_async();
-    tc::tmem_st_wait();
-    tc::tc_fence_before();
-    if (threadIdx.x == 64) stamp(c, tile_iter, S, 10 + 4 * H);
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(H == 0 ? c.a1_addr : c.a2_addr) : "memory");
   }
   if (threadIdx.x == 64) stamp(c, tile_iter, S, 5 + 2 * H);
   if constexpr (d.relu != 0) {
@@ -308,13 +323,13 @@ __device__ __forceinline__ void epi_half(const Args& a, const float* cst, const 
       // layout (fused::Args::relu_bits): [tile][9 layers][2 halves][128 rows] x 16 B, bit = column inside the
       // half; this warp's 32-bit words are number cw/32 .. of half H (view layer: halves are 64 columns)
       constexpr int L = S == 9 ? 8 : S;
-      uint32_t* mw = reinterpret_cast<uint32_t*>(a.relu_bits + ((size_t)(tile * 9 + L) * 2 + H) * 128 + row) + (cw >> 5);
+      uint32_t* mw = reinterpret_cast<uint32_t*>(a.relu_bits + ((size_t)(tile * 9 + L) * 2 + H) * 128 + row) + (cw >> 5);   // chunk cc -> word (cw + cc * CSTEP) / 32
 #pragma unroll
       for (int cc = 0; cc < nchunk; ++cc) {
         uint32_t bits = 0;
 #pragma unroll
         for (int j = 0; j < 32; ++j) bits |= (__uint_as_float(v[cc][j]) > 0.f ? 1u : 0u) << j;
-        mw[cc] = bits;
+        mw[cc * (CSTEP / 32)] = bits;
       }
     }
   }
@@ -340,15 +355,14 @@ __global__ void __launch_bounds__(320, 1) field_fwd_pipe_kernel(const __grid_con
   uint64_t* full = reinterpret_cast<uint64_t*>(psm + C::OFF_BAR);
   uint64_t* empty = full + C::NSLOT;
   uint64_t* accf = empty + C::NSLOT;      // [2]
-  uint64_t* a1 = accf + 2;
-  uint64_t* a2 = a1 + 1;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a2 + 1);
+  uint64_t* aq = accf + 2;                // [4]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aq + 4);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (tid == 0) {
     for (int i = 0; i < C::NSLOT; ++i) { tc::mbar_init(&full[i], 1); tc::mbar_init(&empty[i], 1); }
     tc::mbar_init(&accf[0], 1); tc::mbar_init(&accf[1], 1);
-    tc::mbar_init(a1, 256); tc::mbar_init(a2, 256);
+    for (int i = 0; i < 4; ++i) tc::mbar_init(&aq[i], 256);
     tc::fence_mbar_init();
   }
   for (int i = tid; i < C_TOTAL; i += blockDim.x) cst[i] = a.cbuf[i];
@@ -370,7 +384,7 @@ __global__ void __launch_bounds__(320, 1) field_fwd_pipe_kernel(const __grid_con
   ctx.e.tmem_acc = tmem; ctx.e.tmem_ahi = tmem + 256; ctx.e.tmem_alo = 0; ctx.e.smem_a = tc::smem_u32(areg);
   ctx.e.dbg = nullptr; ctx.e.dbg_tiles = 0;
   ctx.e.pol_keep = tc::policy_evict_last(); ctx.e.pol_stream = tc::policy_evict_first();
-  ctx.accf_addr = tc::smem_u32(accf); ctx.a1_addr = tc::smem_u32(a1); ctx.a2_addr = tc::smem_u32(a2);
+  ctx.accf_addr = tc::smem_u32(accf); ctx.aq_addr = tc::smem_u32(aq);
   ctx.smem_lo = tc::smem_u32(lo_area);
   ctx.dbg = a.dbg; ctx.dbg_tiles = a.dbg_tiles;
 
@@ -442,8 +456,7 @@ __global__ void __launch_bounds__(320, 1) field_fwd_pipe_kernel(const __grid_con
       }
       tc::fence_proxy_async();
       tc::tc_fence_before();        // the previous tile's accumulator loads are complete (ordered before the arrive)
-      tc::mbar_arrive(a1);
-      tc::mbar_arrive(a2);
+      for (int i = 0; i < 4; ++i) tc::mbar_arrive(&aq[i]);
       float alpha = 0.f, rgb[3] = {0.f, 0.f, 0.f};
       epi_tile<NSPLIT>(a, cst, ctx, lo_area, lane_base, half, row, tile, p, valid, alpha, rgb, tile_iter,
                        std::make_index_sequence<NSTAGE>{});

@@ -22,7 +22,8 @@ constexpr int TILE_M = 128;
 constexpr int MAX_SLABS = 352;   // the N-half pipelined forward issues 336 half-slabs per tile
 
 enum : uint8_t { A_TMEM = 0, A_SMEM = 1, A_MIX = 2 };   // A_MIX: hi in TMEM (a_off), lo in shared memory (a_lo_delta)
-enum : uint8_t { F_ZERO_ACC = 1, F_STAGE_END = 2, F_HI_ONLY_A = 4, F_STAGE_BEGIN = 8, F_WAIT_A2 = 16 };
+enum : uint8_t { F_ZERO_ACC = 1, F_STAGE_END = 2, F_HI_ONLY_A = 4, F_STAGE_BEGIN = 8,
+                 F_WAIT_Q1 = 16, F_WAIT_Q2 = 32, F_WAIT_Q3 = 64, F_COMMIT_BOTH = 128 };   // pipelined plans: A-ready barriers of column quarters 1..3 (F_STAGE_BEGIN = quarter 0)
 
 struct SlabDef {
   uint16_t n;          // rows of the B slab (= GEMM N), multiple of 16

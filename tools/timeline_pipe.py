@@ -28,6 +28,6 @@ for t in range(1, 3):
         r = b[t, s] - t0
         print(f"tile {t} stage {s}: " + " ".join(f"{int(x):8d}" for x in r[:4]) + " | " + " ".join(f"{int(x):8d}" for x in r[4:]) +
               f" | mma h0 {int(r[2] - r[0]):6d} h1 {int(r[3] - r[2]):6d} epi0 {int(r[5] - r[4]):6d} epi1 {int(r[7] - r[6]):6d}"
-              f" | epi0: ld {int(r[8] - r[4]):5d} cvt+st {int(r[9] - r[8]):5d} fence {int(r[10] - r[9]):5d}"
-              f" | epi1: ld {int(r[12] - r[6]):5d} cvt+st {int(r[13] - r[12]):5d} fence {int(r[14] - r[13]):5d}")
+              f" | epi0 quarters handed over at +{int(r[9] - r[4]):5d} +{int(r[10] - r[4]):5d}"
+              f" | epi1 at +{int(r[13] - r[6]):5d} +{int(r[14] - r[6]):5d}")
     print(f"tile {t} total cycles: {b[t + 1, 0, 0] - b[t, 0, 0]}")
