@@ -227,7 +227,9 @@ def main():
     traffic = None
     tpath = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "traffic.json")
     if os.path.exists(tpath):
-        traffic = json.load(open(tpath)).get(f"field_fused_fwd_kernel/{args.precision}/inference", {}).get("dram_bytes")
+        tj = json.load(open(tpath))
+        pipe = os.environ.get("SCNERF_FWD_PIPE", "1") != "0"      # which forward kernel this process launches
+        traffic = tj.get(f"{'field_fwd_pipe_kernel' if pipe else 'field_fused_fwd_kernel'}/{args.precision}/inference", {}).get("dram_bytes")
     field_flop = P_rays * (NC + NF) * FLOP_PER_SAMPLE
     achieved = field_flop / (ms_field * 1e-3) / 1e12
 

@@ -14,9 +14,9 @@ timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > $out/${tag}_
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $out/${tag}_launches_bf16x3.csv \
   python bench.py --steps 2 --warmup 1 --no-cpu-baseline > $out/${tag}_launches.log 2>&1
 # one full-set capture per tensor-core kernel: inference forward (the roofline kernel), then the training fine pass
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:field_fused_fwd_kernel --launch-skip 3 -c 1 \
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:"field_fused_fwd_kernel|field_fwd_pipe_kernel" --launch-skip 3 -c 1 \
   -o $out/${tag}_fwd_infer_bf16x3 -f python tools/prof_field.py bf16x3 > $out/${tag}_ncu_fwd.log 2>&1
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:"field_fused_dgrad_kernel|field_wgrad_kernel|field_fused_fwd_kernel" \
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:"field_fused_dgrad_kernel|field_dgrad_pipe_kernel|field_wgrad_kernel|field_fused_fwd_kernel|field_fwd_pipe_kernel" \
   --launch-skip 16 -c 6 -o $out/${tag}_train_bf16x3 -f python tools/step_breakdown.py bf16x3 > $out/${tag}_ncu_train.log 2>&1
 # digest the captures on the box: the reports themselves exceed what gpurun copies back
 python tools/ncu_top.py $out/${tag}_fwd_infer_bf16x3.ncu-rep 20 > $out/${tag}_fwd_infer_bf16x3_ncu_summary.txt 2>&1

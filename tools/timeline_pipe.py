@@ -2,6 +2,7 @@
 0 MMA passed a1, 1 MMA passed a2, 2 MMA committed h0, 3 MMA committed h1,
 4 epilogue saw accf0, 5 epilogue arrived a1, 6 epilogue saw accf1, 7 epilogue arrived a2."""
 import sys, os
+os.environ["SCNERF_DBG_MIN_TILES"] = "1000000000"   # keep the wgrad kernel (same debug pointer, other layout) from stamping
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch, numpy as np
 from tests.util import build_modules
@@ -10,19 +11,29 @@ from scnerf_b200 import _lib
 prec = sys.argv[1] if len(sys.argv) > 1 else "bf16x3"
 lib = _lib.load()
 mods = build_modules(0, "cuda:0")
-N = 4096
-pts = torch.rand(N, 192, 3, device="cuda") * 2 - 1
-vd = torch.nn.functional.normalize(torch.randn(N, 3, device="cuda"), dim=-1)
-run_network(pts, vd, mods["fine"], None, None, precision=prec)
+TRAIN = len(sys.argv) > 2 and sys.argv[2] == "train"     # training step: the fine-pass forward (image dumps on) stamps last
 T = 4
 buf = torch.zeros(T, 10, 16, dtype=torch.int64, device="cuda")
-lib.scnerf_debug_timeline(_lib.ptr(buf), T)
-run_network(pts, vd, mods["fine"], None, None, precision=prec)
+if TRAIN:
+    from scnerf_b200 import synth
+    from scnerf_b200.engine import TrainStep
+    kps, idx, target = (torch.from_numpy(x).cuda() for x in synth.pixel_batch(1000, 4096))
+    eng = TrainStep(mods["cam"], mods["coarse"], mods["fine"], 4096, 64, 128, precision=prec)
+    eng.step_device(kps, idx, target)
+    lib.scnerf_debug_timeline(_lib.ptr(buf), T)
+    eng.step_device()
+else:
+    N = 4096
+    pts = torch.rand(N, 192, 3, device="cuda") * 2 - 1
+    vd = torch.nn.functional.normalize(torch.randn(N, 3, device="cuda"), dim=-1)
+    run_network(pts, vd, mods["fine"], None, None, precision=prec)
+    lib.scnerf_debug_timeline(_lib.ptr(buf), T)
+    run_network(pts, vd, mods["fine"], None, None, precision=prec)
 torch.cuda.synchronize()
 lib.scnerf_debug_timeline(None, 0)
 b = buf.cpu().numpy()
 t0 = b[b > 0].min()
-print(prec, "stage: mma_a1 mma_a2 commit0 commit1 | epi_accf0 epi_a1 epi_accf1 epi_a2   (cycles from the first stamp)")
+print(prec, "TRAIN" if TRAIN else "INFER", "stage: mma_a1 mma_a2 commit0 commit1 | epi_accf0 epi_a1 epi_accf1 epi_a2   (cycles from the first stamp)")
 for t in range(1, 3):
     for s in range(10):
         r = b[t, s] - t0
