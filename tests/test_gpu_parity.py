@@ -615,3 +615,19 @@ def test_prd_loss(lib, golden):
     assert none is None
     assert abs(float(lv) - float(g["val_loss"])) <= 1e-4 * float(g["val_loss"])
     assert abs(float(lpp) - float(g["val_loss_pp"])) <= 1e-4 * float(g["val_loss_pp"])
+
+
+def test_serial_tensor_core_kernels_still_pass():
+    """The N-half pipelined forward / dgrad are the default; the serial kernels they replaced stay in the library
+    (SCNERF_FWD_PIPE=0 / SCNERF_DGRAD_PIPE=0, and the 96-wide d(PE) dgrad of the NeRF++ background network).  The
+    switches are read once per process, so the tensor-core parity tests are replayed in a child process with both off."""
+    import os, subprocess, sys
+    if os.environ.get("SCNERF_FWD_PIPE") == "0" and os.environ.get("SCNERF_DGRAD_PIPE") == "0":
+        pytest.skip("already running with the serial kernels")
+    env = dict(os.environ, SCNERF_FWD_PIPE="0", SCNERF_DGRAD_PIPE="0")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-x", "-q", "-m", "gpu", "-k",
+                        "field_tc_forward_vs_fp32 or train_step_gradients_bf16x3 or engine_full_size_tc_backward"],
+                       cwd=root, env=env, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+    assert "passed" in r.stdout and "failed" not in r.stdout
