@@ -289,12 +289,22 @@ int scnerf_tc_selftest(const float* A, const float* B, float* D, int32_t N, int3
                        void* workspace, size_t workspace_bytes, void* stream);
 
 /* Diagnostics: have the next fused-forward launches record clock64() stamps of CTA 0 for the first
- * `tiles` tiles into dev_buf[tiles][10 stages][4] (NULL disables).  Not part of the product path. */
+ * `tiles` tiles into dev_buf (NULL disables): the pipelined forward writes [tiles][10 stages][16]
+ * (tools/timeline_pipe.py), the serial one [tiles][10][4] (tools/timeline.py).  Not part of the product path. */
 int scnerf_debug_timeline(long long* dev_buf, int32_t tiles);
 
-/* Diagnostics: raw tcgen05 throughput probe (cycles for iters*16 MMAs of 128x256x16 per CTA).
- * mode 0 SS K-major, 1 TS, 2 SS MN-major/MN-major, 3 SS MN-major A + K-major B. */
+/* Diagnostics: raw tcgen05 throughput probe.  mode 0..3: cycles for iters*16 MMAs of 128x256x16 per CTA
+ * (0 SS K-major, 1 TS, 2 SS MN-major/MN-major, 3 SS MN-major A + K-major B); mode = 256 + (N/8 << 4) + pattern:
+ * iters*24 MMAs of 128xNx16, N in {256,128,64,32}, pattern 0 TS, 1 TS alternating accumulators, 2 SS,
+ * 3 TS/SS/TS, 4 SS/TS (tools/mma_bench.py). */
 int scnerf_debug_mma_bench(int32_t mode, int32_t iters, long long* dev_out, int32_t nblocks, void* stream);
+
+/* Diagnostics (host only, no GPU needed): the compile-time slab tables the tensor-core kernels unroll.
+ * which: 0 serial forward, 1 pipelined forward (3-D points), 2 pipelined forward (4-D points), 3 serial dgrad,
+ * 4 pipelined dgrad.  index < 0: out = {n_slabs, n_stages, split-bf16 weight-image bytes, 0...};
+ * else out = {n, acc_col, a_off, a_lo_delta, a_kind, flags, stage, pad, img_off} of slab `index`.
+ * Returns 0, or SCNERF_ERR_ARG.  Used by tests/test_host_abi.py to check the plans' hazard invariants. */
+int scnerf_debug_slab_plan(int32_t which, int32_t index, int64_t* out9);
 
 /* Kernel-launch counter (bench.py's gpu_launches): number of kernels this library has launched
  * in this process since the last reset. */

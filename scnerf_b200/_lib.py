@@ -103,6 +103,7 @@ SIGNATURES = {
     "scnerf_launch_count": (_I64, [C.c_int32]),
     "scnerf_debug_mma_bench": (_I, [C.c_int32, C.c_int32, vp, C.c_int32, vp]),
     "scnerf_debug_timeline": (_I, [vp, C.c_int32]),
+    "scnerf_debug_slab_plan": (_I, [C.c_int32, C.c_int32, C.POINTER(C.c_int64)]),
     "scnerf_tc_selftest": (_I, [vp, vp, vp, C.c_int32, C.c_int32, C.c_int32, vp, _SZ, vp]),
     "scnerf_searchsorted_f32": (_I, [vp, vp, vp, _I64, _I64, _I64, _I64, _I, vp]),
     "scnerf_camera_matrices": (_I, [_P(Camera), vp, vp, vp]),

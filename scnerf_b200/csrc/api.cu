@@ -41,6 +41,24 @@ int scnerf_debug_mma_bench(int32_t mode, int32_t iters, long long* dev_out, int3
   return tc_mma_bench(mode, iters, dev_out, nblocks, stream);
 }
 
+int scnerf_debug_slab_plan(int32_t which, int32_t index, int64_t* out9) {
+  SCNERF_CHECK_ARG(out9 != nullptr, "slab_plan: null output");
+  static const eng::Plan plans[5] = {fused::make_fwd_plan<3, 4>(), fpipe::make_plan<3, 4>(), fpipe::make_plan<3, 6>(),
+                                     dgrad::make_plan<64>(), dpipe::make_plan()};
+  SCNERF_CHECK_ARG(which >= 0 && which < 5, "slab_plan: unknown plan %d", which);
+  const eng::Plan& P = plans[which];
+  for (int i = 0; i < 9; ++i) out9[i] = 0;
+  if (index < 0) {
+    out9[0] = P.n_slabs; out9[1] = P.n_stages; out9[2] = (int64_t)fused::plan_image_bytes(P, 3);
+    return 0;
+  }
+  SCNERF_CHECK_ARG(index < P.n_slabs, "slab_plan: slab %d of %d", index, P.n_slabs);
+  const eng::SlabDef& d = P.slab[index];
+  out9[0] = d.n; out9[1] = d.acc_col; out9[2] = d.a_off; out9[3] = d.a_lo_delta; out9[4] = d.a_kind;
+  out9[5] = d.flags; out9[6] = d.stage; out9[7] = d.pad; out9[8] = d.img_off;
+  return 0;
+}
+
 int scnerf_debug_timeline(long long* dev_buf, int32_t tiles) {
   tc_dbg_ptr() = dev_buf;
   tc_dbg_tiles() = tiles;

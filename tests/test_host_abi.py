@@ -152,3 +152,91 @@ def test_checkpoint_layout(tmp_path):
     assert "module.pts_linears.0.weight" in ck["network_fn_state_dict"]          # nn.DataParallel prefix kept
     fresh = mk()
     fresh.load_state_dict(ck["network_fine_state_dict"])
+
+
+# ---- slab plans of the N-half pipelined tensor-core kernels (host-side tables, no GPU needed) ----------------
+F_ZERO_ACC, F_STAGE_END, F_HI_ONLY_A, F_STAGE_BEGIN, F_WAIT_Q1, F_WAIT_Q2, F_WAIT_Q3, F_COMMIT_BOTH = 1, 2, 4, 8, 16, 32, 64, 128
+A_TMEM, A_SMEM, A_MIX = 0, 1, 2
+
+
+def _plan(which):
+    import ctypes as C
+    _lib = _ensure_built()
+    lib = _lib.load()
+    out = (C.c_int64 * 9)()
+    _lib.check(lib.scnerf_debug_slab_plan(which, -1, out))
+    n_slabs, n_stages, img_bytes = out[0], out[1], out[2]
+    slabs = []
+    for i in range(n_slabs):
+        _lib.check(lib.scnerf_debug_slab_plan(which, i, out))
+        slabs.append(dict(zip(("n", "acc_col", "a_off", "a_lo", "a_kind", "flags", "stage", "pad", "img_off"), list(out))))
+    return n_slabs, n_stages, img_bytes, slabs
+
+
+@pytest.mark.parametrize("which,name,ring_multiples", [(1, "pipelined forward (3-D points)", (8, 24)),
+                                                       (2, "pipelined forward (4-D points)", (6, 24)),
+                                                       (4, "pipelined dgrad", (8, 24))])
+def test_pipelined_slab_plans(which, name, ring_multiples):
+    """Hazard invariants of the N-half pipelined schedules (csrc/field_tc_fwd_pipe.cuh, field_tc_dgrad_pipe.cuh):
+    every K-slab that reads operand quarter q is issued after this stage's wait on quarter barrier q; an accumulator
+    half is only re-initialised after the barrier that says it was drained; each barrier is waited exactly once per
+    stage (the kernels derive every mbarrier parity from `stage & 1`); the weight image is one contiguous run in
+    issue order; ring geometry divides the slab count."""
+    n_slabs, n_stages, img_bytes, slabs = _plan(which)
+    assert n_stages == 10 and n_stages % 2 == 0
+    for m in ring_multiples:                       # GROUP x NSLOT of the split-bf16 / bf16 builds
+        assert n_slabs % m == 0, (name, n_slabs, m)
+    off = 0
+    for s in slabs:                                # packed in issue order, no holes
+        assert s["img_off"] == off
+        off += s["n"] * 32
+    assert img_bytes == 2 * off
+    for st in range(n_stages):
+        mine = [s for s in slabs if s["stage"] == st]
+        waited = set()
+        zeroed = set()
+        commits = []
+        for s in mine:
+            fl = s["flags"]
+            for q, bit in enumerate((F_STAGE_BEGIN, F_WAIT_Q1, F_WAIT_Q2, F_WAIT_Q3)):
+                if fl & bit:
+                    assert q not in waited, (name, st, "barrier waited twice", q)
+                    waited.add(q)
+            acc = s["acc_col"]
+            assert acc in (0, 128, 448) and (acc + s["n"] <= 256 or (acc == 448 and s["n"] <= 64)), (name, st, s)
+            if fl & F_ZERO_ACC:
+                # acc0 (columns 0..127) is drained by the owners of quarters 0 and 1: quarter 0's arrival follows
+                # the loads of BOTH chunks of a thread, so waiting quarter 0 is enough; acc1 needs quarter 2
+                if acc == 0:
+                    assert 0 in waited, (name, st, "acc0 re-initialised before it was drained")
+                if acc == 128:
+                    assert 2 in waited, (name, st, "acc1 re-initialised before it was drained")
+                zeroed.add(acc)
+            else:
+                assert acc in zeroed or s["n"] == 16, (name, st, "accumulate into an uninitialised accumulator", s)
+            if s["a_kind"] == A_MIX:               # hidden-state operand: hi in TMEM, lo in smem
+                col = s["a_off"]
+                assert 0 <= col < 192 and col % 8 == 0
+                if col < 128:                      # first operand half: buffer P[stage & 1], quarters 0 / 1
+                    assert col // 64 == st % 2, (name, st, "wrong half of the P double buffer", col)
+                    q = (col % 64) // 32
+                    assert s["a_lo"] * 16 == (st % 2) * 32768 + (col % 64) // 8 * 4096
+                else:                              # second half: Q, quarters 2 / 3
+                    q = 2 + (col - 128) // 32
+                    assert s["a_lo"] * 16 == 65536 + (col - 128) // 8 * 4096
+                assert q in waited, (name, st, f"slab reads operand quarter {q} before its barrier", s)
+            if fl & F_STAGE_END:
+                commits.append(s["pad"])
+                if fl & F_COMMIT_BOTH:
+                    commits.append(s["pad"] ^ 1)
+        assert waited == {0, 1, 2, 3}, (name, st, waited)          # every barrier advances once per stage
+        assert sorted(commits) == [0, 1], (name, st, commits)      # both accumulator-half barriers fire once
+        assert mine[-1]["flags"] & F_STAGE_END                     # nothing is issued after the stage's last commit
+
+
+def test_serial_plans_unchanged_by_the_pipelined_ones():
+    """The serial kernels' tables (kept for SCNERF_*_PIPE=0 and the 96-wide d(PE) dgrad) still fit their rings."""
+    n, st, _, slabs = _plan(0)
+    assert (n, st) == (168, 10) and all(s["n"] in (256, 128, 16) for s in slabs)
+    n, st, _, slabs = _plan(3)
+    assert (n, st) == (176, 11)
