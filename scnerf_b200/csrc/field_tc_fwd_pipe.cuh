@@ -165,8 +165,10 @@ struct PCtx {
   uint32_t smem_lo;            // shared address of the lo area
   long long* dbg; int dbg_tiles;
 };
-// timeline: [tile][stage][16] (8 + 4h + {0 loads done, 1 quarter 2h handed over, 2 quarter 2h+1 handed over}; rest unused): 0 MMA passed a1, 1 MMA passed a2, 2 MMA committed h0, 3 MMA committed h1,
-//                             4 epilogue saw accf0, 5 epilogue arrived a1, 6 epilogue saw accf1, 7 epilogue arrived a2
+// timeline: [tile][stage][16] clock64 stamps of CTA 0 (tools/timeline_pipe.py):
+//   0 MMA passed aq[0], 1 MMA passed aq[2], 2 MMA committed h0, 3 MMA committed h1,
+//   4 epilogue saw accf[0], 5 epilogue finished h0, 6 epilogue saw accf[1], 7 epilogue finished h1,
+//   8 + 4h: accumulator loads of half h done, 9 + 4h / 10 + 4h: quarter 2h / 2h+1 handed over
 __device__ __forceinline__ void stamp(const PCtx& c, int tile_iter, int stage, int slot) {
   if (c.dbg != nullptr && blockIdx.x == 0 && tile_iter < c.dbg_tiles)
     c.dbg[((size_t)tile_iter * NSTAGE + stage) * 16 + slot] = clock64();
