@@ -1,6 +1,6 @@
 """NeRF++ training step (ddp_train_nerf.py:421-488 through the host mirror) at BASELINE configs[3]-like sizes:
-N rays x cascade (64, 128), learnable distortion camera, fg field on the tensor-core kernels (bf16x3) or fp32,
-bg field on the fp32 CUDA-core kernels.  Prints ms/step and a per-phase breakdown (CUDA events)."""
+N rays x cascade (64, 128), learnable distortion camera, fg and bg fields on the tensor-core kernels (bf16x3 / bf16)
+or the fp32 CUDA-core kernels.  Prints ms/step and a per-phase breakdown (CUDA events)."""
 import sys, os, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
