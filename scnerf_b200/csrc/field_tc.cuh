@@ -361,6 +361,13 @@ inline bool fwd_pipe_enabled() {
   if (on < 0) { const char* e = getenv("SCNERF_FWD_PIPE"); on = e ? (atoi(e) != 0) : 1; }
   return on != 0;
 }
+// Experimental (default off, not yet measured on hardware): SCNERF_EPI_ROLL=1 runs the repeated epilogue stages of the
+// pipelined kernels from one copy of the code (instruction-cache footprint; see fpipe::epi_half_rt)
+inline bool epi_roll_enabled() {
+  static int on = -1;
+  if (on < 0) { const char* e = getenv("SCNERF_EPI_ROLL"); on = e ? (atoi(e) != 0) : 0; }
+  return on != 0;
+}
 template <int XS = 4>
 inline const eng::Plan& pipe_plan_host() {
   static eng::Plan P = fpipe::make_plan<3, XS>();   // (slab order, sizes and image offsets do not depend on NSPLIT)
@@ -390,6 +397,10 @@ inline int pipe_plan_init() {
                                    fpipe::Cfg<1, 6>::SMEM_BYTES));
   SCNERF_CUDA(cudaFuncSetAttribute((fpipe::field_fwd_pipe_kernel<3, 6>), cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    fpipe::Cfg<3, 6>::SMEM_BYTES));
+  SCNERF_CUDA(cudaFuncSetAttribute((fpipe::field_fwd_pipe_kernel<1, 4, true>), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   fpipe::Cfg<1, 4>::SMEM_BYTES));
+  SCNERF_CUDA(cudaFuncSetAttribute((fpipe::field_fwd_pipe_kernel<3, 4, true>), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   fpipe::Cfg<3, 4>::SMEM_BYTES));
   if (dev < 64) done[dev] = true;
   return 0;
 }
@@ -480,7 +491,9 @@ inline int field_tc_fwd_impl(const scnerf_mlp& m, const float* rays, int ray_col
   }
   a.dbg = tc_dbg_ptr(); a.dbg_tiles = tc_dbg_tiles();
   int grid = std::min(device_sm_count(), a.num_tiles);
-  if (pipe) SCNERF_LAUNCH((fpipe::field_fwd_pipe_kernel<NSPLIT, XS>), grid, 320, (fpipe::Cfg<NSPLIT, XS>::SMEM_BYTES), stream, a);
+  if (pipe && XS == 4 && epi_roll_enabled())
+    SCNERF_LAUNCH((fpipe::field_fwd_pipe_kernel<NSPLIT, 4, true>), grid, 320, (fpipe::Cfg<NSPLIT, 4>::SMEM_BYTES), stream, a);
+  else if (pipe) SCNERF_LAUNCH((fpipe::field_fwd_pipe_kernel<NSPLIT, XS>), grid, 320, (fpipe::Cfg<NSPLIT, XS>::SMEM_BYTES), stream, a);
   else SCNERF_LAUNCH((field_fused_fwd_kernel<NSPLIT, XS>), grid, 320, (Cfg<NSPLIT, XS>::SMEM_BYTES), stream, a);
   return 0;
 }
@@ -561,6 +574,10 @@ inline int dpipe_plan_init() {
                                    dpipe::Cfg<1>::SMEM_BYTES));
   SCNERF_CUDA(cudaFuncSetAttribute(dpipe::field_dgrad_pipe_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    dpipe::Cfg<3>::SMEM_BYTES));
+  SCNERF_CUDA(cudaFuncSetAttribute((dpipe::field_dgrad_pipe_kernel<1, true>), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   dpipe::Cfg<1>::SMEM_BYTES));
+  SCNERF_CUDA(cudaFuncSetAttribute((dpipe::field_dgrad_pipe_kernel<3, true>), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   dpipe::Cfg<3>::SMEM_BYTES));
   if (dev < 64) done[dev] = true;
   return 0;
 }
@@ -605,8 +622,11 @@ inline int field_tc_bwd_impl(const scnerf_mlp& m, const scnerf_mlp& g, const flo
   a.g_raw = g_raw; a.wimg = G.wimg; a.cbuf = B.tc_cbuf;
   for (int i = 0; i < 8; ++i) a.out_dz[i] = G.dz[i];
   a.relu_bits = I.relu_bits; a.out_dfeat = G.dfeat; a.out_dzv = G.dzv; a.g_pts = G.g_pts; a.g_vd = G.g_vd;
-  if (dp) SCNERF_LAUNCH((dpipe::field_dgrad_pipe_kernel<NSPLIT>), std::min(device_sm_count(), T), 320,
-                        (dpipe::Cfg<NSPLIT>::SMEM_BYTES), stream, a);
+  if (dp && epi_roll_enabled())
+    SCNERF_LAUNCH((dpipe::field_dgrad_pipe_kernel<NSPLIT, true>), std::min(device_sm_count(), T), 320,
+                  (dpipe::Cfg<NSPLIT>::SMEM_BYTES), stream, a);
+  else if (dp) SCNERF_LAUNCH((dpipe::field_dgrad_pipe_kernel<NSPLIT>), std::min(device_sm_count(), T), 320,
+                             (dpipe::Cfg<NSPLIT>::SMEM_BYTES), stream, a);
   else SCNERF_LAUNCH((dgrad::field_fused_dgrad_kernel<NSPLIT, XN>), std::min(device_sm_count(), T), 320,
                      (dgrad::Cfg<NSPLIT, XN>::SMEM_BYTES), stream, a);
   if (XN == 96) {

@@ -249,6 +249,49 @@ __device__ __forceinline__ void epi_half(const Args& a, const float* cst, const 
     }
   }
 }
+// Trunk stages T2, T3, T5..T8 share one epilogue (mask of layer 8-T, image out_dz[8-T], no head term).  ROLL builds run
+// them from one copy of the code with T as a run-time value (see fpipe::epi_half_rt for why).
+template <int NSPLIT, int H>
+__device__ __forceinline__ void epi_half_rt(const Args& a, const fpipe::PCtx& c, uint8_t* lo_area, uint32_t lane_base,
+                                            int half, int row, int tile, int T) {
+  constexpr bool SPLIT = NSPLIT == 3;
+  const int mlayer = 8 - T;
+  const uint32_t* mw = reinterpret_cast<const uint32_t*>(a.relu_bits + ((size_t)(tile * 9 + mlayer) * 2 + H) * 128 + row);
+  uint32_t mk[2];
+  mk[0] = __ldg(mw + half);
+  mk[1] = __ldg(mw + 2 + half);
+  eng::mbar_wait_a(c.accf_addr + H * 8, (uint32_t)(T & 1));
+  tc::tc_fence_after();
+  uint32_t v[2][32];
+#pragma unroll
+  for (int cc = 0; cc < 2; ++cc) tc::tmem_ld32(c.e.tmem_acc + lane_base + H * 128 + half * 32 + cc * 64, v[cc]);
+  tc::tmem_ld_wait();
+  const uint32_t par = (uint32_t)((T + 1) & 1);
+  const uint32_t buf_col = H == 0 ? par * 64u : 128u;
+  const uint32_t buf_lo = H == 0 ? par * 32768u : 65536u;
+#pragma unroll
+  for (int cc = 0; cc < 2; ++cc) {
+    const int cb = half * 32 + cc * 64;     // column inside the 128-wide half
+    const int cu = H * 128 + cb;            // output column
+    float f[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) f[j] = ((mk[cc] >> j) & 1u) ? __uint_as_float(v[cc][j]) : 0.f;
+    uint32_t hi[16], lo[16];
+    eng::split32<SPLIT, false>(f, hi, lo);
+    tc::tmem_st16(c.e.tmem_ahi + lane_base + buf_col + (uint32_t)(cb >> 1), hi);
+    if constexpr (SPLIT) {
+#pragma unroll
+      for (int g = 0; g < 4; ++g)
+        *reinterpret_cast<uint4*>(lo_area + buf_lo + tc::canon_off(row, cb + 8 * g, TILE_M)) =
+            make_uint4(lo[4 * g], lo[4 * g + 1], lo[4 * g + 2], lo[4 * g + 3]);
+      tc::fence_proxy_async();
+    }
+    tc::tmem_st_wait();
+    tc::tc_fence_before();
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(c.aq_addr + (uint32_t)(H * 2 + cc) * 8u) : "memory");
+    eng::dump32<SPLIT>(a.out_dz[8 - T], tile, row, cu, hi, lo, c.e.pol_stream);
+  }
+}
 template <int NSPLIT, size_t... Ts>
 __device__ __forceinline__ void epi_tile(const Args& a, const float* cst, const fpipe::PCtx& c, uint8_t* lo_area,
                                          float* gx_s, float* out_s, uint32_t lane_base, int half, int row, int tile,
@@ -257,7 +300,7 @@ __device__ __forceinline__ void epi_tile(const Args& a, const float* cst, const 
     epi_half<NSPLIT, (int)Ts, 1>(a, cst, c, lo_area, gx_s, out_s, lane_base, half, row, tile, p, valid, gr)), ...);
 }
 
-template <int NSPLIT>
+template <int NSPLIT, bool ROLL = false>
 __global__ void __launch_bounds__(320, 1) field_dgrad_pipe_kernel(const __grid_constant__ Args a) {
   using C = Cfg<NSPLIT>;
   constexpr bool SPLIT = NSPLIT == 3;
@@ -338,8 +381,27 @@ __global__ void __launch_bounds__(320, 1) field_dgrad_pipe_kernel(const __grid_c
       tc::tmem_st_wait();
       tc::tc_fence_before();
       for (int i = 0; i < 4; ++i) tc::mbar_arrive(&aq[i]);
-      epi_tile<NSPLIT>(a, cst, ctx, lo_area, gx_s, out_s, lane_base, half, row, tile, p, valid, gr,
-                       std::make_index_sequence<NSTAGE>{});
+      if constexpr (ROLL) {
+        epi_half<NSPLIT, 0, 0>(a, cst, ctx, lo_area, gx_s, out_s, lane_base, half, row, tile, p, valid, gr);
+        epi_half<NSPLIT, 0, 1>(a, cst, ctx, lo_area, gx_s, out_s, lane_base, half, row, tile, p, valid, gr);
+        epi_half<NSPLIT, 1, 0>(a, cst, ctx, lo_area, gx_s, out_s, lane_base, half, row, tile, p, valid, gr);
+        epi_half<NSPLIT, 1, 1>(a, cst, ctx, lo_area, gx_s, out_s, lane_base, half, row, tile, p, valid, gr);
+#pragma unroll 1
+        for (int T = 2; T < 9; ++T) {
+          if (T == 4) {
+            epi_half<NSPLIT, 4, 0>(a, cst, ctx, lo_area, gx_s, out_s, lane_base, half, row, tile, p, valid, gr);
+            epi_half<NSPLIT, 4, 1>(a, cst, ctx, lo_area, gx_s, out_s, lane_base, half, row, tile, p, valid, gr);
+          } else {
+            epi_half_rt<NSPLIT, 0>(a, ctx, lo_area, lane_base, half, row, tile, T);
+            epi_half_rt<NSPLIT, 1>(a, ctx, lo_area, lane_base, half, row, tile, T);
+          }
+        }
+        epi_half<NSPLIT, 9, 0>(a, cst, ctx, lo_area, gx_s, out_s, lane_base, half, row, tile, p, valid, gr);
+        epi_half<NSPLIT, 9, 1>(a, cst, ctx, lo_area, gx_s, out_s, lane_base, half, row, tile, p, valid, gr);
+      } else {
+        epi_tile<NSPLIT>(a, cst, ctx, lo_area, gx_s, out_s, lane_base, half, row, tile, p, valid, gr,
+                         std::make_index_sequence<NSTAGE>{});
+      }
       tc::tc_fence_before();
       asm volatile("bar.sync 1, 256;" ::: "memory");
       if (half == 0 && valid) {

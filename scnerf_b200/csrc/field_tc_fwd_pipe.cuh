@@ -336,6 +336,71 @@ __device__ __forceinline__ void epi_half(const Args& a, const float* cst, const 
     }
   }
 }
+// Stages 0..6 share one epilogue (256-wide, ReLU, no head term).  ROLL builds run them from ONE copy of the code with
+// the stage as a run-time value (buffer parity, barrier parity, image / dump pointers indexed in the kernel
+// parameters): the fully unrolled epilogue is ~220 KB of straight-line code per tile, executed once, and the ncu stall
+// samples of the training forward put 27 % of its stalls on instruction fetch (profiles/README.md section 5).
+template <int NSPLIT, int H>
+__device__ __forceinline__ void epi_half_rt(const Args& a, const PCtx& c, uint8_t* lo_area, uint32_t lane_base, int half,
+                                            int row, int tile, int64_t p, bool valid, int tile_iter, int S) {
+  constexpr bool SPLIT = NSPLIT == 3;
+  const int cw = half * 32;                 // first column inside the N-half (chunk 0)
+  const int cbase = H * 128 + cw;           // first layer-output column
+  eng::mbar_wait_a(c.accf_addr + H * 8, (uint32_t)(S & 1));
+  tc::tc_fence_after();
+  if (threadIdx.x == 64) stamp(c, tile_iter, S, 4 + 2 * H);
+  uint32_t v[2][32];
+#pragma unroll
+  for (int cc = 0; cc < 2; ++cc) tc::tmem_ld32(c.e.tmem_acc + lane_base + H * 128 + cw + cc * 64, v[cc]);
+  tc::tmem_ld_wait();
+  if (threadIdx.x == 64) stamp(c, tile_iter, S, 8 + 4 * H);
+  // next stage's A operand: columns [0,128) -> P[(S+1)&1], [128,256) -> Q
+  const uint32_t par = (uint32_t)((S + 1) & 1);
+  const uint32_t buf_col = H == 0 ? par * 64u : 128u;
+  const uint32_t buf_lo = H == 0 ? par * 32768u : 65536u;
+  float* const dump_s = a.dump[S];
+  const bool has_img = a.img_out[S].base != nullptr;
+#pragma unroll
+  for (int cc = 0; cc < 2; ++cc) {
+    const int cu = cbase + cc * 64;         // layer-output column of v[cc][0]
+    float f[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[cc][j]);
+    if (dump_s != nullptr && valid) {
+      float* dp = dump_s + p * a.dump_ld[S] + cu;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) dp[j] = fmaxf(f[j], 0.f);
+    }
+    uint32_t hi[16], lo[16];
+    eng::split32<SPLIT, true>(f, hi, lo);
+    const int cb = cw + cc * 64;            // column inside the 128-wide buffer
+    tc::tmem_st16(c.e.tmem_ahi + lane_base + buf_col + (uint32_t)(cb >> 1), hi);
+    if constexpr (SPLIT) {
+#pragma unroll
+      for (int g = 0; g < 4; ++g)
+        *reinterpret_cast<uint4*>(lo_area + buf_lo + tc::canon_off(row, cb + 8 * g, TILE_M)) =
+            make_uint4(lo[4 * g], lo[4 * g + 1], lo[4 * g + 2], lo[4 * g + 3]);
+      tc::fence_proxy_async();
+    }
+    // hand this quarter over before converting the next one
+    tc::tmem_st_wait();
+    tc::tc_fence_before();
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(c.aq_addr + (uint32_t)(H * 2 + cc) * 8u) : "memory");
+    if (threadIdx.x == 64) stamp(c, tile_iter, S, 9 + 4 * H + cc);
+    if (has_img) eng::dump32<SPLIT>(a.img_out[S], tile, row, cu, hi, lo, c.e.pol_stream);
+  }
+  if (threadIdx.x == 64) stamp(c, tile_iter, S, 5 + 2 * H);
+  if (a.relu_bits != nullptr) {      // after the hand-off: off the MMA's critical path (layout: see epi_half)
+    uint32_t* mw = reinterpret_cast<uint32_t*>(a.relu_bits + ((size_t)(tile * 9 + S) * 2 + H) * 128 + row) + (cw >> 5);
+#pragma unroll
+    for (int cc = 0; cc < 2; ++cc) {
+      uint32_t bits = 0;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) bits |= (__uint_as_float(v[cc][j]) > 0.f ? 1u : 0u) << j;
+      mw[cc * 2] = bits;
+    }
+  }
+}
 template <int NSPLIT, size_t... Ss>
 __device__ __forceinline__ void epi_tile(const Args& a, const float* cst, const PCtx& c, uint8_t* lo_area,
                                          uint32_t lane_base, int half, int row, int tile, int64_t p, bool valid,
@@ -344,7 +409,7 @@ __device__ __forceinline__ void epi_tile(const Args& a, const float* cst, const 
     epi_half<NSPLIT, (int)Ss, 1>(a, cst, c, lo_area, lane_base, half, row, tile, p, valid, alpha, rgb, tile_iter)), ...);
 }
 
-template <int NSPLIT, int XS = 4>
+template <int NSPLIT, int XS = 4, bool ROLL = false>
 __global__ void __launch_bounds__(320, 1) field_fwd_pipe_kernel(const __grid_constant__ Args a) {
   using C = Cfg<NSPLIT, XS>;
   using L = ALay<NSPLIT, XS>;
@@ -460,8 +525,22 @@ __global__ void __launch_bounds__(320, 1) field_fwd_pipe_kernel(const __grid_con
       tc::tc_fence_before();        // the previous tile's accumulator loads are complete (ordered before the arrive)
       for (int i = 0; i < 4; ++i) tc::mbar_arrive(&aq[i]);
       float alpha = 0.f, rgb[3] = {0.f, 0.f, 0.f};
-      epi_tile<NSPLIT>(a, cst, ctx, lo_area, lane_base, half, row, tile, p, valid, alpha, rgb, tile_iter,
-                       std::make_index_sequence<NSTAGE>{});
+      if constexpr (ROLL) {
+#pragma unroll 1
+        for (int S = 0; S < 7; ++S) {
+          epi_half_rt<NSPLIT, 0>(a, ctx, lo_area, lane_base, half, row, tile, p, valid, tile_iter, S);
+          epi_half_rt<NSPLIT, 1>(a, ctx, lo_area, lane_base, half, row, tile, p, valid, tile_iter, S);
+        }
+        epi_half<NSPLIT, 7, 0>(a, cst, ctx, lo_area, lane_base, half, row, tile, p, valid, alpha, rgb, tile_iter);
+        epi_half<NSPLIT, 7, 1>(a, cst, ctx, lo_area, lane_base, half, row, tile, p, valid, alpha, rgb, tile_iter);
+        epi_half<NSPLIT, 8, 0>(a, cst, ctx, lo_area, lane_base, half, row, tile, p, valid, alpha, rgb, tile_iter);
+        epi_half<NSPLIT, 8, 1>(a, cst, ctx, lo_area, lane_base, half, row, tile, p, valid, alpha, rgb, tile_iter);
+        epi_half<NSPLIT, 9, 0>(a, cst, ctx, lo_area, lane_base, half, row, tile, p, valid, alpha, rgb, tile_iter);
+        epi_half<NSPLIT, 9, 1>(a, cst, ctx, lo_area, lane_base, half, row, tile, p, valid, alpha, rgb, tile_iter);
+      } else {
+        epi_tile<NSPLIT>(a, cst, ctx, lo_area, lane_base, half, row, tile, p, valid, alpha, rgb, tile_iter,
+                         std::make_index_sequence<NSTAGE>{});
+      }
       // combine the two column-halves of each row: both add into smem, half 0 finishes
       atomicAdd(out_s + row * 4 + 0, rgb[0]);
       atomicAdd(out_s + row * 4 + 1, rgb[1]);
