@@ -397,10 +397,12 @@ inline int pipe_plan_init() {
                                    fpipe::Cfg<1, 6>::SMEM_BYTES));
   SCNERF_CUDA(cudaFuncSetAttribute((fpipe::field_fwd_pipe_kernel<3, 6>), cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    fpipe::Cfg<3, 6>::SMEM_BYTES));
-  SCNERF_CUDA(cudaFuncSetAttribute((fpipe::field_fwd_pipe_kernel<1, 4, true>), cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   fpipe::Cfg<1, 4>::SMEM_BYTES));
-  SCNERF_CUDA(cudaFuncSetAttribute((fpipe::field_fwd_pipe_kernel<3, 4, true>), cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   fpipe::Cfg<3, 4>::SMEM_BYTES));
+  if (epi_roll_enabled()) {     // experimental builds: touched only when asked for
+    SCNERF_CUDA(cudaFuncSetAttribute((fpipe::field_fwd_pipe_kernel<1, 4, true>), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     fpipe::Cfg<1, 4>::SMEM_BYTES));
+    SCNERF_CUDA(cudaFuncSetAttribute((fpipe::field_fwd_pipe_kernel<3, 4, true>), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     fpipe::Cfg<3, 4>::SMEM_BYTES));
+  }
   if (dev < 64) done[dev] = true;
   return 0;
 }
@@ -574,10 +576,12 @@ inline int dpipe_plan_init() {
                                    dpipe::Cfg<1>::SMEM_BYTES));
   SCNERF_CUDA(cudaFuncSetAttribute(dpipe::field_dgrad_pipe_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    dpipe::Cfg<3>::SMEM_BYTES));
-  SCNERF_CUDA(cudaFuncSetAttribute((dpipe::field_dgrad_pipe_kernel<1, true>), cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   dpipe::Cfg<1>::SMEM_BYTES));
-  SCNERF_CUDA(cudaFuncSetAttribute((dpipe::field_dgrad_pipe_kernel<3, true>), cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   dpipe::Cfg<3>::SMEM_BYTES));
+  if (epi_roll_enabled()) {     // experimental builds: touched only when asked for
+    SCNERF_CUDA(cudaFuncSetAttribute((dpipe::field_dgrad_pipe_kernel<1, true>), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     dpipe::Cfg<1>::SMEM_BYTES));
+    SCNERF_CUDA(cudaFuncSetAttribute((dpipe::field_dgrad_pipe_kernel<3, true>), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     dpipe::Cfg<3>::SMEM_BYTES));
+  }
   if (dev < 64) done[dev] = true;
   return 0;
 }
