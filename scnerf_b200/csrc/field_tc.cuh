@@ -363,11 +363,12 @@ inline bool fwd_pipe_enabled() {
 }
 // Experimental (default off, not yet measured on hardware): SCNERF_EPI_ROLL=1 runs the repeated epilogue stages of the
 // pipelined kernels from one copy of the code (instruction-cache footprint; see fpipe::epi_half_rt)
-inline bool epi_roll_enabled() {
-  static int on = -1;
-  if (on < 0) { const char* e = getenv("SCNERF_EPI_ROLL"); on = e ? (atoi(e) != 0) : 0; }
-  return on != 0;
+inline int epi_roll_level() {        // 0 off (default), 1 rolled epilogue, 2 + rolled MMA issue loop (split-bf16 forward)
+  static int lv = -1;
+  if (lv < 0) { const char* e = getenv("SCNERF_EPI_ROLL"); lv = e ? std::max(0, std::min(2, atoi(e))) : 0; }
+  return lv;
 }
+inline bool epi_roll_enabled() { return epi_roll_level() > 0; }
 template <int XS = 4>
 inline const eng::Plan& pipe_plan_host() {
   static eng::Plan P = fpipe::make_plan<3, XS>();   // (slab order, sizes and image offsets do not depend on NSPLIT)
@@ -398,9 +399,11 @@ inline int pipe_plan_init() {
   SCNERF_CUDA(cudaFuncSetAttribute((fpipe::field_fwd_pipe_kernel<3, 6>), cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    fpipe::Cfg<3, 6>::SMEM_BYTES));
   if (epi_roll_enabled()) {     // experimental builds: touched only when asked for
-    SCNERF_CUDA(cudaFuncSetAttribute((fpipe::field_fwd_pipe_kernel<1, 4, true>), cudaFuncAttributeMaxDynamicSharedMemorySize,
+    SCNERF_CUDA(cudaFuncSetAttribute((fpipe::field_fwd_pipe_kernel<1, 4, 1>), cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      fpipe::Cfg<1, 4>::SMEM_BYTES));
-    SCNERF_CUDA(cudaFuncSetAttribute((fpipe::field_fwd_pipe_kernel<3, 4, true>), cudaFuncAttributeMaxDynamicSharedMemorySize,
+    SCNERF_CUDA(cudaFuncSetAttribute((fpipe::field_fwd_pipe_kernel<3, 4, 1>), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     fpipe::Cfg<3, 4>::SMEM_BYTES));
+    SCNERF_CUDA(cudaFuncSetAttribute((fpipe::field_fwd_pipe_kernel<3, 4, 2>), cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      fpipe::Cfg<3, 4>::SMEM_BYTES));
   }
   if (dev < 64) done[dev] = true;
@@ -493,8 +496,10 @@ inline int field_tc_fwd_impl(const scnerf_mlp& m, const float* rays, int ray_col
   }
   a.dbg = tc_dbg_ptr(); a.dbg_tiles = tc_dbg_tiles();
   int grid = std::min(device_sm_count(), a.num_tiles);
-  if (pipe && XS == 4 && epi_roll_enabled())
-    SCNERF_LAUNCH((fpipe::field_fwd_pipe_kernel<NSPLIT, 4, true>), grid, 320, (fpipe::Cfg<NSPLIT, 4>::SMEM_BYTES), stream, a);
+  if (pipe && XS == 4 && NSPLIT == 3 && epi_roll_level() >= 2)
+    SCNERF_LAUNCH((fpipe::field_fwd_pipe_kernel<3, 4, 2>), grid, 320, (fpipe::Cfg<3, 4>::SMEM_BYTES), stream, a);
+  else if (pipe && XS == 4 && epi_roll_enabled())
+    SCNERF_LAUNCH((fpipe::field_fwd_pipe_kernel<NSPLIT, 4, 1>), grid, 320, (fpipe::Cfg<NSPLIT, 4>::SMEM_BYTES), stream, a);
   else if (pipe) SCNERF_LAUNCH((fpipe::field_fwd_pipe_kernel<NSPLIT, XS>), grid, 320, (fpipe::Cfg<NSPLIT, XS>::SMEM_BYTES), stream, a);
   else SCNERF_LAUNCH((field_fused_fwd_kernel<NSPLIT, XS>), grid, 320, (Cfg<NSPLIT, XS>::SMEM_BYTES), stream, a);
   return 0;

@@ -247,6 +247,111 @@ __device__ __forceinline__ void mma_loop(const PCtx& c, int num_tiles) {
     mma_tile<K>(c, tp, it, std::make_index_sequence<K::PLAN.n_slabs>{});
 }
 
+// ---- rolled MMA issue loop (experimental, ROLL >= 2, split-bf16 / 3-D points only) -------------------------------------
+// Stages 1-4 and 6-8 issue the same 34 half-slabs (bias + 16 hidden K-slabs, twice); they differ in the parity of the P
+// buffer, of the stage barriers and in where the weight ring stands.  The rolled loop issues them from ONE unrolled copy
+// of a stage with those three as run-time values (one add / and per descriptor), instead of 7 x 34 unrolled steps: the
+// issue thread's straight-line code shrinks from ~160 KB to ~60 KB.  Stage boundaries fall on ring-group boundaries
+// because GROUP = 2 and every stage has an even slab count.
+template <class K> struct StdStage {
+  static constexpr int FIRST = [] { int i = 0; while (K::PLAN.slab[i].stage != 1) ++i; return i; }();   // first slab of stage 1
+  static constexpr int COUNT = [] { int n = 0; for (int i = 0; i < K::PLAN.n_slabs; ++i) n += K::PLAN.slab[i].stage == 1; return n; }();
+  __host__ __device__ static constexpr int first_of(int st) { int i = 0; while (K::PLAN.slab[i].stage != st) ++i; return i; }
+  __host__ __device__ static constexpr bool same_as_stage1(int st) {
+    const int f = first_of(st);
+    for (int i = 0; i < COUNT; ++i) {
+      const eng::SlabDef a = K::PLAN.slab[FIRST + i], b = K::PLAN.slab[f + i];
+      if (b.stage != st || a.n != b.n || a.acc_col != b.acc_col || a.a_kind != b.a_kind || a.flags != b.flags || a.pad != b.pad) return false;
+    }
+    return K::PLAN.slab[f + COUNT].stage != st;
+  }
+  static_assert(FIRST % K::GROUP == 0 && COUNT % K::GROUP == 0, "standard stages must start and end on ring-group boundaries");
+  static_assert(same_as_stage1(2) && same_as_stage1(3) && same_as_stage1(4) && same_as_stage1(6) && same_as_stage1(7) && same_as_stage1(8),
+                "stages 1-4 and 6-8 must issue the same slab sequence");
+};
+template <class K, int I1>
+__device__ __forceinline__ void mma_step_std(const PCtx& c, uint32_t tp, int tile_iter, int st, uint32_t g0) {
+  constexpr eng::SlabDef d = K::PLAN.slab[StdStage<K>::FIRST + I1];       // stage 1's slab as the template
+  constexpr bool SPLIT = K::NSPLIT == 3;
+  constexpr int g = I1 / K::GROUP;
+  constexpr bool wraps_odd = (((K::PLAN.n_slabs / K::GROUP) / K::NSLOT) & 1) != 0;
+  constexpr uint32_t in_slot = eng::group_bytes<K>(StdStage<K>::FIRST + g * K::GROUP, StdStage<K>::FIRST + I1);
+  const uint32_t G = g0 + (uint32_t)g;                                    // ring group number inside the tile
+  const uint32_t idx = G % (uint32_t)K::NSLOT, wrap = G / (uint32_t)K::NSLOT;
+  const uint32_t par = (uint32_t)st & 1u;
+  if constexpr ((d.flags & eng::F_STAGE_BEGIN) != 0) {
+    eng::mbar_wait_a(c.aq_addr, par);
+    tc::tc_fence_after();
+    stamp(c, tile_iter, st, 0);
+  }
+  if constexpr ((d.flags & eng::F_WAIT_Q1) != 0) { eng::mbar_wait_a(c.aq_addr + 8, par); tc::tc_fence_after(); }
+  if constexpr ((d.flags & eng::F_WAIT_Q2) != 0) { eng::mbar_wait_a(c.aq_addr + 16, par); tc::tc_fence_after(); stamp(c, tile_iter, st, 1); }
+  if constexpr ((d.flags & eng::F_WAIT_Q3) != 0) { eng::mbar_wait_a(c.aq_addr + 24, par); tc::tc_fence_after(); }
+  if constexpr (I1 % K::GROUP == 0) {
+    eng::mbar_wait_a(c.e.full_addr + idx * 8, (wrap & 1u) ^ (wraps_odd ? tp : 0u));
+    tc::tc_fence_after();
+  }
+  constexpr uint32_t idesc = tc::idesc_bf16_f32(TILE_M, d.n);
+  constexpr uint32_t LBO_B = (uint32_t)d.n * 16u;
+  const uint32_t slot = c.e.ring_addr + idx * (uint32_t)K::SLOT_BYTES + in_slot;
+  const uint64_t b_hi = eng::desc_at<LBO_B, 128>(slot);
+  const uint64_t b_lo = eng::desc_at<LBO_B, 128>(slot + (uint32_t)d.n * 32u);
+  const uint32_t acc = c.e.tmem_acc + d.acc_col;
+  constexpr uint32_t first = (d.flags & eng::F_ZERO_ACC) ? 0u : 1u;
+  if constexpr (d.a_kind == eng::A_MIX) {
+    // stage 1 reads P1 (columns 64.., lo image 32768..): slabs of the P half follow the stage's parity, Q slabs do not
+    constexpr bool in_p = d.a_off < 128;
+    const uint32_t a_col = in_p ? (uint32_t)(d.a_off - 64) + par * 64u : (uint32_t)d.a_off;
+    const uint32_t a_lo = in_p ? (uint32_t)d.a_lo_delta * 16u - 32768u + par * 32768u : (uint32_t)d.a_lo_delta * 16u;
+    tc::mma_ts(acc, c.e.tmem_ahi + a_col, b_hi, idesc, first);
+    if constexpr (SPLIT) {
+      tc::mma_ss(acc, eng::desc_at<2048, 128>(c.smem_lo + a_lo), b_hi, idesc, 1);
+      tc::mma_ts(acc, c.e.tmem_ahi + a_col, b_lo, idesc, 1);
+    }
+  } else {
+    const uint32_t a_addr = c.e.smem_a + (uint32_t)d.a_off * 16u;
+    const uint64_t a_hi = eng::desc_at<2048, 128>(a_addr);
+    tc::mma_ss(acc, a_hi, b_hi, idesc, first);
+    if constexpr (SPLIT) {
+      if constexpr ((d.flags & eng::F_HI_ONLY_A) == 0)
+        tc::mma_ss(acc, eng::desc_at<2048, 128>(a_addr + (uint32_t)d.a_lo_delta * 16u), b_hi, idesc, 1);
+      tc::mma_ss(acc, a_hi, b_lo, idesc, 1);
+    }
+  }
+  if constexpr (I1 % K::GROUP == K::GROUP - 1) eng::commit_a(c.e.empty_addr + idx * 8);
+  if constexpr ((d.flags & eng::F_STAGE_END) != 0) {
+    eng::commit_a(c.accf_addr + d.pad * 8);
+    stamp(c, tile_iter, st, 2 + d.pad);
+  }
+}
+template <class K, size_t... Is>
+__device__ __forceinline__ void mma_std_stage(const PCtx& c, uint32_t tp, int tile_iter, int st, uint32_t g0, std::index_sequence<Is...>) {
+  (mma_step_std<K, (int)Is>(c, tp, tile_iter, st, g0), ...);
+}
+template <class K, int I0, size_t... Is>
+__device__ __forceinline__ void mma_range(const PCtx& c, uint32_t tp, int tile_iter, std::index_sequence<Is...>) {
+  (mma_step<K, I0 + (int)Is>(c, tp, tile_iter), ...);
+}
+template <class K>
+__device__ __forceinline__ void mma_loop_rolled(const PCtx& c, int num_tiles) {
+  using SS = StdStage<K>;
+  constexpr int F1 = SS::FIRST, N1 = SS::COUNT, F5 = SS::first_of(5), F6 = SS::first_of(6), F9 = SS::first_of(9);
+  static_assert(F5 == F1 + 4 * N1 && F9 == F6 + 3 * N1, "stages 1-4 and 6-8 are contiguous runs of standard stages");
+  uint32_t tp = 0;
+  int it = 0;
+  for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, tp ^= 1u, ++it) {
+    mma_range<K, 0>(c, tp, it, std::make_index_sequence<F1>{});                       // stage 0
+#pragma unroll 1
+    for (int st = 1; st <= 4; ++st)
+      mma_std_stage<K>(c, tp, it, st, (uint32_t)((F1 + (st - 1) * N1) / K::GROUP), std::make_index_sequence<N1>{});
+    mma_range<K, F5>(c, tp, it, std::make_index_sequence<F6 - F5>{});                 // stage 5 (PE(pts) + hidden)
+#pragma unroll 1
+    for (int st = 6; st <= 8; ++st)
+      mma_std_stage<K>(c, tp, it, st, (uint32_t)((F6 + (st - 6) * N1) / K::GROUP), std::make_index_sequence<N1>{});
+    mma_range<K, F9>(c, tp, it, std::make_index_sequence<K::PLAN.n_slabs - F9>{});    // view layer + padding
+  }
+}
+
 // Epilogue of N-half H of stage S for this warp's columns (compile-time stage parameters).
 // 256-wide stages: the N-half is handed over as two 64-column quarters; chunk cc of warp `half` (0/1) is
 // columns [H*128 + cc*64 + half*32, +32).  View layer (N-halves of 64): one chunk, [H*64 + half*32, +32).
@@ -409,7 +514,7 @@ __device__ __forceinline__ void epi_tile(const Args& a, const float* cst, const 
     epi_half<NSPLIT, (int)Ss, 1>(a, cst, c, lo_area, lane_base, half, row, tile, p, valid, alpha, rgb, tile_iter)), ...);
 }
 
-template <int NSPLIT, int XS = 4, bool ROLL = false>
+template <int NSPLIT, int XS = 4, int ROLL = 0>     // ROLL: 0 fully unrolled (default), 1 rolled epilogue, 2 + rolled MMA issue loop
 __global__ void __launch_bounds__(320, 1) field_fwd_pipe_kernel(const __grid_constant__ Args a) {
   using C = Cfg<NSPLIT, XS>;
   using L = ALay<NSPLIT, XS>;
@@ -458,7 +563,10 @@ __global__ void __launch_bounds__(320, 1) field_fwd_pipe_kernel(const __grid_con
   if (warp == 0) {
     if (lane == 0) eng::producer_loop<C>(ctx.e, a.wimg, a.num_tiles);
   } else if (warp == 1) {
-    if (lane == 0) mma_loop<C>(ctx, a.num_tiles);
+    if (lane == 0) {
+      if constexpr (ROLL >= 2 && NSPLIT == 3 && XS == 4) mma_loop_rolled<C>(ctx, a.num_tiles);
+      else mma_loop<C>(ctx, a.num_tiles);
+    }
   } else {
     // ===================== epilogue: 8 warps, 2 per TMEM lane quadrant =============================
     const int quad = warp & 3, half = (warp - 2) >> 2;
@@ -525,7 +633,7 @@ __global__ void __launch_bounds__(320, 1) field_fwd_pipe_kernel(const __grid_con
       tc::tc_fence_before();        // the previous tile's accumulator loads are complete (ordered before the arrive)
       for (int i = 0; i < 4; ++i) tc::mbar_arrive(&aq[i]);
       float alpha = 0.f, rgb[3] = {0.f, 0.f, 0.f};
-      if constexpr (ROLL) {
+      if constexpr (ROLL >= 1) {
 #pragma unroll 1
         for (int S = 0; S < 7; ++S) {
           epi_half_rt<NSPLIT, 0>(a, ctx, lo_area, lane_base, half, row, tile, p, valid, tile_iter, S);
