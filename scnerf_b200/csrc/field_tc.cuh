@@ -582,9 +582,13 @@ inline int dpipe_plan_init() {
   SCNERF_CUDA(cudaFuncSetAttribute(dpipe::field_dgrad_pipe_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    dpipe::Cfg<3>::SMEM_BYTES));
   if (epi_roll_enabled()) {     // experimental builds: touched only when asked for
-    SCNERF_CUDA(cudaFuncSetAttribute((dpipe::field_dgrad_pipe_kernel<1, true>), cudaFuncAttributeMaxDynamicSharedMemorySize,
+    SCNERF_CUDA(cudaFuncSetAttribute((dpipe::field_dgrad_pipe_kernel<1, 1>), cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      dpipe::Cfg<1>::SMEM_BYTES));
-    SCNERF_CUDA(cudaFuncSetAttribute((dpipe::field_dgrad_pipe_kernel<3, true>), cudaFuncAttributeMaxDynamicSharedMemorySize,
+    SCNERF_CUDA(cudaFuncSetAttribute((dpipe::field_dgrad_pipe_kernel<3, 1>), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     dpipe::Cfg<3>::SMEM_BYTES));
+    SCNERF_CUDA(cudaFuncSetAttribute((dpipe::field_dgrad_pipe_kernel<1, 2>), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     dpipe::Cfg<1>::SMEM_BYTES));
+    SCNERF_CUDA(cudaFuncSetAttribute((dpipe::field_dgrad_pipe_kernel<3, 2>), cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      dpipe::Cfg<3>::SMEM_BYTES));
   }
   if (dev < 64) done[dev] = true;
@@ -631,8 +635,11 @@ inline int field_tc_bwd_impl(const scnerf_mlp& m, const scnerf_mlp& g, const flo
   a.g_raw = g_raw; a.wimg = G.wimg; a.cbuf = B.tc_cbuf;
   for (int i = 0; i < 8; ++i) a.out_dz[i] = G.dz[i];
   a.relu_bits = I.relu_bits; a.out_dfeat = G.dfeat; a.out_dzv = G.dzv; a.g_pts = G.g_pts; a.g_vd = G.g_vd;
-  if (dp && epi_roll_enabled())
-    SCNERF_LAUNCH((dpipe::field_dgrad_pipe_kernel<NSPLIT, true>), std::min(device_sm_count(), T), 320,
+  if (dp && epi_roll_level() >= 2)
+    SCNERF_LAUNCH((dpipe::field_dgrad_pipe_kernel<NSPLIT, 2>), std::min(device_sm_count(), T), 320,
+                  (dpipe::Cfg<NSPLIT>::SMEM_BYTES), stream, a);
+  else if (dp && epi_roll_enabled())
+    SCNERF_LAUNCH((dpipe::field_dgrad_pipe_kernel<NSPLIT, 1>), std::min(device_sm_count(), T), 320,
                   (dpipe::Cfg<NSPLIT>::SMEM_BYTES), stream, a);
   else if (dp) SCNERF_LAUNCH((dpipe::field_dgrad_pipe_kernel<NSPLIT>), std::min(device_sm_count(), T), 320,
                              (dpipe::Cfg<NSPLIT>::SMEM_BYTES), stream, a);

@@ -105,6 +105,7 @@ template <int NSPLIT_> struct Cfg {
   static constexpr int NSLOT = NSPLIT_ == 1 ? 6 : 4;
   static constexpr int SLOT_BYTES = 16384;
   static_assert(PLAN.n_slabs % (GROUP * NSLOT) == 0, "ring size must divide the slab-group count");
+  static constexpr int STD_A0 = 1, STD_A1 = 3, STD_B0 = 5, STD_B1 = 8;   // runs of identical stages (rolled MMA issue loop)
   static constexpr int LO_BYTES = NSPLIT_ == 3 ? 3 * 32768 : 0;
   static constexpr int OFF_RING = 0;
   static constexpr int OFF_LO = NSLOT * SLOT_BYTES;
@@ -300,7 +301,7 @@ __device__ __forceinline__ void epi_tile(const Args& a, const float* cst, const 
     epi_half<NSPLIT, (int)Ts, 1>(a, cst, c, lo_area, gx_s, out_s, lane_base, half, row, tile, p, valid, gr)), ...);
 }
 
-template <int NSPLIT, bool ROLL = false>
+template <int NSPLIT, int ROLL = 0>     // ROLL: 0 fully unrolled (default), 1 rolled epilogue, 2 + rolled MMA issue loop
 __global__ void __launch_bounds__(320, 1) field_dgrad_pipe_kernel(const __grid_constant__ Args a) {
   using C = Cfg<NSPLIT>;
   constexpr bool SPLIT = NSPLIT == 3;
@@ -342,7 +343,10 @@ __global__ void __launch_bounds__(320, 1) field_dgrad_pipe_kernel(const __grid_c
   if (warp == 0) {
     if (lane == 0) eng::producer_loop<C>(ctx.e, a.wimg, a.num_tiles);
   } else if (warp == 1) {
-    if (lane == 0) fpipe::mma_loop<C>(ctx, a.num_tiles);
+    if (lane == 0) {
+      if constexpr (ROLL >= 2) fpipe::mma_loop_rolled<C>(ctx, a.num_tiles);
+      else fpipe::mma_loop<C>(ctx, a.num_tiles);
+    }
   } else {
     const int quad = warp & 3, half = (warp - 2) >> 2;
     const int row = quad * 32 + lane;
@@ -381,7 +385,7 @@ __global__ void __launch_bounds__(320, 1) field_dgrad_pipe_kernel(const __grid_c
       tc::tmem_st_wait();
       tc::tc_fence_before();
       for (int i = 0; i < 4; ++i) tc::mbar_arrive(&aq[i]);
-      if constexpr (ROLL) {
+      if constexpr (ROLL >= 1) {
         epi_half<NSPLIT, 0, 0>(a, cst, ctx, lo_area, gx_s, out_s, lane_base, half, row, tile, p, valid, gr);
         epi_half<NSPLIT, 0, 1>(a, cst, ctx, lo_area, gx_s, out_s, lane_base, half, row, tile, p, valid, gr);
         epi_half<NSPLIT, 1, 0>(a, cst, ctx, lo_area, gx_s, out_s, lane_base, half, row, tile, p, valid, gr);

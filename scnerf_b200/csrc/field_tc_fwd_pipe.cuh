@@ -147,6 +147,7 @@ template <int NSPLIT_, int XS_ = 4> struct Cfg {
   static constexpr int NSLOT = NSPLIT_ == 1 ? 6 : (XS_ == 4 ? 4 : 3);
   static constexpr int SLOT_BYTES = 16384;
   static_assert(PLAN.n_slabs % (GROUP * NSLOT) == 0, "ring size must divide the slab-group count");
+  static constexpr int STD_A0 = 1, STD_A1 = 4, STD_B0 = 6, STD_B1 = 8;   // runs of identical stages (rolled MMA issue loop)
   static constexpr int LO_BYTES = NSPLIT_ == 3 ? 3 * 32768 : 0;
   static constexpr int OFF_RING = 0;
   static constexpr int OFF_A = NSLOT * SLOT_BYTES;
@@ -253,21 +254,34 @@ __device__ __forceinline__ void mma_loop(const PCtx& c, int num_tiles) {
 // of a stage with those three as run-time values (one add / and per descriptor), instead of 7 x 34 unrolled steps: the
 // issue thread's straight-line code shrinks from ~160 KB to ~60 KB.  Stage boundaries fall on ring-group boundaries
 // because GROUP = 2 and every stage has an even slab count.
+// K::STD_A0..STD_A1 and K::STD_B0..STD_B1 are the two runs of standard stages; K::STD_A0 is the template.
 template <class K> struct StdStage {
-  static constexpr int FIRST = [] { int i = 0; while (K::PLAN.slab[i].stage != 1) ++i; return i; }();   // first slab of stage 1
-  static constexpr int COUNT = [] { int n = 0; for (int i = 0; i < K::PLAN.n_slabs; ++i) n += K::PLAN.slab[i].stage == 1; return n; }();
-  __host__ __device__ static constexpr int first_of(int st) { int i = 0; while (K::PLAN.slab[i].stage != st) ++i; return i; }
-  __host__ __device__ static constexpr bool same_as_stage1(int st) {
+  __host__ __device__ static constexpr int first_of(int st) { int i = 0; while (i < K::PLAN.n_slabs && K::PLAN.slab[i].stage != st) ++i; return i; }
+  __host__ __device__ static constexpr int count_of(int st) { int n = 0; for (int i = 0; i < K::PLAN.n_slabs; ++i) n += K::PLAN.slab[i].stage == st; return n; }
+  static constexpr int TEMPLATE = K::STD_A0;
+  static constexpr int FIRST = first_of(TEMPLATE);
+  static constexpr int COUNT = count_of(TEMPLATE);
+  __host__ __device__ static constexpr bool same_as_template(int st) {
     const int f = first_of(st);
+    if (count_of(st) != COUNT) return false;
     for (int i = 0; i < COUNT; ++i) {
       const eng::SlabDef a = K::PLAN.slab[FIRST + i], b = K::PLAN.slab[f + i];
       if (b.stage != st || a.n != b.n || a.acc_col != b.acc_col || a.a_kind != b.a_kind || a.flags != b.flags || a.pad != b.pad) return false;
+      // operand addresses may differ only by the parity of the P buffer
+      const int dp = ((st & 1) - (TEMPLATE & 1));
+      if (a.a_kind == eng::A_MIX && a.a_off < 128 && (b.a_off != a.a_off + dp * 64 || b.a_lo_delta * 16 != a.a_lo_delta * 16 + dp * 32768)) return false;
+      if ((a.a_kind != eng::A_MIX || a.a_off >= 128) && (b.a_off != a.a_off || b.a_lo_delta != a.a_lo_delta)) return false;
     }
-    return K::PLAN.slab[f + COUNT].stage != st;
+    return true;
   }
-  static_assert(FIRST % K::GROUP == 0 && COUNT % K::GROUP == 0, "standard stages must start and end on ring-group boundaries");
-  static_assert(same_as_stage1(2) && same_as_stage1(3) && same_as_stage1(4) && same_as_stage1(6) && same_as_stage1(7) && same_as_stage1(8),
-                "stages 1-4 and 6-8 must issue the same slab sequence");
+  __host__ __device__ static constexpr bool all_same() {
+    for (int st = K::STD_A0; st <= K::STD_A1; ++st) if (!same_as_template(st) || first_of(st) != FIRST + (st - K::STD_A0) * COUNT) return false;
+    for (int st = K::STD_B0; st <= K::STD_B1; ++st) if (!same_as_template(st) || first_of(st) != first_of(K::STD_B0) + (st - K::STD_B0) * COUNT) return false;
+    return true;
+  }
+  static_assert(FIRST % K::GROUP == 0 && COUNT % K::GROUP == 0 && first_of(K::STD_B0) % K::GROUP == 0,
+                "standard stages must start and end on ring-group boundaries");
+  static_assert(all_same(), "the standard stages must issue the same slab sequence in contiguous runs");
 };
 template <class K, int I1>
 __device__ __forceinline__ void mma_step_std(const PCtx& c, uint32_t tp, int tile_iter, int st, uint32_t g0) {
@@ -299,10 +313,11 @@ __device__ __forceinline__ void mma_step_std(const PCtx& c, uint32_t tp, int til
   const uint32_t acc = c.e.tmem_acc + d.acc_col;
   constexpr uint32_t first = (d.flags & eng::F_ZERO_ACC) ? 0u : 1u;
   if constexpr (d.a_kind == eng::A_MIX) {
-    // stage 1 reads P1 (columns 64.., lo image 32768..): slabs of the P half follow the stage's parity, Q slabs do not
+    // slabs of the P half follow the stage's parity (the template stage's is compiled in), Q slabs do not
     constexpr bool in_p = d.a_off < 128;
-    const uint32_t a_col = in_p ? (uint32_t)(d.a_off - 64) + par * 64u : (uint32_t)d.a_off;
-    const uint32_t a_lo = in_p ? (uint32_t)d.a_lo_delta * 16u - 32768u + par * 32768u : (uint32_t)d.a_lo_delta * 16u;
+    constexpr uint32_t tpar = (uint32_t)(StdStage<K>::TEMPLATE & 1);
+    const uint32_t a_col = in_p ? (uint32_t)d.a_off - tpar * 64u + par * 64u : (uint32_t)d.a_off;
+    const uint32_t a_lo = in_p ? (uint32_t)d.a_lo_delta * 16u - tpar * 32768u + par * 32768u : (uint32_t)d.a_lo_delta * 16u;
     tc::mma_ts(acc, c.e.tmem_ahi + a_col, b_hi, idesc, first);
     if constexpr (SPLIT) {
       tc::mma_ss(acc, eng::desc_at<2048, 128>(c.smem_lo + a_lo), b_hi, idesc, 1);
@@ -335,20 +350,20 @@ __device__ __forceinline__ void mma_range(const PCtx& c, uint32_t tp, int tile_i
 template <class K>
 __device__ __forceinline__ void mma_loop_rolled(const PCtx& c, int num_tiles) {
   using SS = StdStage<K>;
-  constexpr int F1 = SS::FIRST, N1 = SS::COUNT, F5 = SS::first_of(5), F6 = SS::first_of(6), F9 = SS::first_of(9);
-  static_assert(F5 == F1 + 4 * N1 && F9 == F6 + 3 * N1, "stages 1-4 and 6-8 are contiguous runs of standard stages");
+  constexpr int FA = SS::FIRST, N1 = SS::COUNT, FB = SS::first_of(K::STD_B0);
+  constexpr int EA = FA + (K::STD_A1 - K::STD_A0 + 1) * N1, EB = FB + (K::STD_B1 - K::STD_B0 + 1) * N1;
   uint32_t tp = 0;
   int it = 0;
   for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, tp ^= 1u, ++it) {
-    mma_range<K, 0>(c, tp, it, std::make_index_sequence<F1>{});                       // stage 0
+    mma_range<K, 0>(c, tp, it, std::make_index_sequence<FA>{});                        // stages before the first run
 #pragma unroll 1
-    for (int st = 1; st <= 4; ++st)
-      mma_std_stage<K>(c, tp, it, st, (uint32_t)((F1 + (st - 1) * N1) / K::GROUP), std::make_index_sequence<N1>{});
-    mma_range<K, F5>(c, tp, it, std::make_index_sequence<F6 - F5>{});                 // stage 5 (PE(pts) + hidden)
+    for (int st = K::STD_A0; st <= K::STD_A1; ++st)
+      mma_std_stage<K>(c, tp, it, st, (uint32_t)((FA + (st - K::STD_A0) * N1) / K::GROUP), std::make_index_sequence<N1>{});
+    mma_range<K, EA>(c, tp, it, std::make_index_sequence<FB - EA>{});                  // the odd stage between the runs
 #pragma unroll 1
-    for (int st = 6; st <= 8; ++st)
-      mma_std_stage<K>(c, tp, it, st, (uint32_t)((F6 + (st - 6) * N1) / K::GROUP), std::make_index_sequence<N1>{});
-    mma_range<K, F9>(c, tp, it, std::make_index_sequence<K::PLAN.n_slabs - F9>{});    // view layer + padding
+    for (int st = K::STD_B0; st <= K::STD_B1; ++st)
+      mma_std_stage<K>(c, tp, it, st, (uint32_t)((FB + (st - K::STD_B0) * N1) / K::GROUP), std::make_index_sequence<N1>{});
+    mma_range<K, EB>(c, tp, it, std::make_index_sequence<K::PLAN.n_slabs - EB>{});     // the tail stages
   }
 }
 
