@@ -1,5 +1,5 @@
 """CPU emulation: how much accuracy the weight-gradient GEMM dW = dZ^T X loses if the tile images drop an operand half
-(float64 sums of rounded operands, 60 K samples of the test network).  Quoted in DESIGN.md section 9."""
+or store the lo halves as fp8 (float64 sums of rounded operands, 60 K samples of the test network).  Quoted in DESIGN.md section 9."""
 import sys, os, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from tests.util import build_modules
@@ -58,3 +58,20 @@ for i in (1, 3, 5, 7):
     x1 = dh.t() @ xh
     m = exact.abs().max()
     print(f"  {i}   : {((x3 - exact).abs().max() / m):.2e}   {((x2 - exact).abs().max() / m):.2e}   {((x1 - exact).abs().max() / m):.2e}    (max |dW| {m:.3e}, N = {N} samples)")
+print("compact images: lo half stored as fp8 (e4m3 / e5m2), expanded to bf16 before the MMA; same three MMAs")
+def f8(t, dt):
+    return t.float().to(dt).float().double()
+for dt, name in ((torch.float8_e4m3fn, "e4m3"), (torch.float8_e5m2, "e5m2")):
+    for i in (1, 5, 7):
+        dZ = pre[i].grad; Xl = acts[i]
+        exact = dZ.t() @ Xl
+        dh, dl = split(dZ); xh, xl = split(Xl)
+        # fp8 has a narrow exponent range: scale lo by 2^k per tensor so that its max sits near the top (a per-image scale would do the same)
+        def q(l):
+            sc = 2.0 ** torch.floor(torch.log2(l.abs().max() / 200.0))
+            return f8(l / sc, dt) * sc
+        xl8, dl8 = q(xl), q(dl)
+        m = exact.abs().max()
+        a = dh.t() @ xh + dl.t() @ xh + dh.t() @ xl8
+        b = dh.t() @ xh + dl8.t() @ xh + dh.t() @ xl8
+        print(f"  {name} layer {i}: X lo in fp8 {((a - exact).abs().max() / m):.2e}   X lo and dZ lo in fp8 {((b - exact).abs().max() / m):.2e}")
