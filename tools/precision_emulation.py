@@ -49,3 +49,34 @@ for fa, fw, name in (("bf16", "bf16", "bf16 single pass (1 MMA)"), ("bf16x2", "b
     e = (out - ref).abs().max() / ref.abs().max()
     er = (torch.sigmoid(out[:, :3]) - torch.sigmoid(ref[:, :3])).abs().max()
     print(f"{name:70s}: raw rel-to-max err {e:.2e}   max |d sigmoid(rgb)| {er:.2e}")
+
+# ---- correction terms (lo x hi, hi x lo) as FP8 MMAs (2x rate): main term bf16 -----------------------------------
+def bf(t): return t.float().bfloat16().double()
+def f8(t, dt=torch.float8_e4m3fn):
+    sc = 2.0 ** torch.floor(torch.log2(t.abs().max().clamp_min(1e-30) / 200.0))
+    return (t / sc).float().to(dt).float().double() * sc
+def mm(a, W, mode):
+    ah, wh = bf(a), bf(W); al, wl = bf(a - ah), bf(W - wh)
+    if mode == "exact": return a @ W.t()
+    if mode == "x3": return ah @ wh.t() + al @ wh.t() + ah @ wl.t()
+    if mode == "fp8corr": return ah @ wh.t() + f8(al) @ f8(wh).t() + f8(ah) @ f8(wl).t()
+    if mode == "fp8corr_rowscale":   # per-row scales for the activation operands (one scale per sample)
+        def f8r(t):
+            sc = 2.0 ** torch.floor(torch.log2(t.abs().amax(-1, keepdim=True).clamp_min(1e-30) / 200.0))
+            return (t / sc).float().to(torch.float8_e4m3fn).float().double() * sc
+        return ah @ wh.t() + f8r(al) @ f8(wh).t() + f8r(ah) @ f8(wl).t()
+def forward(mode):
+    h = X
+    for i in range(8):
+        h = torch.relu(mm(h, sd[f"pts_linears.{i}.weight"], mode) + sd[f"pts_linears.{i}.bias"])
+        if i == 4: h = torch.cat([X, h], -1)
+    alpha = h @ sd["alpha_linear.weight"].t() + sd["alpha_linear.bias"]
+    feat = mm(h, sd["feature_linear.weight"], mode) + sd["feature_linear.bias"]
+    hv = torch.relu(mm(torch.cat([feat, V], -1), sd["views_linears.0.weight"], mode) + sd["views_linears.0.bias"])
+    rgb = hv @ sd["rgb_linear.weight"].t() + sd["rgb_linear.bias"]
+    return torch.cat([rgb, alpha], -1)
+ref = forward("exact")
+print("split-bf16 with the two correction terms in fp8 (e4m3):")
+for mode in ("x3", "fp8corr", "fp8corr_rowscale"):
+    out = forward(mode)
+    print(f"{mode:18s}: raw rel-to-max err {((out - ref).abs().max() / ref.abs().max()):.2e}   max |d sigmoid(rgb)| {((torch.sigmoid(out[:, :3]) - torch.sigmoid(ref[:, :3])).abs().max()):.2e}")
