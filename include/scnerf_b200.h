@@ -79,7 +79,10 @@ int scnerf_camera_matrices(const scnerf_camera* cam, float* K_out, float* E_out,
  *   :75-90   get_rays_kps_no_camera         (cam == NULL, focal given)
  *   :5-23    get_rays_full_image_no_camera  (cam == NULL, kps == NULL)
  * Pose source (exactly one): idx[N] (per-ray camera index), idx_scalar >= 0, or `extrinsic`
- * ([4,4], or [N,4,4] when extrinsic_per_ray).  kps is [N,2] int64 (x, y). */
+ * ([4,4], or [N,4,4] when extrinsic_per_ray).  kps is [N,2] int64 (x, y); sub-pixel keypoints (SIFT / SuperGlue
+ * matches fed to the PRD loss) come as kps_f32 [N,2] float instead: the direction uses the float value
+ * (get_rays.py:112-123 `kps_list_expand.float()`), the ray_o / ray_d residual lookup its truncation (`.long()`, :134,140).
+ * A per-ray idx outside [0, n_cams) yields NaN rays (forward) and contributes no gradient (backward). */
 typedef struct scnerf_raygen_args {
   const scnerf_camera* cam; /* NULL = fixed pinhole with `focal`, H, W below */
   float focal;
@@ -90,6 +93,7 @@ typedef struct scnerf_raygen_args {
   const float* extrinsic;
   int32_t extrinsic_per_ray;
   int64_t N;
+  const float* kps_f32; /* [N,2] float (x, y); used when kps == NULL */
 } scnerf_raygen_args;
 
 int scnerf_raygen_fwd(const scnerf_raygen_args* a, float* rays_o, float* rays_d, void* stream);

@@ -158,7 +158,9 @@ class Camera:
 
 
 def rays_pixels_camera(H, W, cam: Camera, kps, idx=None, extrinsic=None):
-    """NeRF/get_rays.py:93-148.  kps is (x, y) int64; exactly one of idx / extrinsic."""
+    """NeRF/get_rays.py:93-148.  kps is (x, y), int64 pixels or float sub-pixel keypoints: the direction uses
+    ``kps.float()`` (:112-123), the ray_o / ray_d residual lookup ``kps.long()`` (:134,140).  Exactly one of idx /
+    extrinsic."""
     assert (idx is None) != (extrinsic is None)
     dtype = cam.intrinsics_initial.dtype
     pix = torch.stack([kps[:, 0], kps[:, 1], torch.ones_like(kps[:, 0])], -1).to(dtype)
@@ -172,7 +174,8 @@ def rays_pixels_camera(H, W, cam: Camera, kps, idx=None, extrinsic=None):
     else:
         rays_d = (dirs[:, None, :] * c2w[:3, :3]).sum(-1)               # :131
         rays_o = c2w[:3, 3].expand(rays_d.shape)
-    flat = kps[:, 1] * W + kps[:, 0]
+    kl = kps.long()
+    flat = kl[:, 1] * W + kl[:, 0]
     rays_o = rays_o + cam.ray_o_field()[flat]                           # :134-138
     rays_d = rays_d + cam.ray_d_field()[flat]                           # :140-145
     rays_d = rays_d / (rays_d.norm(dim=1)[:, None] + 1e-10)             # :146
@@ -422,6 +425,23 @@ def train_step(cam: Camera, P_coarse, P_fine, kps, idx, target, H, W, N_samples,
     if "rgb0" in ret:
         loss = loss + img2mse(ret["rgb0"], target)
     return loss, ret, rays
+
+
+def c3_train_step(cam: Camera, P_coarse, P_fine, kps, idx, target, H, W, N_samples, N_importance, matches, pair,
+                  prd_weight, threshold, **rand):
+    """BASELINE configs[2] forward, NeRF/run_nerf.py:482-598: the render loss of ``train_step`` plus
+    ``ray_dist_loss_weight`` x the projected-ray-distance loss on the sub-pixel matches (kps0, kps1) of the image
+    pair ``pair`` = (i, j), whose rays come from the same learnable camera (:535-548, :571-586).
+    -> (total, dict(loss_render, prd, n_match, rgb))."""
+    loss, ret, _ = train_step(cam, P_coarse, P_fine, kps, idx, target, H, W, N_samples, N_importance, **rand)
+    kps0, kps1 = matches
+    i, j = pair
+    rays_i = rays_pixels_camera(H, W, cam, kps0, idx=i)
+    rays_j = rays_pixels_camera(H, W, cam, kps1, idx=j)
+    E2 = cam.extrinsic()[[i, j]]
+    prd, n_match = proj_ray_dist_loss(kps0, kps1, rays_i, rays_j, cam.intrinsic(), E2, threshold, train=True,
+                                      method="NeRF")
+    return loss + prd_weight * prd, dict(loss_render=loss, prd=prd, n_match=n_match, rgb=ret["rgb_map"])
 
 
 def state_to_tensors(state, dtype=torch.float32, requires_grad=False):

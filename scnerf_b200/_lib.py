@@ -36,7 +36,7 @@ class CameraGrads(C.Structure):
 class RaygenArgs(C.Structure):
     _fields_ = [("cam", C.POINTER(Camera)), ("focal", C.c_float), ("H", C.c_int32), ("W", C.c_int32),
                 ("kps", vp), ("idx", vp), ("idx_scalar", C.c_int64), ("extrinsic", vp),
-                ("extrinsic_per_ray", C.c_int32), ("N", C.c_int64)]
+                ("extrinsic_per_ray", C.c_int32), ("N", C.c_int64), ("kps_f32", vp)]
 
 
 class RayprepArgs(C.Structure):

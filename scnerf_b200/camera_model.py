@@ -13,8 +13,9 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from . import _lib
+from .camera_utils import *  # noqa: F401,F403  (the reference re-exports camera_utils here: model/camera_model.py:9)
 from .camera_utils import (get_44_rotation_matrix_from_33_rotation_matrix, intrinsic_param_to_K,
-                           ortho2rotation, rotation2orth)
+                           ortho2rotation, rotation2orth, to_pil_normalize)
 
 
 class CameraModel(nn.Module):
@@ -83,6 +84,28 @@ class CameraModel(nn.Module):
         """(K, c2w[idx]) (model/camera_model.py:192-206)."""
         E = self._extrinsic_of(self.extrinsics_initial[idx, None], self.extrinsics_noise[idx, None])
         return self.get_intrinsic(), E.squeeze()
+
+    def log_noises(self, gt_intrinsic, gt_extrinsic):
+        """Scalars / images the trainers push to wandb (model/camera_model.py:54-117): same keys.  Logging only."""
+        K = self.get_intrinsic()
+        scal = {"camera/intrinsic_noise_mean": K.abs().mean(), "camera/intrinsic_noise_std": K.abs().mean()}
+        for name, (r, c) in (("fx", (0, 0)), ("fy", (1, 1)), ("cx", (0, 2)), ("cy", (1, 2))):
+            scal["camera/" + name] = K[r][c]
+            scal["camera/" + name + "_err"] = (K[r][c] - gt_intrinsic[r][c]).abs()
+        imgs = {}
+        if hasattr(self, "extrinsics_noise"):
+            E = self.get_extrinsic()
+            scal["camera/extrinsic_noise_mean"] = E.abs().mean()
+            scal["camera/extrinsic_noise_std"] = E.abs().std()
+            scal["camera/extrinisic_err"] = (E - gt_extrinsic).abs().mean()
+        for tag, getter in (("ray_o_noise", self.get_ray_o_noise), ("ray_d_noise", self.get_ray_d_noise)):
+            if hasattr(self, tag):
+                f = getter()
+                scal[f"camera/{tag}_mean"], scal[f"camera/{tag}_std"] = f.abs().mean(), f.abs().std()
+                imgs[f"camera/{tag}"] = to_pil_normalize(f.reshape(self.H, self.W, 3))
+        if hasattr(self, "distortion_noise"):
+            scal["camera/k1"], scal["camera/k2"] = self.get_distortion()
+        return scal, imgs
 
     # ---- C-ABI view ------------------------------------------------------------------------------
     LEARNABLE = ("intrinsics_noise", "extrinsics_noise", "ray_o_noise", "ray_d_noise")

@@ -105,7 +105,7 @@ static int make_raygen_dev(const scnerf_raygen_args* a, RaygenDev& d) {
     SCNERF_CHECK_ARG(a->extrinsic, "raygen: fixed-pinhole variant needs an extrinsic matrix");
   }
   SCNERF_CHECK_ARG(d.H > 0 && d.W > 0, "raygen: bad image size %dx%d", d.H, d.W);
-  d.kps = a->kps; d.idx = a->idx; d.idx_scalar = a->idx_scalar;
+  d.kps = a->kps; d.kps_f = a->kps ? nullptr : a->kps_f32; d.idx = a->idx; d.idx_scalar = a->idx_scalar;
   d.extrinsic = a->extrinsic; d.extrinsic_per_ray = a->extrinsic_per_ray; d.N = a->N;
   if (!a->extrinsic) {
     // exactly one pose source (NeRF/get_rays.py:107-110)
@@ -438,6 +438,13 @@ static int composite_bwd_launch(const scnerf_render_cfg& cfg, const float* raw, 
   b.g_rgb = g_rgb; b.g_disp = g_disp; b.g_acc = g_acc; b.acc_saved = acc_saved; b.depth_saved = depth_saved;
   b.g_raw = g_raw; b.g_rays = d_rays; b.g_rays_cols = cfg.ray_cols;
   size_t smem = sizeof(float) * 2 * S * 4;
+  if (smem > 48 * 1024) {    // S > 1536: opt in to the large dynamic shared-memory carve-out (S <= 4096 -> 128 KB)
+    static bool opted = false;
+    if (!opted) {
+      SCNERF_CUDA(cudaFuncSetAttribute(composite_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 4096 * 4 * 4));
+      opted = true;
+    }
+  }
   SCNERF_LAUNCH(composite_bwd_kernel, (unsigned)cdiv(N, 4), 128, smem, stream, b);
   return 0;
 }

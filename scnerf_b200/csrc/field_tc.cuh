@@ -361,11 +361,12 @@ inline bool fwd_pipe_enabled() {
   if (on < 0) { const char* e = getenv("SCNERF_FWD_PIPE"); on = e ? (atoi(e) != 0) : 1; }
   return on != 0;
 }
-// Experimental (default off, not yet measured on hardware): SCNERF_EPI_ROLL=1 runs the repeated epilogue stages of the
-// pipelined kernels from one copy of the code (instruction-cache footprint; see fpipe::epi_half_rt)
-inline int epi_roll_level() {        // 0 off (default), 1 rolled epilogue, 2 + rolled MMA issue loop (split-bf16 forward)
+// SCNERF_EPI_ROLL=1 (default since round 2: training forward 3.99 -> 3.52 ms, dgrad 3.26 -> 3.13 ms per step,
+// profiles/r2a_ktimes_x3_roll*.txt) runs the repeated epilogue stages of the pipelined kernels from one copy of the
+// code (instruction-cache footprint; see fpipe::epi_half_rt); 2 also rolls the MMA issue loop (measured slower); 0 = fully unrolled
+inline int epi_roll_level() {        // 0 unrolled, 1 rolled epilogue (default), 2 + rolled MMA issue loop (split-bf16 forward)
   static int lv = -1;
-  if (lv < 0) { const char* e = getenv("SCNERF_EPI_ROLL"); lv = e ? std::max(0, std::min(2, atoi(e))) : 0; }
+  if (lv < 0) { const char* e = getenv("SCNERF_EPI_ROLL"); lv = e ? std::max(0, std::min(2, atoi(e))) : 1; }
   return lv;
 }
 inline bool epi_roll_enabled() { return epi_roll_level() > 0; }

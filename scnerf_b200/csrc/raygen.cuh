@@ -146,6 +146,7 @@ struct RaygenDev {  // by-value kernel argument (camera struct copied, pointers 
   float focal;
   int H, W;
   const int64_t* kps;
+  const float* kps_f;      // sub-pixel keypoints (used when kps == nullptr)
   const int64_t* idx;
   int64_t idx_scalar;
   const float* extrinsic;
@@ -153,16 +154,22 @@ struct RaygenDev {  // by-value kernel argument (camera struct copied, pointers 
   int64_t N;
 };
 
-__device__ __forceinline__ void ray_pixel(const RaygenDev& a, int64_t i, int& px, int& py) {
-  if (a.kps) { px = (int)a.kps[2 * i]; py = (int)a.kps[2 * i + 1]; }
-  else { px = (int)(i % a.W); py = (int)(i / a.W); }
+// (u, v): the pixel coordinate the direction is computed from (float for sub-pixel keypoints, get_rays.py:112-123);
+// (px, py): its truncation, which indexes the ray_o / ray_d residual fields (`.long()`, get_rays.py:134,140)
+__device__ __forceinline__ void ray_pixel(const RaygenDev& a, int64_t i, int& px, int& py, float& u, float& v) {
+  if (a.kps) { px = (int)a.kps[2 * i]; py = (int)a.kps[2 * i + 1]; u = (float)px; v = (float)py; }
+  else if (a.kps_f) { u = a.kps_f[2 * i]; v = a.kps_f[2 * i + 1]; px = (int)u; py = (int)v; }
+  else { px = (int)(i % a.W); py = (int)(i / a.W); u = (float)px; v = (float)py; }
 }
-__device__ __forceinline__ bool ray_pose(const RaygenDev& a, int64_t i, Pose& P) {
+// returns whether the pose is a learnable camera's; `ok` = false for a per-ray camera index out of range
+__device__ __forceinline__ bool ray_pose(const RaygenDev& a, int64_t i, Pose& P, bool& ok) {
+  ok = true;
   if (a.extrinsic) {
     pose_from_matrix(a.extrinsic + (a.extrinsic_per_ray ? i * 16 : 0), P);
     return false;
   }
   int64_t ci = a.idx ? a.idx[i] : a.idx_scalar;
+  if ((uint64_t)ci >= (uint64_t)a.cam.n_cams) { ok = false; ci = 0; }
   pose_from_params(a.cam, ci, P);
   return true;
 }
@@ -173,20 +180,22 @@ __global__ void __launch_bounds__(128) raygen_fwd_kernel(RaygenDev a, float* __r
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= a.N) return;
   int px, py;
-  ray_pixel(a, i, px, py);
+  float u, v;
+  ray_pixel(a, i, px, py, u, v);
   Pose P;
-  ray_pose(a, i, P);
+  bool pose_ok;
+  ray_pose(a, i, P, pose_ok);
   float dc[3];
   if (a.has_cam) {
     Intr K = load_intrinsics(a.cam);
     // torch.inverse of the upper-triangular K: [1/fx, 0, -cx/fx; 0, 1/fy, -cy/fy; 0 0 1]
     float i00 = 1.f / K.fx, i02 = -K.cx / K.fx, i11 = 1.f / K.fy, i12 = -K.cy / K.fy;
-    dc[0] = (float)px * i00 + i02;
-    dc[1] = -((float)py * i11 + i12);
+    dc[0] = u * i00 + i02;
+    dc[1] = -(v * i11 + i12);
     dc[2] = -1.f;
   } else {
-    dc[0] = ((float)px - a.W * .5f) / a.focal;
-    dc[1] = -((float)py - a.H * .5f) / a.focal;
+    dc[0] = (u - a.W * .5f) / a.focal;
+    dc[1] = -(v - a.H * .5f) / a.focal;
     dc[2] = -1.f;
   }
   float o[3], d[3];
@@ -213,6 +222,10 @@ __global__ void __launch_bounds__(128) raygen_fwd_kernel(RaygenDev a, float* __r
       for (int j = 0; j < 3; ++j) d[j] *= inv;
     }
   }
+  if (!pose_ok) {   // camera index out of range: poison the ray instead of reading out of bounds
+#pragma unroll
+    for (int j = 0; j < 3; ++j) { o[j] = __int_as_float(0x7fc00000); d[j] = o[j]; }
+  }
 #pragma unroll
   for (int j = 0; j < 3; ++j) { rays_o[i * 3 + j] = o[j]; rays_d[i * 3 + j] = d[j]; }
 }
@@ -222,13 +235,18 @@ __global__ void __launch_bounds__(128) raygen_bwd_kernel(RaygenDev a, const floa
                                                          scnerf_camera_grads G) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   float g_intr[4] = {0.f, 0.f, 0.f, 0.f};
+  bool pose_ok = true;
+  int px = 0, py = 0;
+  float u = 0.f, v = 0.f;
+  Pose P;
+  bool learn_pose = false;
   if (i < a.N) {
-    int px, py;
-    ray_pixel(a, i, px, py);
-    Pose P;
-    bool learn_pose = ray_pose(a, i, P);
+    ray_pixel(a, i, px, py, u, v);
+    learn_pose = ray_pose(a, i, P, pose_ok);
+  }
+  if (i < a.N && pose_ok) {
     Intr K = load_intrinsics(a.cam);
-    float dc[3] = {(float)px / K.fx - K.cx / K.fx, -((float)py / K.fy - K.cy / K.fy), -1.f};
+    float dc[3] = {u / K.fx - K.cx / K.fx, -(v / K.fy - K.cy / K.fy), -1.f};
     float go[3] = {g_o[i * 3], g_o[i * 3 + 1], g_o[i * 3 + 2]};
     float gd[3] = {g_d[i * 3], g_d[i * 3 + 1], g_d[i * 3 + 2]};
     Tap ty = bilinear_tap(py, a.cam.gh, a.cam.H), tx = bilinear_tap(px, a.cam.gw, a.cam.W);
@@ -264,9 +282,9 @@ __global__ void __launch_bounds__(128) raygen_bwd_kernel(RaygenDev a, const floa
       }
     }
     // dc0 = (px - cx)/fx ; dc1 = -(py - cy)/fy
-    g_intr[0] = -g_dc0 * ((float)px - K.cx) / (K.fx * K.fx);
+    g_intr[0] = -g_dc0 * (u - K.cx) / (K.fx * K.fx);
     g_intr[2] = -g_dc0 / K.fx;
-    g_intr[1] = g_dc1 * ((float)py - K.cy) / (K.fy * K.fy);
+    g_intr[1] = g_dc1 * (v - K.cy) / (K.fy * K.fy);
     g_intr[3] = g_dc1 / K.fy;
   }
   if (G.intrinsics_noise) {   // block reduction -> 4 atomics per block

@@ -10,7 +10,7 @@ import torch
 from . import _lib
 
 
-def _pose_source(args, idx_in_camera_param, extrinsic, N, keep):
+def _pose_source(args, idx_in_camera_param, extrinsic, N, keep, n_cams=None):
     """Fill the pose fields of a RaygenArgs: per-ray idx tensor | scalar idx | [4,4] | [N,4,4]."""
     if extrinsic is not None:
         e = _lib.f32(extrinsic)
@@ -26,11 +26,16 @@ def _pose_source(args, idx_in_camera_param, extrinsic, N, keep):
         i = _lib.i64(idx_in_camera_param).reshape(-1)
         if i.numel() != N:
             raise ValueError(f"idx_in_camera_param has {i.numel()} entries for {N} rays")
+        if n_cams is not None:
+            # Python indexing semantics of `camera_model.get_extrinsic()[idx]` (get_rays.py:120): negative
+            # indices wrap; out-of-range ones are poisoned to NaN rays by the kernel (no host sync here)
+            i = torch.where(i < 0, i + n_cams, i)
         keep.append(i)
         args.idx = _lib.ptr(i)
         args.idx_scalar = -1
     else:
-        args.idx_scalar = int(idx_in_camera_param)
+        s = int(idx_in_camera_param)
+        args.idx_scalar = s + n_cams if (s < 0 and n_cams is not None) else s
 
 
 class _RayGen(torch.autograd.Function):
@@ -45,10 +50,17 @@ class _RayGen(torch.autograd.Function):
         keep = [cam]
         args.cam = C.pointer(cam)
         if kps is not None:
-            k = _lib.i64(kps)
+            # integer pixels -> int64; sub-pixel keypoints (SIFT / SuperGlue matches for the PRD loss) stay float:
+            # the direction uses the float value, the ray_o / ray_d residual lookup its truncation
+            # (get_rays.py:112-123 `.float()`, :134,140 `.long()`)
+            if torch.is_floating_point(kps):
+                k = _lib.f32(kps[:, :2])
+                args.kps_f32 = _lib.ptr(k)
+            else:
+                k = _lib.i64(kps[:, :2])
+                args.kps = _lib.ptr(k)
             keep.append(k)
-            args.kps = _lib.ptr(k)
-        _pose_source(args, idx, extrinsic, N, keep)
+        _pose_source(args, idx, extrinsic, N, keep, int(camera_model.extrinsics_initial.shape[0]))
         args.N = N
         rays_o = torch.empty(N, 3, device=dev, dtype=torch.float32)
         rays_d = torch.empty(N, 3, device=dev, dtype=torch.float32)
@@ -114,7 +126,7 @@ def _run_pinhole(H, W, focal, extrinsic, kps_list, N):
     args.extrinsic, args.idx_scalar = _lib.ptr(e), -1
     k = None
     if kps_list is not None:
-        k = _lib.i64(kps_list[:, :2])
+        k = _lib.i64(kps_list[:, :2])              # get_rays.py:82 truncates first: kps_list.long()
         args.kps = _lib.ptr(k)
     rays_o = torch.empty(N, 3, device=e.device, dtype=torch.float32)
     rays_d = torch.empty(N, 3, device=e.device, dtype=torch.float32)

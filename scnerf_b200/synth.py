@@ -186,3 +186,43 @@ def adam_case(seed, n_steps=3):
     grads = [[(rng.standard_normal(s) * 10.0 ** rng.uniform(-4, 0)).astype(np.float32) for s in shapes]
              for _ in range(n_steps)]
     return params, grads
+
+
+# ---------------------------------------------------------------------------------------------
+# Round 2: sub-pixel keypoints and the composed configs[2] step (render + PRD + custom Adam)
+# ---------------------------------------------------------------------------------------------
+def subpixel_kps(seed, N, H=FERN_H, W=FERN_W, n_cams=FERN_NCAM):
+    """kps[N,2] float32 (x, y) with fractional parts (SIFT / SuperGlue keypoints), idx[N] int64."""
+    rng = np.random.default_rng(seed + 5000)
+    kps = np.stack([rng.uniform(0, W - 1, N), rng.uniform(0, H - 1, N)], -1).astype(np.float32)
+    kps[: N // 8] = np.floor(kps[: N // 8])          # some exactly on the pixel grid
+    return kps, rng.integers(0, n_cams, N).astype(np.int64)
+
+
+def c3_case():
+    """Sizes / hyper-parameters of the composed configs[2] step (tests/golden/make_golden_r2.py, bench --workload c3)."""
+    return dict(seed=31, N_rays=48, Nc=64, Nf=128, pair=(2, 5), n_matches=192, threshold=5.0, prd_weight=1e-4,
+                lrate=5e-4, lrate_decay=250, weight_decay=0.1, global_step0=1001, n_steps=2)
+
+
+def c3_matches(seed, N=None, H=FERN_H, W=FERN_W):
+    """Sub-pixel matches (kps0, kps1) [N,2] float32 of the image pair ``c3_case()["pair"]``: random sub-pixel keypoints
+    of image i, lifted to a random depth along their (noise-free pinhole) rays and projected into image j, plus 0.3 px of
+    detector noise; the first 8 are outliers (threshold / chirality masks of the PRD loss)."""
+    C = c3_case()
+    N = N or C["n_matches"]
+    i, j = C["pair"]
+    rng = np.random.default_rng(seed + 7000)
+    poses = camera_poses(C["seed"]).astype(np.float64)
+    K = intrinsic_init(H, W).astype(np.float64)
+    fx, fy, cx, cy = K[0, 0], K[1, 1], K[0, 2], K[1, 2]
+    kps0 = np.stack([rng.uniform(30, W - 30, 4 * N), rng.uniform(30, H - 30, 4 * N)], -1)
+    dirs = np.stack([(kps0[:, 0] - cx) / fx, -(kps0[:, 1] - cy) / fy, -np.ones(4 * N)], -1)
+    P = poses[i, :3, 3] + rng.uniform(2.0, 6.0, (4 * N, 1)) * (dirs @ poses[i, :3, :3].T)
+    q = (P - poses[j, :3, 3]) @ poses[j, :3, :3]                  # R_j^T (P - t_j)
+    kps1 = np.stack([cx - fx * q[:, 0] / q[:, 2], cy + fy * q[:, 1] / q[:, 2]], -1) + rng.normal(0, 0.3, (4 * N, 2))
+    ok = (kps1[:, 0] >= 0) & (kps1[:, 0] < W - 1) & (kps1[:, 1] >= 0) & (kps1[:, 1] < H - 1)
+    kps0, kps1 = kps0[ok][:N], kps1[ok][:N]
+    assert len(kps0) == N, len(kps0)
+    kps1[:8] = np.stack([rng.uniform(0, W - 1, 8), rng.uniform(0, H - 1, 8)], -1)
+    return kps0.astype(np.float32), kps1.astype(np.float32)

@@ -631,3 +631,130 @@ def test_serial_tensor_core_kernels_still_pass():
                        cwd=root, env=env, capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
     assert "passed" in r.stdout and "failed" not in r.stdout
+
+
+# ---------------------------------------------------------------------------------------------
+# round 2: sub-pixel keypoints, the composed configs[2] step, parity at the BENCHMARKED size and mode
+# ---------------------------------------------------------------------------------------------
+def test_raygen_subpixel(lib, golden):
+    """fractional keypoints — direction from the float value, ray_o / ray_d residual lookup from
+    its truncation (NeRF/get_rays.py:112-123,134,140).  CUDA vs the live reference's golden, forward + gradients."""
+    from scnerf_b200.get_rays import get_rays_kps_use_camera
+    g = golden("raygen_subpixel")
+    mods = build_modules(12, DEV)
+    cam = mods["cam"]
+    kps, idx = synth.subpixel_kps(12, 256)
+    o, d = get_rays_kps_use_camera(H, W, cam, T(kps).to(DEV), idx_in_camera_param=T(idx).to(DEV))
+    close(o, g["o"], 1e-5, "rays_o"); close(d, g["d"], 1e-5, "rays_d")
+    ((o * T(g["wo"]).to(DEV)).sum() + (d * T(g["wd"]).to(DEV)).sum()).backward()
+    for k in cam.LEARNABLE:
+        close(getattr(cam, k).grad, g["g_" + k], 2e-4, "d/d" + k)
+    with torch.no_grad():
+        o, d = get_rays_kps_use_camera(H, W, cam, T(kps).to(DEV), idx_in_camera_param=4)
+        close(o, g["int_o"], 1e-5, "int o"); close(d, g["int_d"], 1e-5, "int d")
+        o, d = get_rays_kps_use_camera(H, W, cam, T(kps).to(DEV), extrinsic=T(synth.camera_poses(13)[2]).to(DEV))
+        close(o, g["ext_o"], 1e-5, "ext o"); close(d, g["ext_d"], 1e-5, "ext d")
+        # integer keypoints given as float agree bit for bit with the int64 path
+        ki = np.floor(kps)
+        a = get_rays_kps_use_camera(H, W, cam, T(ki).to(DEV), idx_in_camera_param=T(idx).to(DEV))
+        b = get_rays_kps_use_camera(H, W, cam, T(ki.astype(np.int64)).to(DEV), idx_in_camera_param=T(idx).to(DEV))
+        assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
+        # negative camera indices wrap like Python indexing; out-of-range ones poison the ray (no OOB read)
+        neg = get_rays_kps_use_camera(H, W, cam, T(ki).to(DEV), idx_in_camera_param=T(idx - synth.FERN_NCAM).to(DEV))
+        assert torch.equal(neg[0], a[0]) and torch.equal(neg[1], a[1])
+        bad = T(idx).clone(); bad[3] = synth.FERN_NCAM + 5
+        oo, dd = get_rays_kps_use_camera(H, W, cam, T(ki).to(DEV), idx_in_camera_param=bad.to(DEV))
+        assert torch.isnan(oo[3]).all() and torch.isnan(dd[3]).all() and torch.isfinite(oo[4:]).all()
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16x3"])
+def test_c3_composed_step(lib, golden, precision):
+    """BASELINE configs[2] composed exactly as NeRF/run_nerf.py:482-621 runs it: render (64c+128f) -> img2mse x2,
+    + weight x PRD on sub-pixel matches, backward, CustomAdamOptimizer.step, lr decay; two steps.  Through this repo's
+    public API vs the golden produced by the live reference."""
+    from tests.util import CAM_KEYS, cuda_c3_steps
+    g = golden("c3_step")
+    r = cuda_c3_steps(DEV, precision)
+    C = synth.c3_case()
+    ref_render = float(g["loss1"]) + float(g["loss0"])
+    assert abs(r["loss_render"] - ref_render) <= 1e-4 * ref_render, (r["loss_render"], ref_render)
+    assert abs(r["prd"] - float(g["prd"])) <= 1e-3 * float(g["prd"]), (r["prd"], float(g["prd"]))
+    assert r["n_match"] == float(g["n_match"])
+    close(r["rgb"], g["rgb"], 1e-4, "rgb", 1.0)
+    for k in CAM_KEYS:
+        ref = g["g_cam_" + k]
+        e = rel(r["g_cam_" + k], ref)
+        print(f"  c3 {precision} d/d{k}: rel-to-max err {e:.2e}")
+        assert e <= 2e-2, (k, e)            # camera gradients: fp32 noise floor of the reference itself is 4e-3..8e-3
+    for key in list(g):
+        if key.startswith("gpin_"):
+            ref = g[key]
+            assert abs(r[key][0] - ref[0]) <= 3e-3 * ref[0] + 1e-12, (key, r[key], ref)
+    for step in range(C["n_steps"]):
+        tol = (0.002 if step == 0 else 0.06) * C["lrate"]
+        for k in CAM_KEYS:
+            ref = g[f"s{step}_cam_" + k]
+            assert np.abs(r[f"s{step}_cam_" + k] - ref).max() <= tol + 1e-6 * np.abs(ref).max(), (step, k)
+        for key in list(g):
+            if key.startswith(f"s{step}_ppin_"):
+                ref = g[key]
+                assert abs(r[key][0] - ref[0]) <= 1e-5 * ref[0], (key, r[key], ref)
+
+
+def test_full_size_step_vs_oracle(lib):
+    """the BENCHMARKED size and mode against the ORACLE (not against this repo's fp32 path):
+    configs[1] at 4096 rays x (64c+128f), bf16x3, perturb=1, raw_noise_std=1 with the reference's injected draws.
+    rgb / rgb0 / acc within 1e-4 (scale 1) on >= 95 % of rays, outliers bounded by the reference's own fp32-vs-fp64
+    gap; every gradient within max(3 x fp32 floor, 1e-3) of the fp64 oracle.  Counts go to gpurun_out/ (-> profiles/)."""
+    import json
+    import os
+    from tests.util import oracle_step_chunked
+    torch.set_num_threads(min(32, os.cpu_count() or 8))
+    N, Nc, Nf, seed = 4096, 64, 128, 51
+    mods = build_modules(seed, DEV)
+    kps, idx, target = synth.pixel_batch(seed, N)
+    # --- CUDA: public API, tensor-core forward + dgrad + wgrad
+    from scnerf_b200.get_rays import get_rays_kps_use_camera
+    from scnerf_b200.render import render
+    from scnerf_b200.run_nerf_helpers import img2mse
+    cam, net, fine = mods["cam"], mods["coarse"], mods["fine"]
+    o, d = get_rays_kps_use_camera(H, W, cam, T(kps).to(DEV), idx_in_camera_param=T(idx).to(DEV))
+    rgb, disp, acc, ex = render(H, W, 1024 * 32, rays=torch.stack([o, d]), camera_model=cam, ndc=True, near=0., far=1.,
+                                use_viewdirs=True, mode="train", network_query_fn=None, perturb=1., N_importance=Nf,
+                                network_fine=fine, N_samples=Nc, network_fn=net, white_bkgd=False, raw_noise_std=1.,
+                                retraw=True, pytest=True, precision="bf16x3")
+    tgt = T(target).to(DEV)
+    loss = img2mse(rgb, tgt) + img2mse(ex["rgb0"], tgt)
+    loss.backward()
+    grads = {"camera." + k: getattr(cam, k).grad.cpu().numpy() for k in cam.LEARNABLE}
+    grads.update({"coarse." + k: p.grad.cpu().numpy() for k, p in net.named_parameters()})
+    grads.update({"fine." + k: p.grad.cpu().numpy() for k, p in fine.named_parameters()})
+    # --- oracle: fp32 (the reference's arithmetic) and fp64 (the truth the tolerance is calibrated on)
+    l32, o32, g32 = oracle_step_chunked(seed, kps, idx, target, Nc, Nf, torch.float32)
+    l64, o64, g64 = oracle_step_chunked(seed, kps, idx, target, Nc, Nf, torch.float64)
+    report = {"N_rays": N, "N_samples": Nc, "N_importance": Nf, "precision": "bf16x3", "loss_cuda": float(loss),
+              "loss_oracle_fp32": l32, "loss_oracle_fp64": l64, "rays": {}, "grads": {}}
+    assert abs(float(loss) - l32) <= 1e-4 * abs(l32), (float(loss), l32)
+    for name, mine, key in (("rgb", rgb, "rgb_map"), ("rgb0", ex["rgb0"], "rgb0"), ("acc", acc, "acc_map")):
+        a = mine.detach().cpu().numpy().reshape(N, -1).astype(np.float64)
+        dd = np.abs(a - o32[key].reshape(N, -1)).max(1)
+        gap = np.abs(o32[key].reshape(N, -1).astype(np.float64) - o64[key].reshape(N, -1)).max(1)
+        report["rays"][name] = {"over_1e-4": int((dd > 1e-4).sum()), "max": float(dd.max()),
+                                "oracle_fp32_vs_fp64_over_1e-4": int((gap > 1e-4).sum()), "oracle_gap_max": float(gap.max())}
+        print(f"  {name}: {int((dd > 1e-4).sum())} of {N} rays off by > 1e-4 (max {dd.max():.2e}); "
+              f"fp32-vs-fp64 oracle: {int((gap > 1e-4).sum())} rays, max {gap.max():.2e}")
+    worst = 0.0
+    for k in sorted(g64):
+        floor, mine = rel(g32[k], g64[k]), rel(grads[k], g64[k])
+        report["grads"][k] = {"cuda_vs_fp64": mine, "fp32_oracle_vs_fp64": floor}
+        worst = max(worst, mine / max(floor, 1e-12))
+    report["worst_ratio_cuda_over_floor"] = worst
+    os.makedirs("gpurun_out", exist_ok=True)
+    with open("gpurun_out/r2_full_size_parity.json", "w") as f:
+        json.dump(report, f, indent=1)
+    for name, r in report["rays"].items():
+        assert r["over_1e-4"] <= max(0.05 * N, 2 * r["oracle_fp32_vs_fp64_over_1e-4"]), (name, r)
+        assert r["max"] <= 4.0 * r["oracle_gap_max"] + 1e-4, (name, r)
+    for k, r in report["grads"].items():
+        assert r["cuda_vs_fp64"] <= max(3.0 * r["fp32_oracle_vs_fp64"], 1e-3), (k, r)
+    print(f"full-size bf16x3 step: worst (cuda err)/(fp32 oracle err) = {worst:.2f}")

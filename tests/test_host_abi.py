@@ -34,15 +34,33 @@ def test_header_symbols_exported():
     assert lib.scnerf_built_for_sm() == 100
 
 
-def test_struct_sizes_match_header():
-    """ctypes mirrors must have the C layout (pointer-heavy structs: cheap sanity on sizes)."""
+def test_struct_sizes_match_header(tmp_path):
+    """ctypes mirrors must have the C layout: sizes AND the offset of every struct's last member, as the C compiler
+    lays the header's structs out (gcc on include/*.h — the header is plain C)."""
     import ctypes as C
+    import subprocess
     _lib = _ensure_built()
-    assert C.sizeof(_lib.Camera) == 6 * 8 + 4 * 4 + 6 * 4
-    assert C.sizeof(_lib.Mlp) == 9 * 4 + 4 + (2 * 16 + 10) * 8 + 8      # 9 ints + pad + pointers + pts_dim + pad
-    assert C.sizeof(_lib.PPRaygenArgs) == 8 * 3 + 8 + 8 * 4
-    assert C.sizeof(_lib.RenderCfg) == 48
-    assert C.sizeof(_lib.RaygenArgs) == 8 + 4 * 3 + 4 + 8 * 4 + 8 + 8
+    pairs = [("scnerf_camera", _lib.Camera), ("scnerf_camera_grads", _lib.CameraGrads), ("scnerf_mlp", _lib.Mlp),
+             ("scnerf_raygen_args", _lib.RaygenArgs), ("scnerf_rayprep_args", _lib.RayprepArgs),
+             ("scnerf_render_cfg", _lib.RenderCfg), ("scnerf_render_rand", _lib.RenderRand),
+             ("scnerf_render_out", _lib.RenderOut), ("scnerf_render_grads_in", _lib.RenderGradsIn),
+             ("scnerf_step_io", _lib.StepIO), ("scnerf_adam_tensor", _lib.AdamTensor),
+             ("scnerf_pp_raygen_args", _lib.PPRaygenArgs)] + list(getattr(_lib, "EXTRA_STRUCTS", []))
+    src = ['#include <stdio.h>', '#include <stddef.h>', '#include "scnerf_b200.h"', '#include "scnerf_b200_nerfpp.h"',
+           'int main(void) {']
+    for cname, cls in pairs:
+        last = cls._fields_[-1][0]
+        src.append(f'  printf("{cname} %zu %zu\\n", sizeof({cname}), offsetof({cname}, {last}));')
+    src += ['  return 0;', '}']
+    c = tmp_path / "sizes.c"
+    c.write_text("\n".join(src))
+    exe = tmp_path / "sizes"
+    subprocess.run(["gcc", "-std=c11", "-I", os.path.join(ROOT, "include"), str(c), "-o", str(exe)], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split("\n")
+    got = {l.split()[0]: (int(l.split()[1]), int(l.split()[2])) for l in out if l.strip()}
+    for cname, cls in pairs:
+        last = cls._fields_[-1][0]
+        assert got[cname] == (C.sizeof(cls), getattr(cls, last).offset), (cname, got[cname], C.sizeof(cls))
 
 
 def test_no_cpu_fallback():

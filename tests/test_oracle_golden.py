@@ -346,3 +346,53 @@ def test_prd_loss(golden):
     assert none is None
     close(lv, g["val_loss"], 1e-5, 0)
     close(lpp, g["val_loss_pp"], 1e-5, 0)
+
+
+def test_raygen_subpixel(golden):
+    """sub-pixel keypoints — direction from the float value, residual lookup from its truncation
+    (NeRF/get_rays.py:112-123,134,140).  Oracle vs the live reference, forward and camera gradients."""
+    g = golden("raygen_subpixel")
+    cam = make_cam(12, requires_grad=True)
+    kps, idx = synth.subpixel_kps(12, 256)
+    o, d = O.rays_pixels_camera(H, W, cam, T(kps), idx=T(idx))
+    close(o, g["o"]); close(d, g["d"])
+    ((o * T(g["wo"])).sum() + (d * T(g["wd"])).sum()).backward()
+    for k in O.Camera.LEARNABLE:
+        ref = g["g_" + k]
+        close(getattr(cam, k).grad, ref, 2e-3, 2e-5 * np.abs(ref).max())
+    with torch.no_grad():
+        o, d = O.rays_pixels_camera(H, W, cam, T(kps), idx=4)
+        close(o, g["int_o"]); close(d, g["int_d"])
+        o, d = O.rays_pixels_camera(H, W, cam, T(kps), extrinsic=T(synth.camera_poses(13)[2]))
+        close(o, g["ext_o"]); close(d, g["ext_d"])
+
+
+def test_c3_composed_step(golden):
+    """BASELINE configs[2]: render + PRD (sub-pixel matches) + CustomAdamOptimizer + lr decay, two steps, composed as
+    NeRF/run_nerf.py:482-621.  Oracle restatement vs the live reference."""
+    from tests.util import oracle_c3_steps, CAM_KEYS
+    g = golden("c3_step")
+    r = oracle_c3_steps()
+    close(r["loss_render"], float(g["loss1"]) + float(g["loss0"]), 2e-5, 0)
+    close(r["prd"], g["prd"], 1e-4, 0)
+    assert r["n_match"] == float(g["n_match"])
+    close(r["total"], g["total"], 2e-5, 0)
+    for k in CAM_KEYS:
+        ref = g["g_cam_" + k]
+        close(r["g_cam_" + k], ref, 5e-3, 2e-4 * np.abs(ref).max())
+    for key in list(g):
+        if key.startswith("gpin_"):
+            ref = g[key]
+            assert abs(r[key][0] - ref[0]) <= 2e-3 * ref[0] + 1e-12, (key, r[key], ref)
+            assert abs(r[key][1] - ref[1]) <= 2e-3 * ref[0] * 30, (key, r[key], ref)       # projection on a unit-variance probe
+    for step in range(synth.c3_case()["n_steps"]):
+        for k in CAM_KEYS:
+            # Adam's first steps move every element by ~lr regardless of the gradient's size: compare the UPDATE
+            ref = g[f"s{step}_cam_" + k]
+            # (step 0 moves by exactly lr x sign(g); from step 1 on m/sqrt(v) amplifies fp32 noise of small gradients)
+            tol = (0.002 if step == 0 else 0.05) * synth.c3_case()["lrate"]
+            assert np.abs(r[f"s{step}_cam_" + k] - ref).max() <= tol + 1e-6 * np.abs(ref).max(), k
+        for key in list(g):
+            if key.startswith(f"s{step}_ppin_"):
+                ref = g[key]
+                assert abs(r[key][0] - ref[0]) <= 1e-5 * ref[0], (key, r[key], ref)   # the update itself is ~1e-2 of the norm
