@@ -314,6 +314,14 @@ int scnerf_debug_slab_plan(int32_t which, int32_t index, int64_t* out9);
  * in this process since the last reset. */
 int64_t scnerf_launch_count(int32_t reset);
 
+/* Per-launch kernel times (measurement aid; not on the product path).  scnerf_kernel_timing(1) clears the log and
+ * makes every launch of this library record a CUDA event before and after it on the launching stream;
+ * scnerf_kernel_timing(0) stops.  scnerf_kernel_timing_report writes one line per recorded launch, in launch order —
+ * "<launch site>\t<grid size>\t<milliseconds>\n" — into buf (NUL-terminated, truncated to cap) after waiting for the
+ * events, and returns the number of bytes the full report needs. */
+int scnerf_kernel_timing(int32_t enable);
+int64_t scnerf_kernel_timing_report(char* buf, int64_t cap);
+
 #ifdef __cplusplus
 }
 #endif

@@ -53,6 +53,11 @@ int scnerf_pp_intersect_sphere_bwd(const float* rays_o, const float* rays_d, con
 int scnerf_pp_level0_depths(const float* far_, float near_, int64_t N, int64_t S, const float* t_fg,
                             const float* t_bg, float* fg, float* coef, float* bg, void* stream);
 
+/* Same with a per-ray near depth: near_rays[N] = ray_batch['min_depth'] (ddp_train_nerf.py:438; datasets that ship
+ * per-pixel min-depth maps, nerf_sample_ray_split.py:166-171). */
+int scnerf_pp_level0_depths_rays(const float* far_, const float* near_rays, int64_t N, int64_t S, const float* t_fg,
+                                 const float* t_bg, float* fg, float* coef, float* bg, void* stream);
+
 /* Cascade level >= 1, ddp_train_nerf.py:451-467: sample_pdf (:83-132) on the depth mid-points with
  * weights[..., 1:-1], then sort(cat(depth, samples)).  u[N,Nf] = the torch.rand draw, NULL = det.
  * coef / merged_coef (optional) carry d(depth)/d(far) through the lerp and the sort.
@@ -135,6 +140,52 @@ int scnerf_pp_composite_bg_fwd(const float* raw, const float* bg_z, const float*
 int scnerf_pp_composite_bg_bwd(const float* raw, const float* bg_z, const float* bg_lambda, int64_t N,
                                int64_t S, const float* d_rgb, float* d_raw /* overwrite */,
                                float* d_bg_lambda /* overwrite */, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * One whole optimisation step's forward + backward of nerfplusplus/ddp_train_nerf.py:421-488,552 in ONE call:
+ * pixel indices -> render_ray_from_camera -> intersect_sphere -> for each cascade level { depths (level 0:
+ * :437-449; level >= 1: sample_pdf + sort, :451-467) -> NerfNet (fg field, fg composite, depth2pts_outside,
+ * bg field, bg composite) -> img2mse } -> loss = sum of the levels' losses -> every gradient: both networks of
+ * every level (written into g_nets, accumulate), the camera (g_cam / g_distortion, accumulate).
+ * No auto-exposure (optim_autoexpo = False), no PRD term (add it with scnerf_prd_loss_*; the camera gradients
+ * accumulate).  Rays are generated once: the reference regenerates identical rays per level (:423-428).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct scnerf_pp_step_cfg {
+  int32_t cascade_level;       /* 1 or 2 */
+  int32_t cascade_samples[2];  /* samples ADDED at each level: [64, 128] -> 64 at level 0, 192 at level 1 */
+  int32_t precision;           /* SCNERF_PRECISION_* */
+  int32_t perturb;             /* 1: perturb_samples + random u (training); 0: deterministic (evaluation) */
+  float min_depth;             /* fg near depth when io->min_depth_dev == NULL (1e-4) */
+  uint64_t seed;               /* counter RNG seed for the draws that are not injected */
+} scnerf_pp_step_cfg;
+typedef struct scnerf_pp_step_rand { /* injected draws (parity tests); NULL = draw from `seed` */
+  const float* t_fg; /* [N, cascade_samples[0]] perturb_samples(fg) */
+  const float* t_bg; /* [N, cascade_samples[0]] perturb_samples(bg) */
+  const float* u_fg; /* [N, cascade_samples[1]] sample_pdf(fg) */
+  const float* u_bg; /* [N, cascade_samples[1]] sample_pdf(bg) */
+} scnerf_pp_step_rand;
+typedef struct scnerf_pp_nets { /* net_m = NerfNet of cascade level m: foreground (3-D points) and background (4-D) */
+  const scnerf_mlp* fg[2];
+  const scnerf_mlp* bg[2];
+} scnerf_pp_nets;
+typedef struct scnerf_pp_step_io {
+  const int64_t* select_inds_host; /* [N] pinned (inputs_on_host) */
+  const float* target_host;        /* [N,3] pinned */
+  float* loss_host;                /* [1] pinned */
+  int64_t* select_inds_dev;        /* [N] staging / device-resident inputs */
+  float* target_dev;               /* [N,3] */
+  float* loss_dev;                 /* [1] (overwritten) */
+  const float* min_depth_dev;      /* [N] per-ray near depth or NULL */
+  int32_t* miss_dev;               /* [1] rays that miss the unit sphere (the reference raises, :61-65); overwritten */
+  float* rgb_dev;                  /* [cascade_level, N, 3] rendered colours per level, or NULL */
+} scnerf_pp_step_io;
+size_t scnerf_pp_train_step_workspace_bytes(const scnerf_pp_step_cfg* cfg, const scnerf_mlp* fg, const scnerf_mlp* bg,
+                                            int64_t N);
+int scnerf_pp_train_step(const scnerf_pp_raygen_args* cam /* select_inds / N ignored */, const scnerf_camera_grads* g_cam,
+                         float* g_distortion /* [2] or NULL */, const scnerf_pp_step_cfg* cfg,
+                         const scnerf_pp_nets* nets, const scnerf_pp_nets* g_nets, const scnerf_pp_step_rand* rnd,
+                         const scnerf_pp_step_io* io, int32_t inputs_on_host, int64_t N, void* workspace,
+                         size_t workspace_bytes, void* stream);
 
 #ifdef __cplusplus
 }

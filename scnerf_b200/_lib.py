@@ -15,6 +15,17 @@ LIB_PATH = os.path.join(_HERE, "csrc", "libscnerf_b200.so")
 MAX_DEPTH = 16
 PRECISION = {"fp32": 0, "bf16x3": 1, "bf16": 2}
 
+
+def default_precision():
+    """Field arithmetic when the caller does not say: ``SCNERF_PRECISION`` if set, else ``bf16x3`` — the split-bf16
+    tcgen05 path (three MMAs per product, fp32 accumulate), which meets the 1e-4 forward gate and the fp32-noise-floor
+    gradient gate and is the path the library is built for (sm_100a only).  ``fp32`` selects the
+    CUDA-core kernels (exact fp32 arithmetic, ~8x slower), ``bf16`` the single-pass throughput mode (~1e-2 error)."""
+    p = os.environ.get("SCNERF_PRECISION", "bf16x3")
+    if p not in PRECISION:
+        raise ValueError(f"SCNERF_PRECISION={p!r}: expected one of {sorted(PRECISION)}")
+    return p
+
 _f = C.POINTER(C.c_float)
 vp = C.c_void_p
 
@@ -61,6 +72,28 @@ class PPRaygenArgs(C.Structure):          # include/scnerf_b200_nerfpp.h
                 ("extrinsic", vp), ("N", C.c_int64)]
 
 
+class PPStepCfg(C.Structure):            # scnerf_pp_step_cfg
+    _fields_ = [("cascade_level", C.c_int32), ("cascade_samples", C.c_int32 * 2), ("precision", C.c_int32),
+                ("perturb", C.c_int32), ("min_depth", C.c_float), ("seed", C.c_uint64)]
+
+
+class PPStepRand(C.Structure):           # scnerf_pp_step_rand
+    _fields_ = [("t_fg", vp), ("t_bg", vp), ("u_fg", vp), ("u_bg", vp)]
+
+
+class PPNets(C.Structure):               # scnerf_pp_nets
+    _fields_ = [("fg", C.POINTER(Mlp) * 2), ("bg", C.POINTER(Mlp) * 2)]
+
+
+class PPStepIO(C.Structure):             # scnerf_pp_step_io
+    _fields_ = [("select_inds_host", vp), ("target_host", vp), ("loss_host", vp), ("select_inds_dev", vp),
+                ("target_dev", vp), ("loss_dev", vp), ("min_depth_dev", vp), ("miss_dev", vp), ("rgb_dev", vp)]
+
+
+EXTRA_STRUCTS = [("scnerf_pp_step_cfg", PPStepCfg), ("scnerf_pp_step_rand", PPStepRand), ("scnerf_pp_nets", PPNets),
+                 ("scnerf_pp_step_io", PPStepIO)]
+
+
 class AdamTensor(C.Structure):
     _fields_ = [("param", vp), ("grad", vp), ("exp_avg", vp), ("exp_avg_sq", vp), ("max_exp_avg_sq", vp),
                 ("numel", C.c_int64), ("step", C.c_int32), ("decay", C.c_int32)]
@@ -101,6 +134,8 @@ SIGNATURES = {
     "scnerf_built_for_sm": (_I, []),
     "scnerf_device_sm": (_I, []),
     "scnerf_launch_count": (_I64, [C.c_int32]),
+    "scnerf_kernel_timing": (_I, [C.c_int32]),
+    "scnerf_kernel_timing_report": (_I64, [C.c_char_p, _I64]),
     "scnerf_debug_mma_bench": (_I, [C.c_int32, C.c_int32, vp, C.c_int32, vp]),
     "scnerf_debug_timeline": (_I, [vp, C.c_int32]),
     "scnerf_debug_slab_plan": (_I, [C.c_int32, C.c_int32, C.POINTER(C.c_int64)]),
@@ -137,6 +172,10 @@ SIGNATURES = {
     "scnerf_pp_intersect_sphere_fwd": (_I, [vp, vp, _I64, vp, vp, vp]),
     "scnerf_pp_intersect_sphere_bwd": (_I, [vp, vp, vp, _I64, vp, vp, vp]),
     "scnerf_pp_level0_depths": (_I, [vp, C.c_float, _I64, _I64, vp, vp, vp, vp, vp, vp]),
+    "scnerf_pp_level0_depths_rays": (_I, [vp, vp, _I64, _I64, vp, vp, vp, vp, vp, vp]),
+    "scnerf_pp_train_step_workspace_bytes": (_SZ, [_P(PPStepCfg), _P(Mlp), _P(Mlp), _I64]),
+    "scnerf_pp_train_step": (_I, [_P(PPRaygenArgs), _P(CameraGrads), vp, _P(PPStepCfg), _P(PPNets), _P(PPNets),
+                                  _P(PPStepRand), _P(PPStepIO), C.c_int32, _I64, vp, _SZ, vp]),
     "scnerf_pp_sample_pdf": (_I, [vp, vp, vp, vp, _I64, _I64, _I64, vp, vp, vp, vp, vp]),
     "scnerf_pp_sample_pdf_bins": (_I, [vp, vp, vp, _I64, _I64, _I64, vp, vp, vp, vp]),
     "scnerf_pp_sample_pdf_bins_bwd": (_I, [vp, vp, vp, _I64, _I64, _I64, vp, vp]),
@@ -176,6 +215,19 @@ def load():
         fn.restype, fn.argtypes = res, args
     _lib = lib
     return lib
+
+
+def kernel_times():
+    """[(launch site, grid size, ms)] recorded since ``scnerf_kernel_timing(1)`` (launch order)."""
+    lib = load()
+    need = lib.scnerf_kernel_timing_report(None, 0)
+    buf = C.create_string_buffer(int(need) + 16)
+    lib.scnerf_kernel_timing_report(buf, len(buf))
+    out = []
+    for line in buf.value.decode().splitlines():
+        name, grid, ms = line.rsplit("\t", 2)
+        out.append((name, int(grid), float(ms)))
+    return out
 
 
 def check(rc, what=""):

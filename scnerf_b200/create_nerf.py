@@ -22,7 +22,7 @@ def batchify(fn, chunk):
     return ret
 
 
-def run_network(inputs, viewdirs, fn, embed_fn, embeddirs_fn, netchunk=1024 * 64, precision="fp32"):
+def run_network(inputs, viewdirs, fn, embed_fn, embeddirs_fn, netchunk=1024 * 64, precision=None):
     """NeRF/create_nerf.py:18-32: pts [N,S,3] (+ viewdirs [N,3]) -> raw [N,S,4|5].
 
     One C-ABI call (scnerf_field_fwd): positional encoding of points and directions is fused with
@@ -44,7 +44,8 @@ def run_network(inputs, viewdirs, fn, embed_fn, embeddirs_fn, netchunk=1024 * 64
     nbytes = lib.scnerf_field_workspace_bytes(C.byref(m), N * S, 0)
     ws = torch.empty(nbytes, dtype=torch.uint8, device=pts.device)
     _lib.check(lib.scnerf_field_fwd(C.byref(m), _lib.ptr(pts), _lib.ptr(vd), N, S, _lib.ptr(raw),
-                                    _lib.PRECISION[precision], _lib.ptr(ws), nbytes, _lib.stream()),
+                                    _lib.PRECISION[precision or _lib.default_precision()], _lib.ptr(ws), nbytes,
+                                    _lib.stream()),
                "field_fwd")
     return raw
 

@@ -37,6 +37,30 @@ int64_t scnerf_launch_count(int32_t reset) {
   return v;
 }
 
+int scnerf_kernel_timing(int32_t enable) {
+  KernelTimes& k = kernel_times();
+  std::lock_guard<std::mutex> g(k.mu);
+  for (auto& r : k.recs) { k.pool.push_back(r.e0); k.pool.push_back(r.e1); }
+  k.recs.clear();
+  k.on.store(enable != 0);
+  return 0;
+}
+int64_t scnerf_kernel_timing_report(char* buf, int64_t cap) {
+  KernelTimes& k = kernel_times();
+  std::lock_guard<std::mutex> g(k.mu);
+  int64_t need = 0;
+  for (auto& r : k.recs) {
+    float ms = -1.f;
+    if (cudaEventSynchronize(r.e1) == cudaSuccess) cudaEventElapsedTime(&ms, r.e0, r.e1);
+    char line[256];
+    int n = snprintf(line, sizeof(line), "%s\t%u\t%.6f\n", r.name, r.grid, ms);
+    if (buf && need + n < cap) memcpy(buf + need, line, n);
+    need += n;
+  }
+  if (buf && cap > 0) buf[need < cap ? need : cap - 1] = 0;
+  return need + 1;
+}
+
 int scnerf_debug_mma_bench(int32_t mode, int32_t iters, long long* dev_out, int32_t nblocks, void* stream) {
   return tc_mma_bench(mode, iters, dev_out, nblocks, stream);
 }

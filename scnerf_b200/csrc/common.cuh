@@ -5,6 +5,8 @@
 #include <stdio.h>
 #include <stdarg.h>
 #include <atomic>
+#include <mutex>
+#include <vector>
 
 #include "../../include/scnerf_b200.h"
 
@@ -29,11 +31,45 @@ inline std::atomic<int64_t>& launch_counter() {
   static std::atomic<int64_t> c{0};
   return c;
 }
+// Per-launch timing with CUDA events on the launching stream (scnerf_kernel_timing / _report): off by default, so
+// the timed region of a benchmark carries no events; bench.py switches it on for a separate short pass to split a
+// step's time by kernel (roofline object).  One event pair per launch, recycled from a pool.
+struct KernelTimes {
+  struct Rec { const char* name; unsigned grid; cudaEvent_t e0, e1; };
+  std::atomic<bool> on{false};
+  std::mutex mu;
+  std::vector<Rec> recs;
+  std::vector<cudaEvent_t> pool;
+  cudaEvent_t get() {
+    if (!pool.empty()) { cudaEvent_t e = pool.back(); pool.pop_back(); return e; }
+    cudaEvent_t e; cudaEventCreate(&e); return e;
+  }
+  void begin(const char* name, unsigned grid, cudaStream_t st) {
+    std::lock_guard<std::mutex> g(mu);
+    Rec r{name, grid, get(), get()};
+    cudaEventRecord(r.e0, st);
+    recs.push_back(r);
+  }
+  void end(cudaStream_t st) {
+    std::lock_guard<std::mutex> g(mu);
+    if (!recs.empty()) cudaEventRecord(recs.back().e1, st);
+  }
+};
+inline KernelTimes& kernel_times() {
+  static KernelTimes k;
+  return k;
+}
+inline unsigned grid_x(unsigned g) { return g; }
+inline unsigned grid_x(int g) { return (unsigned)g; }
+inline unsigned grid_x(const dim3& g) { return g.x * g.y * g.z; }
 // Every kernel launch in the library goes through this macro: counts it and checks the launch.
 #define SCNERF_LAUNCH(kernel, grid, block, smem, stream, ...)                                   \
   do {                                                                                          \
     (void)cudaGetLastError(); /* drop stale non-sticky errors left by other libraries */        \
+    const bool t__ = scnerf::kernel_times().on.load(std::memory_order_relaxed);                 \
+    if (t__) scnerf::kernel_times().begin(#kernel, scnerf::grid_x(grid), (cudaStream_t)(stream)); \
     kernel<<<(grid), (block), (smem), (cudaStream_t)(stream)>>>(__VA_ARGS__);                   \
+    if (t__) scnerf::kernel_times().end((cudaStream_t)(stream));                                \
     scnerf::launch_counter().fetch_add(1, std::memory_order_relaxed);                           \
     cudaError_t e__ = cudaGetLastError();                                                       \
     if (e__ != cudaSuccess)                                                                     \

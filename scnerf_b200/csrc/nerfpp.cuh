@@ -228,7 +228,8 @@ __global__ void __launch_bounds__(128) sphere_bwd_kernel(const float* __restrict
 
 // Level-0 depths (ddp_train_nerf.py:437-449): fg[r,i] = near + i*step jittered inside its interval,
 // bg[r,i] = linspace(0,1,S)[i] jittered; coef = d(fg)/d(far).  t_* == NULL: no jitter.
-__global__ void __launch_bounds__(256) level0_depths_kernel(const float* __restrict__ far, float near_,
+__global__ void __launch_bounds__(256) level0_depths_kernel(const float* __restrict__ far, float near_s,
+                                                            const float* __restrict__ near_rays,
                                                             int64_t N, int S, const float* __restrict__ t_fg,
                                                             const float* __restrict__ t_bg,
                                                             float* __restrict__ fg, float* __restrict__ coef,
@@ -237,6 +238,7 @@ __global__ void __launch_bounds__(256) level0_depths_kernel(const float* __restr
   if (g >= N * S) return;
   int64_t r = g / S;
   int i = (int)(g % S);
+  const float near_ = near_rays ? near_rays[r] : near_s;     // ray_batch['min_depth'] (ddp_train_nerf.py:438)
   float step = (far[r] - near_) / (float)(S - 1);
   float cstep = 1.f / (float)(S - 1);
   auto zf = [&](int k) { return __fadd_rn(near_, __fmul_rn((float)k, step)); };   // no FMA: mul then add, as torch
@@ -740,6 +742,48 @@ __global__ void __launch_bounds__(128) unpack_rays_bwd_kernel(const float* __res
     g_o[i * 3 + j] += g[j];
     g_d[i * 3 + j] += g[3 + j] + gv[j] * inv - k * dv[j];
   }
+}
+
+
+// ---- small helpers of the fused train step (scnerf_pp_train_step) ---------------------------------------------------
+// out[i] ~ U[0,1) from the library's counter RNG (the trainer's torch.rand / rand_like draws, :75,104)
+__global__ void __launch_bounds__(256) uniform_fill_kernel(uint64_t seed, uint32_t stream_id, int64_t n, float* __restrict__ out) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = Philox::uniform(seed, stream_id, (uint64_t)i);
+}
+// img2mse (nerfplusplus/utils.py:12-14, no mask): loss += mean((rgb - target)^2) ; g_rgb = 2 (rgb - target) / n
+__global__ void __launch_bounds__(256) mse_kernel(const float* __restrict__ rgb, const float* __restrict__ target, int64_t n,
+                                                  float* __restrict__ g_rgb, float* __restrict__ loss) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  float v = 0.f;
+  if (i < n) {
+    float d = rgb[i] - target[i];
+    v = d * d;
+    g_rgb[i] = 2.f * d / (float)n;
+  }
+  v = warp_sum(v);
+  __shared__ float red[8];
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int k = 0; k < 8; ++k) t += red[k];
+    atomicAdd(loss, t / (float)n);
+  }
+}
+// viewdirs[N,3] = rays[:, 8:11]
+__global__ void __launch_bounds__(256) extract_vd_kernel(const float* __restrict__ rays, int64_t N, float* __restrict__ vd) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < N * 3) vd[i] = rays[(i / 3) * 11 + 8 + (i % 3)];
+}
+// d_rays[:, 8:11] += d_vd
+__global__ void __launch_bounds__(256) add_vd_kernel(const float* __restrict__ d_vd, int64_t N, float* __restrict__ d_rays) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < N * 3) d_rays[(i / 3) * 11 + 8 + (i % 3)] += d_vd[i];
+}
+__global__ void __launch_bounds__(256) add_kernel(const float* __restrict__ b, int64_t n, float* __restrict__ a) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) a[i] += b[i];
 }
 
 }  // namespace pp

@@ -14,7 +14,7 @@ from .run_nerf_helpers import unwrap
 class TrainStep:
     def __init__(self, camera_model, network_fn, network_fine, N_rays, N_samples, N_importance,
                  perturb=1.0, raw_noise_std=1.0, white_bkgd=False, lindisp=False, ndc=True, near=0.,
-                 far=1., precision="fp32", seed=0):
+                 far=1., precision=None, seed=0):
         self.lib = _lib.load()
         self.cam = camera_model
         self.net_c, self.net_f = unwrap(network_fn), unwrap(network_fine) if network_fine is not None else None
@@ -26,7 +26,7 @@ class TrainStep:
         cfg.ray_cols = 11 if self.net_c.use_viewdirs else 8
         cfg.lindisp, cfg.white_bkgd = int(lindisp), int(white_bkgd)
         cfg.perturb, cfg.raw_noise_std = int(perturb > 0), float(raw_noise_std)
-        cfg.training, cfg.precision, cfg.seed = 1, _lib.PRECISION[precision], int(seed)
+        cfg.training, cfg.precision, cfg.seed = 1, _lib.PRECISION[precision or _lib.default_precision()], int(seed)
         self.cfg = cfg
         named = [("coarse." + str(i), t) for i, t in enumerate(self.net_c.field_tensors())]
         if self.net_f is not None:
@@ -36,7 +36,7 @@ class TrainStep:
         nc = len(self.net_c.field_tensors())
         gviews = [self.grads.views[n] for n, _ in named]
         self.g_c = self.net_c.c_struct(gviews[:nc])
-        self.g_f = self.net_f.c_struct(gviews[nc:2 * nc]) if self.net_f is not None else None
+        self.g_f = self.net_f.c_struct(gviews[nc:nc + len(self.net_f.field_tensors())]) if self.net_f is not None else None
         self.g_cam = _lib.CameraGrads()
         for n in self.cam.LEARNABLE:
             setattr(self.g_cam, n, _lib.ptr(self.grads.views["camera." + n]))
@@ -72,6 +72,17 @@ class TrainStep:
             C.byref(mc), C.byref(mf) if mf is not None else None, C.byref(self.g_c),
             C.byref(self.g_f) if self.g_f is not None else None, C.byref(self.io), int(on_host),
             self.N, _lib.ptr(self.ws), self.ws_bytes, _lib.stream()), "train_step")
+
+    def assign_grads(self):
+        """Point every parameter's ``.grad`` at its view of the flat buffer, so autograd terms computed outside the
+        fused step (the PRD loss) accumulate into the same buffer and torch optimisers read it without copies."""
+        for i, p in enumerate(self.net_c.field_tensors()):
+            p.grad = self.grads.views[f"coarse.{i}"]
+        if self.net_f is not None:
+            for i, p in enumerate(self.net_f.field_tensors()):
+                p.grad = self.grads.views[f"fine.{i}"]
+        for n in self.cam.LEARNABLE:
+            getattr(self.cam, n).grad = self.grads.views["camera." + n]
 
     def step_device(self, kps=None, idx=None, target=None):
         """Inputs already in HBM (copied into the staging tensors if given).  Returns the device

@@ -16,7 +16,6 @@ import torch.nn as nn
 from .. import _lib
 from .nerf_network import Embedder, MLPNet
 
-DEFAULT_PRECISION = os.environ.get("SCNERF_PRECISION", "fp32")
 
 
 class _Depth2Pts(torch.autograd.Function):
@@ -108,6 +107,9 @@ class _NerfNetFn(torch.autograd.Function):
     def backward(ctx, g_rgb, *_unused):
         lib = _lib.load()
         st = _lib.stream()
+        if ctx.t is None:
+            raise RuntimeError("NerfNet: backward ran twice through the same forward — the fused node releases its "
+                               "workspace after the first pass; sum the losses and call backward once")
         net, N, Sf, Sb, prec = ctx.net, ctx.N, ctx.Sf, ctx.Sb, ctx.prec
         o, d, fz, bz, zmax, rays, raw_fg, lam, pts4, vd, raw_bg, ws_fg, ws_bg = ctx.t
         dev = o.device
@@ -161,8 +163,8 @@ class NerfNet(nn.Module):
         self.bg_embedder_viewdir = Embedder(3, args.max_freq_log2_viewdirs - 1, args.max_freq_log2_viewdirs)
         self.bg_net = MLPNet(D=args.netdepth, W=args.netwidth, input_ch=self.bg_embedder_position.out_dim,
                              input_ch_viewdirs=self.bg_embedder_viewdir.out_dim, use_viewdirs=args.use_viewdirs)
-        # "fp32" (CUDA cores) | "bf16x3" (tcgen05, split-bf16, parity-grade) | "bf16" (tcgen05, single pass)
-        self.precision = precision or DEFAULT_PRECISION
+        # "bf16x3" (default: tcgen05, split-bf16, parity-grade) | "fp32" (CUDA cores) | "bf16" (tcgen05, single pass)
+        self.precision = precision or _lib.default_precision()
 
     def forward(self, ray_o, ray_d, fg_z_max, fg_z_vals, bg_z_vals):
         params = self.fg_net.field_tensors() + self.bg_net.field_tensors()

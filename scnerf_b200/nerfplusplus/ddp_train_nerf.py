@@ -132,7 +132,8 @@ class _DepthsOfFar(torch.autograd.Function):
 
 def level0_depths(fg_far_depth, N_samples, min_depth=1e-4, t_fg=None, t_bg=None, perturb=True):
     """ddp_train_nerf.py:437-449 in one kernel -> (fg_depth[N,S] differentiable w.r.t. fg_far_depth,
-    fg_coef[N,S], bg_depth[N,S])."""
+    fg_coef[N,S], bg_depth[N,S]).  ``min_depth``: scalar, or an [N] tensor = ``ray_batch['min_depth']`` (:438; datasets
+    with per-pixel min-depth maps, nerf_sample_ray_split.py:166-171)."""
     lib = _lib.load()
     far = _lib.f32(fg_far_depth)
     N, S = far.shape[0], int(N_samples)
@@ -141,8 +142,16 @@ def level0_depths(fg_far_depth, N_samples, min_depth=1e-4, t_fg=None, t_bg=None,
         t_fg = torch.rand(N, S, device=dev) if t_fg is None else _lib.f32(t_fg)
         t_bg = torch.rand(N, S, device=dev) if t_bg is None else _lib.f32(t_bg)
     fg, coef, bg = (torch.empty(N, S, device=dev, dtype=torch.float32) for _ in range(3))
-    _lib.check(lib.scnerf_pp_level0_depths(_lib.ptr(far), float(min_depth), N, S, _lib.ptr(t_fg), _lib.ptr(t_bg),
-                                           _lib.ptr(fg), _lib.ptr(coef), _lib.ptr(bg), _lib.stream()), "level0_depths")
+    if torch.is_tensor(min_depth) and min_depth.numel() > 1:
+        near = _lib.f32(min_depth).reshape(-1).to(dev)
+        if near.numel() != N:
+            raise ValueError(f"min_depth has {near.numel()} entries for {N} rays")
+        _lib.check(lib.scnerf_pp_level0_depths_rays(_lib.ptr(far), _lib.ptr(near), N, S, _lib.ptr(t_fg), _lib.ptr(t_bg),
+                                                    _lib.ptr(fg), _lib.ptr(coef), _lib.ptr(bg), _lib.stream()),
+                   "level0_depths")
+    else:
+        _lib.check(lib.scnerf_pp_level0_depths(_lib.ptr(far), float(min_depth), N, S, _lib.ptr(t_fg), _lib.ptr(t_bg),
+                                               _lib.ptr(fg), _lib.ptr(coef), _lib.ptr(bg), _lib.stream()), "level0_depths")
     return _DepthsOfFar.apply(fg_far_depth, fg, coef), coef, bg
 
 
@@ -173,6 +182,8 @@ def render_single_image(rank, world_size, models, ray_sampler, chunk_size, camer
     contiguous slice of the pixels.  ``models`` = {'cascade_level', 'cascade_samples', 'net_0', ...} as in the
     reference; ``ray_sampler`` only needs ``.H``, ``.W`` and, when ``camera_idx`` is None, ``.c2w_mat``.
 
+    ``min_depth``: scalar (1e-4, what the reference uses with a camera model, nerf_sample_ray_split.py:168-169) or a
+    [H*W] tensor (the dataset's min-depth map, :166-167).
     Returns (rank 0 only, like the reference) a list over cascade levels of OrderedDicts of [H, W(, 3)] tensors.
     Deviation: results stay on the device and ranks are merged with one NCCL all_gather per
     key instead of per-chunk ``.cpu()`` copies and a Gloo gather."""
@@ -200,7 +211,10 @@ def render_single_image(rank, world_size, models, ray_sampler, chunk_size, camer
                 Ns = models['cascade_samples'][m]
                 if m == 0:
                     fg_far_depth = intersect_sphere(ray_o, ray_d)
-                    fg_depth, _, bg_depth = level0_depths(fg_far_depth, Ns, min_depth, perturb=False)
+                    near = min_depth
+                    if torch.is_tensor(min_depth) and min_depth.numel() > 1:
+                        near = min_depth.reshape(-1).to(dev)[rank * per + s0: rank * per + s0 + sel.numel()]
+                    fg_depth, _, bg_depth = level0_depths(fg_far_depth, Ns, near, perturb=False)
                 else:
                     fg_depth, _ = level1_depths(fg_depth, ret['fg_weights'], Ns, det=True)
                     bg_depth, _ = level1_depths(bg_depth, ret['bg_weights'], Ns, det=True)

@@ -21,7 +21,6 @@ from .run_nerf_helpers import NeRF, unwrap
 
 to8b = lambda x: (255 * np.clip(x, 0, 1)).astype(np.uint8)  # noqa: E731
 
-DEFAULT_PRECISION = os.environ.get("SCNERF_PRECISION", "fp32")
 _call_counter = itertools.count()
 
 
@@ -138,6 +137,10 @@ class _RenderRays(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g_rgb, g_disp, g_acc, g_rgb0, g_disp0, g_acc0, _gz, _graw):
         lib = _lib.load()
+        if ctx.state is None:
+            raise RuntimeError("render_rays: backward ran twice through the same forward — the fused node releases its "
+                               "workspace (tile images of every layer) after the first pass; sum the losses and call "
+                               "backward once (retain_graph is not supported here)")
         cfg, rays, mc, mf, rnd, inj, ws, nbytes, net_c, net_f, nc, two = ctx.state
         N, dev = rays.shape[0], rays.device
         gi = _lib.RenderGradsIn()
@@ -188,7 +191,8 @@ def render_rays(ray_batch, network_fn, network_query_fn, N_samples, retraw=False
     ``network_query_fn`` is accepted for signature parity; when ``network_fn`` is this package's
     ``NeRF`` the field is evaluated by the fused CUDA kernels straight from (rays, z) — positional
     encoding included — so the [N,S,90] embedding and the [N,S,256] activations of the reference
-    are never formed.  ``precision`` (extension): "fp32" | "bf16x3" | "bf16"."""
+    are never formed.  ``precision`` (extension): "bf16x3" (default, tcgen05 split-bf16) | "fp32" | "bf16"
+    (``_lib.default_precision``)."""
     net_c = unwrap(network_fn)
     net_f = unwrap(network_fine) if network_fine is not None else None
     if not isinstance(net_c, NeRF) or (net_f is not None and not isinstance(net_f, NeRF)):
@@ -198,7 +202,7 @@ def render_rays(ray_batch, network_fn, network_query_fn, N_samples, retraw=False
     dev = ray_batch.device
     opt = dict(N_samples=int(N_samples), N_importance=int(N_importance), lindisp=bool(lindisp),
                white_bkgd=bool(white_bkgd), perturb=float(perturb), raw_noise_std=float(raw_noise_std),
-               retraw=bool(retraw), precision=precision or DEFAULT_PRECISION, seed=_seed())
+               retraw=bool(retraw), precision=precision or _lib.default_precision(), seed=_seed())
     if pytest:
         if perturb > 0.:
             opt["t_rand"] = _np_rand((N, N_samples), dev)

@@ -205,7 +205,7 @@ def c3_case():
                 lrate=5e-4, lrate_decay=250, weight_decay=0.1, global_step0=1001, n_steps=2)
 
 
-def c3_matches(seed, N=None, H=FERN_H, W=FERN_W):
+def c3_matches(seed, N=None, H=FERN_H, W=FERN_W, pose_seed=None):
     """Sub-pixel matches (kps0, kps1) [N,2] float32 of the image pair ``c3_case()["pair"]``: random sub-pixel keypoints
     of image i, lifted to a random depth along their (noise-free pinhole) rays and projected into image j, plus 0.3 px of
     detector noise; the first 8 are outliers (threshold / chirality masks of the PRD loss)."""
@@ -213,7 +213,7 @@ def c3_matches(seed, N=None, H=FERN_H, W=FERN_W):
     N = N or C["n_matches"]
     i, j = C["pair"]
     rng = np.random.default_rng(seed + 7000)
-    poses = camera_poses(C["seed"]).astype(np.float64)
+    poses = camera_poses(C["seed"] if pose_seed is None else pose_seed).astype(np.float64)
     K = intrinsic_init(H, W).astype(np.float64)
     fx, fy, cx, cy = K[0, 0], K[1, 1], K[0, 2], K[1, 2]
     kps0 = np.stack([rng.uniform(30, W - 30, 4 * N), rng.uniform(30, H - 30, 4 * N)], -1)
@@ -226,3 +226,51 @@ def c3_matches(seed, N=None, H=FERN_H, W=FERN_W):
     assert len(kps0) == N, len(kps0)
     kps1[:8] = np.stack([rng.uniform(0, W - 1, 8), rng.uniform(0, H - 1, 8)], -1)
     return kps0.astype(np.float32), kps1.astype(np.float32)
+
+
+# ---------------------------------------------------------------------------------------------
+# Seeded scenes as CUDA modules (tests, smoke(), bench.py): camera + networks loaded from the states above
+# ---------------------------------------------------------------------------------------------
+def build_modules(seed, device, mult=True, n_cams=FERN_NCAM):
+    """NeRF/ scene: learnable camera (pinhole_rot_noise_10k_rayo_rayd) + coarse/fine 8x256 MLPs."""
+    import torch
+    from .camera_dict import camera_dict
+    from .run_nerf_helpers import NeRF
+    args = camera_args(multiplicative_noise=mult)
+    cam = camera_dict[args.camera_model](intrinsics=intrinsic_init(), extrinsics=list(camera_poses(seed, n_cams)),
+                                         args=args, H=FERN_H, W=FERN_W)
+    with torch.no_grad():
+        for k, v in camera_noise_state(seed, n_cams).items():
+            getattr(cam, k).copy_(torch.from_numpy(v))
+    nets = []
+    for s in (seed, seed + 1):
+        net = NeRF(D=8, W=256, input_ch=63, output_ch=5, skips=[4], input_ch_views=27, use_viewdirs=True)
+        net.load_state_dict({k: torch.from_numpy(v) for k, v in mlp_state(s).items()})
+        nets.append(net.to(device))
+    return dict(cam=cam.to(device), coarse=nets[0], fine=nets[1], args=args)
+
+
+def pp_net_args():
+    return types.SimpleNamespace(max_freq_log2=10, max_freq_log2_viewdirs=4, netdepth=8, netwidth=256, use_viewdirs=True)
+
+
+def build_pp_modules(seed, device, levels=2, precision=None, distortion=True):
+    """NeRF++ scene: ring of cameras inside the unit sphere (learnable, with radial distortion unless
+    ``distortion=False``) + one NerfNet (fg + bg 8x256 MLPs) per cascade level."""
+    import torch
+    from .camera_dict import camera_dict
+    from .nerfplusplus import NerfNet
+    args = pp_camera_args() if distortion else pp_camera_args(camera_model="pinhole_rot_noise_10k_rayo_rayd")
+    kw = dict(k=(-0.05, 0.01)) if distortion else {}
+    cam = camera_dict[args.camera_model](intrinsics=intrinsic_init(PP_H, PP_W, PP_FOCAL), extrinsics=list(pp_camera_poses(seed)),
+                                         args=args, H=PP_H, W=PP_W, **kw)
+    with torch.no_grad():
+        for k, v in camera_noise_state(seed, n_cams=PP_NCAM, H=PP_H, W=PP_W, with_distortion=distortion).items():
+            getattr(cam, k).copy_(torch.from_numpy(v))
+    nets = []
+    for m in range(levels):
+        net = NerfNet(pp_net_args(), precision=precision)
+        net.fg_net.load_state_dict({k: torch.from_numpy(v) for k, v in pp_mlp_state(seed + 10 + 2 * m, 63).items()})
+        net.bg_net.load_state_dict({k: torch.from_numpy(v) for k, v in pp_mlp_state(seed + 11 + 2 * m, 84).items()})
+        nets.append(net.to(device))
+    return dict(cam=cam.to(device), nets=nets, args=args)

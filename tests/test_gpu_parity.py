@@ -145,11 +145,13 @@ def test_field_golden(lib, golden):
     close(e4(dirs), g["pe_dirs"], 2e-6, "PE dirs")
     net = build_modules(3, DEV)["coarse"]
     # golden evaluates point i with direction i: N=64 rays of S=1 sample
-    raw = run_network(pts[:, None, :], dirs, net, e10, e4)
+    raw = run_network(pts[:, None, :], dirs, net, e10, e4, precision="fp32")
     close(raw[:, 0, :], g["raw"], 1e-5, "raw")
+    raw = run_network(pts[:, None, :], dirs, net, e10, e4)          # the default: split-bf16 tensor-core path
+    close(raw[:, 0, :], g["raw"], 3e-5, "raw (default precision)")
     nv = NeRF(D=8, W=256, input_ch=63, output_ch=5, skips=[4], input_ch_views=0, use_viewdirs=False)
     nv.load_state_dict({k: T(v) for k, v in synth.mlp_state(4, use_viewdirs=False, input_ch_views=0).items()})
-    raw = run_network(pts[:, None, :], None, nv.to(DEV), e10, None)
+    raw = run_network(pts[:, None, :], None, nv.to(DEV), e10, None, precision="fp32")   # (no tensor-core plan for this shape)
     close(raw[:, 0, :], g["raw_noview"], 1e-5, "raw (no viewdirs)")
 
 
@@ -361,7 +363,8 @@ def test_train_step_gradients(lib, golden):
     print(f"train_step: worst (cuda err)/(fp32 oracle err) ratio = {worst:.2f}")
 
 
-def test_engine_step_matches_autograd_path_full_size(lib):
+@pytest.mark.parametrize("precision", ["fp32", "bf16x3"])
+def test_engine_step_matches_autograd_path_full_size(lib, precision):
     """BASELINE.json configs[1] at full size (4096 x (64+128)): the one-call C-ABI step
     (scnerf_train_step) and the three-node autograd path agree; gradients are additive over ray
     shards (the data-parallel property the multi-GPU path relies on)."""
@@ -369,8 +372,8 @@ def test_engine_step_matches_autograd_path_full_size(lib):
     N = 4096
     mods = build_modules(40, DEV)
     kps, idx, target = synth.pixel_batch(40, N)
-    loss_a, rgb_a, grads_a = cuda_step(mods, kps, idx, target, 64, 128, perturb=0., std=0.)
-    eng = TrainStep(mods["cam"], mods["coarse"], mods["fine"], N, 64, 128, perturb=0., raw_noise_std=0.)
+    loss_a, rgb_a, grads_a = cuda_step(mods, kps, idx, target, 64, 128, perturb=0., std=0., precision=precision)
+    eng = TrainStep(mods["cam"], mods["coarse"], mods["fine"], N, 64, 128, perturb=0., raw_noise_std=0., precision=precision)
     loss_e = eng.step_device(T(kps).to(DEV), T(idx).to(DEV), T(target).to(DEV))
     torch.cuda.synchronize()
     assert abs(float(loss_e) - loss_a) <= 1e-5 * abs(loss_a)
@@ -390,7 +393,7 @@ def test_engine_step_matches_autograd_path_full_size(lib):
     half = N // 2
     acc = None
     for sl in (slice(0, half), slice(half, N)):
-        e2 = TrainStep(mods["cam"], mods["coarse"], mods["fine"], half, 64, 128, perturb=0., raw_noise_std=0.)
+        e2 = TrainStep(mods["cam"], mods["coarse"], mods["fine"], half, 64, 128, perturb=0., raw_noise_std=0., precision=precision)
         e2.step_device(T(kps[sl]).to(DEV), T(idx[sl]).to(DEV), T(target[sl]).to(DEV))
         acc = e2.grads.flat.clone() if acc is None else acc + e2.grads.flat
     close(acc * 0.5, eng.grads.flat.cpu().numpy(), 2e-3, "shard additivity")
@@ -695,10 +698,17 @@ def test_c3_composed_step(lib, golden, precision):
         for k in CAM_KEYS:
             ref = g[f"s{step}_cam_" + k]
             assert np.abs(r[f"s{step}_cam_" + k] - ref).max() <= tol + 1e-6 * np.abs(ref).max(), (step, k)
+        # Adam's early steps move EVERY element by ~lr x sign-like ratios of tiny gradients: where the reference's
+        # own fp32 gradient of an element is noise, its update flips.  So: the norm of each updated tensor within 2 %
+        # of the size of the update (lr sqrt(numel) / |p| ~ 1e-2), and for the small tensors held in full, at most
+        # 5 % of the elements may differ by more than 0.1 lr at step 0.
         for key in list(g):
             if key.startswith(f"s{step}_ppin_"):
                 ref = g[key]
-                assert abs(r[key][0] - ref[0]) <= 1e-5 * ref[0], (key, r[key], ref)
+                assert abs(r[key][0] - ref[0]) <= 2e-4 * ref[0], (key, r[key], ref)
+            if step == 0 and key.startswith("s0_p_"):
+                dd = np.abs(r[key] - g[key])
+                assert (dd > 0.1 * C["lrate"]).mean() <= 0.05, (key, float((dd > 0.1 * C["lrate"]).mean()))
 
 
 def test_full_size_step_vs_oracle(lib):

@@ -67,6 +67,49 @@ def relmax(a, b):
     return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-30))
 
 
+def gate_gradients(grads, g64, g32, g64_free):
+    """-> (report, fails).  ``grads``: CUDA; ``g64``: fp64 oracle at the CUDA path's own discrete sampling decisions;
+    ``g32`` / ``g64_free``: fp32 and fp64 oracle (their gap is the reference's own noise floor)."""
+    # Gradient gate.  Raw criterion (as the NeRF/ path): err(cuda, fp64 at own samples) <= max(3 x fp32-oracle floor, 1e-3)
+    # per tensor.  A ReLU unit whose pre-activation is ~0 takes a different side in any two fp32-level implementations;
+    # for the one sample concerned that switches a whole gradient row on or off and perturbs dW of every earlier layer by
+    # a RANK-1 term (dZ[s,:]^T X[s,:]).  The reference's own fp32-vs-fp64 error on these tensors is such an event
+    # (99.9 % of its Frobenius norm in one singular component, profiles/r2c_relu_sign_events.txt), and which
+    # implementation draws one is a coin flip (the exact-fp32 CUDA-core path draws a 2e-2 one on this batch where the
+    # tensor-core path draws none, and vice versa).  So a tensor that misses the raw gate must (a) meet it once the
+    # two largest singular components of its error matrix are projected out — of the cuda error and of the floor alike —
+    # and (b) stay below 5e-2 raw.
+    def filtered(E_w, E_b, k=2):
+        U, S, Vt = np.linalg.svd(E_w.astype(np.float64), full_matrices=False)
+        Ew = E_w - (U[:, :k] * S[:k]) @ Vt[:k]
+        Eb = E_b - U[:, :k] @ (U[:, :k].T @ E_b) if E_b is not None else None
+        return Ew, Eb
+
+    rep, fails = {}, []
+    for k in sorted(g64):
+        e_cuda, e_ref = relmax(grads[k], g64[k]), relmax(g32[k], g64_free[k])
+        rep[k] = {"cuda_vs_fp64_at_own_samples": e_cuda, "fp32_oracle_vs_fp64": e_ref}
+    for k in sorted(g64):
+        r = rep[k]
+        if r["cuda_vs_fp64_at_own_samples"] <= max(3.0 * r["fp32_oracle_vs_fp64"], 1e-3):
+            continue
+        kw = k[:-4] + "weight" if k.endswith("bias") else k
+        kb = kw[:-6] + "bias"
+        if not kw.endswith("weight") or kb not in g64 or g64[kw].ndim != 2 or r["cuda_vs_fp64_at_own_samples"] > 5e-2:
+            fails.append((k, r))
+            continue
+        Ew, Eb = filtered(grads[kw] - g64[kw], grads[kb] - g64[kb])
+        Fw, Fb = filtered(g32[kw] - g64_free[kw], g32[kb] - g64_free[kb])
+        mw, mb = np.abs(g64[kw]).max(), np.abs(g64[kb]).max()
+        e_f = (np.abs(Ew).max() / mw) if k == kw else (np.abs(Eb).max() / mb)
+        f_f = (np.abs(Fw).max() / mw) if k == kw else (np.abs(Fb).max() / mb)
+        r.update(relu_sign_event=True, cuda_err_without_top2_components=float(e_f), floor_without_top2_components=float(f_f))
+        if e_f > max(3.0 * f_f, 1e-3):
+            fails.append((k, r))
+
+    return rep, fails
+
+
 def close(a, b, rtol, atol, what=""):
     a = a.detach().cpu().numpy() if isinstance(a, torch.Tensor) else np.asarray(a)
     np.testing.assert_allclose(a, np.asarray(b), rtol=rtol, atol=atol, err_msg=what)
@@ -245,7 +288,7 @@ def test_pp_field(golden, precision):
         close(pts4, g["pts4"], 1e-4, 2e-6, "depth2pts_outside")
         close(real, g["depth_real"], 1e-3, 1e-3, "depth_real")
     ret = net(o, d, far, fg, bg)
-    tol = 1e-4 if precision == "fp32" else 2e-4        # split-bf16 fg field: ~1.5e-5 on raw
+    tol = 1e-4                                         # the north-star gate, both precisions (split-bf16: ~1.5e-5 on raw)
     for k, v in ret.items():
         e = relmax(v, g["ret_" + k])
         print(f"pp_field[{precision}] {k}: rel-to-max err {e:.2e}")
@@ -254,8 +297,7 @@ def test_pp_field(golden, precision):
     assert abs(float(loss) - float(g["loss"])) <= 1e-4 * float(g["loss"])
     loss.backward()
     g64 = oracle64_field(g)
-    # split-bf16 backward: same bound as the NeRF/ engine test (worst tensor there: 2.3e-2 of its maximum)
-    slack, floor = (3.0, 2e-4) if precision == "fp32" else (25.0, 2.5e-2)
+    slack, floor = (3.0, 2e-4) if precision == "fp32" else (3.0, 1e-3)     # the NeRF/ path's gates
     named = dict(net.named_parameters())
     for k in list(g):
         if k.startswith("g_fg_net.") or k.startswith("g_bg_net."):
@@ -264,13 +306,15 @@ def test_pp_field(golden, precision):
         floor_check(f"pp_field[{precision}] d/d(ray_{name})", a, g["g_" + name], g64[name], slack, floor)
 
 
-def test_pp_train_step(golden):
-    """Two cascade levels, learnable camera (ddp_train_nerf.py:421-488) through the host mirror."""
+@pytest.mark.parametrize("precision", ["fp32", "bf16x3"])
+def test_pp_train_step(golden, precision):
+    """Two cascade levels, learnable camera (ddp_train_nerf.py:421-488) through the host mirror, against the golden the
+    live reference produced at cascade (24, 48)."""
     from scnerf_b200.nerfplusplus import intersect_sphere, render_ray_from_camera
     from scnerf_b200.nerfplusplus.ddp_train_nerf import level0_depths, level1_depths
     g = golden("pp_train_step")
     cam = make_cam(35)
-    nets = [make_net(50), make_net(52)]
+    nets = [make_net(50, precision), make_net(52, precision)]
     target = T(g["target"]).to(DEV)
     sel, ci = g["sel"], int(g["cam_idx"])
     cascade = [24, 48]
@@ -287,43 +331,39 @@ def test_pp_train_step(golden):
         loss = loss + torch.mean((ret["rgb"] - target) ** 2)
         if m == 0:
             e = relmax(ret["rgb"], g["rgb0"])
-            print(f"pp_train_step level 0 rgb: rel-to-max err {e:.2e}")
+            print(f"pp_train_step[{precision}] level 0 rgb: rel-to-max err {e:.2e}")
             assert e <= 1e-4
     bad = np.abs(fg.detach().cpu().numpy() - g["fg1"]) > 1e-5 * np.abs(g["fg1"]) + 1e-6
-    print(f"pp_train_step: {bad.sum()} of {bad.size} level-1 fg depths off")
+    print(f"pp_train_step[{precision}]: {bad.sum()} of {bad.size} level-1 fg depths off")
     d_rgb = np.abs(ret["rgb"].detach().cpu().numpy() - g["rgb1"]).max(1)
-    print(f"pp_train_step level 1 rgb: {(d_rgb > 1e-4).sum()} of {d_rgb.size} rays off by > 1e-4 (max {d_rgb.max():.2e})")
+    print(f"pp_train_step[{precision}] level 1 rgb: {(d_rgb > 1e-4).sum()} of {d_rgb.size} rays off by > 1e-4 (max {d_rgb.max():.2e})")
     assert (d_rgb > 1e-4).sum() <= 2 and d_rgb.max() <= 5e-3
     assert abs(float(loss) - float(g["loss"])) <= 2e-4 * float(g["loss"]), (float(loss), float(g["loss"]))
     loss.backward()
     # Inverse-CDF sampling is discontinuous in the weights: two fp32 implementations put the odd sample in a
     # neighbouring bin (rows counted above), which changes that ray's gradient.  So gradients are compared with
     # the fp64 oracle evaluated AT the CUDA path's own level-1 samples (differentiable through coef); the
-    # reference's fp32-vs-fp64 gap (golden vs the unconstrained fp64 oracle) calibrates the tolerance.
+    # reference's fp32-vs-fp64 gap (golden vs the unconstrained fp64 oracle) calibrates the tolerance
+    # (gate_gradients: raw gate max(3 x floor, 1e-3); isolated ReLU-sign events are identified and bounded).
     g64_free = oracle64_train_step(g)
     ov = tuple(x.detach().cpu().double() for x in (fg, coef, bg))
     g64 = oracle64_train_step(g, level1_override=ov)
-
-    worst = []
-
-    def check(what, cuda, golden, free, at_samples):
-        e_cuda, e_ref = relmax(cuda, at_samples), relmax(golden, free)
-        print(f"{what}: err vs fp64-at-own-samples {e_cuda:.2e} (reference fp32 vs fp64 {e_ref:.2e})")
-        worst.append((e_cuda / max(e_ref, 1e-12), what))
-        # fp32 round-off on these gradients is ill-conditioned and varies by 100x from batch to batch: on five
-        # cascade configurations the fp32 CPU oracle is 1e-4 ... 6.5e-2 away from fp64 and the CUDA path is as
-        # close or closer every time there; on this batch it is the other way round (tools/debug_pp_step.py, profiles/r1j_pp_step_gradient_noise.txt).  The
-        # component tests above are the tight ones (1e-7); this one checks the composition.
-        assert e_cuda <= max(5.0 * e_ref, 6.5e-2), (what, e_cuda, e_ref)
-
+    cuda, gold, f64, f64_free = {}, {}, {}, {}
     for name in CAM_NAMES:
-        check(f"pp_train_step d/d(camera.{name})", getattr(cam, name).grad, g["g_cam_" + name], g64_free["cam_" + name],
-              g64["cam_" + name])
+        cuda["cam_" + name] = getattr(cam, name).grad.cpu().numpy()
+        gold["cam_" + name], f64["cam_" + name], f64_free["cam_" + name] = g["g_cam_" + name], g64["cam_" + name], g64_free["cam_" + name]
     for k in list(g):
-        if k.startswith("g_net"):
+        if k.startswith("g_net"):      # the golden holds the first 8 rows of every network gradient
             m, name = int(k[5]), k[7:]
-            check(f"pp_train_step d/d(net{m}.{name})", dict(nets[m].named_parameters())[name].grad[:8], g[k],
-                  g64_free[f"net{m}_{name}"][:8], g64[f"net{m}_{name}"][:8])
+            key = f"net{m}_{name}"
+            cuda[key] = dict(nets[m].named_parameters())[name].grad[:8].cpu().numpy()
+            gold[key], f64[key], f64_free[key] = g[k], g64[key][:8], g64_free[key][:8]
+    rep, fails = gate_gradients(cuda, f64, gold, f64_free)
+    worst = max(r["cuda_vs_fp64_at_own_samples"] / max(r["fp32_oracle_vs_fp64"], 1e-12) for r in rep.values())
+    print(f"pp_train_step[{precision}]: worst (cuda err)/(reference fp32 err) = {worst:.2f}; "
+          f"largest cuda err {max(r['cuda_vs_fp64_at_own_samples'] for r in rep.values()):.2e}; "
+          f"{sum(1 for r in rep.values() if r.get('relu_sign_event'))} tensors with a ReLU-sign event")
+    assert not fails, fails
 
 
 def test_pp_render_single_image():
@@ -383,3 +423,147 @@ def test_pp_bg_field_tensor_core_forward():
             e = relmax(got, ref.cpu().numpy())
             print(f"bg field {prec} N={N} S={S}: rel-to-max err {e:.2e}")
             assert e <= tol, (prec, N, S, e)
+
+
+# ---------------------------------------------------------------------------------------------
+# round 2: the composed NeRF++ step at the trainer's cascade (64, 128), on the TENSOR-CORE path, gated like NeRF/
+# ---------------------------------------------------------------------------------------------
+def _pp_case(seed, N, cascade):
+    sel, cam_idx, target = synth.pp_pixel_batch(seed, N)
+    rng = np.random.default_rng(seed + 9000)
+    rand = {"t_fg": rng.random((N, cascade[0]), dtype=np.float32), "t_bg": rng.random((N, cascade[0]), dtype=np.float32),
+            "u_fg": rng.random((N, cascade[1]), dtype=np.float32), "u_bg": rng.random((N, cascade[1]), dtype=np.float32)}
+    return sel, cam_idx, target, rand
+
+
+def _pp_oracle_step(seed, N, cascade, dtype, level1_override=None):
+    from oracle import scnerf_pp_oracle as OP
+    sel, cam_idx, target, rand = _pp_case(seed, N, cascade)
+    cam = OP.CameraPP(synth.intrinsic_init(PH, PW, PF), synth.pp_camera_poses(seed), synth.pp_camera_args(), PH, PW,
+                      k=(-0.05, 0.01), dtype=dtype)
+    cam.load(synth.camera_noise_state(seed, n_cams=PN, H=PH, W=PW, with_distortion=True), True)
+    cv = lambda st: {k: T(v).to(dtype).requires_grad_(True) for k, v in st.items()}     # noqa: E731
+    nets = [(cv(synth.pp_mlp_state(s, 63)), cv(synth.pp_mlp_state(s + 1, 84))) for s in (seed + 10, seed + 12)]
+    loss, rets, _ = OP.train_step(cam, cam_idx, T(sel), T(target).to(dtype), nets, cascade,
+                                  {k: T(v).to(dtype) for k, v in rand.items()}, level1_override=level1_override)
+    loss.backward()
+    grads = {"cam." + k: getattr(cam, k).grad.numpy() for k in OP.CameraPP.LEARNABLE}
+    for m, (fgst, bgst) in enumerate(nets):
+        grads.update({f"net{m}.fg_net." + k: v.grad.numpy() for k, v in fgst.items()})
+        grads.update({f"net{m}.bg_net." + k: v.grad.numpy() for k, v in bgst.items()})
+    return float(loss.detach()), [r["rgb"].detach().numpy() for r in rets], grads
+
+
+def _pp_cuda_step(seed, N, cascade, precision):
+    """Through the host mirror exactly as the trainer composes it (ddp_train_nerf.py:421-488)."""
+    from scnerf_b200.nerfplusplus import intersect_sphere, render_ray_from_camera
+    from scnerf_b200.nerfplusplus.ddp_train_nerf import level0_depths, level1_depths
+    sel, cam_idx, target, rand = _pp_case(seed, N, cascade)
+    R = {k: T(v).to(DEV) for k, v in rand.items()}
+    cam = make_cam(seed)
+    nets = [make_net(seed + 10, precision), make_net(seed + 12, precision)]
+    tgt = T(target).to(DEV)
+    loss, rgbs = 0.0, []
+    for m in range(2):
+        o, d, _ = render_ray_from_camera(cam, cam_idx, sel, DEV)
+        if m == 0:
+            far = intersect_sphere(o, d)
+            fg, coef, bg = level0_depths(far, cascade[0], 1e-4, R["t_fg"], R["t_bg"])
+        else:
+            fg, coef = level1_depths(fg, ret["fg_weights"], cascade[1], fg_far_depth=far, coef=coef, u=R["u_fg"])
+            bg, _ = level1_depths(bg, ret["bg_weights"], cascade[1], u=R["u_bg"])
+        ret = nets[m](o, d, far, fg, bg)
+        rgbs.append(ret["rgb"].detach().cpu().numpy())
+        loss = loss + torch.mean((ret["rgb"] - tgt) ** 2)
+    loss.backward()
+    grads = {"cam." + k: getattr(cam, k).grad.cpu().numpy() for k in CAM_NAMES}
+    for m, net in enumerate(nets):
+        grads.update({f"net{m}." + k: p.grad.cpu().numpy() for k, p in net.named_parameters()})
+    own = tuple(x.detach().cpu().double() for x in (fg, coef, bg))
+    return float(loss.detach()), rgbs, grads, own
+
+
+@pytest.mark.parametrize("precision", ["bf16x3", "fp32"])
+def test_pp_train_step_cascade_64_128(precision):
+    """the composed NeRF++ step at the trainer's own cascade (64, 128) on the tensor-core path,
+    with the NeRF/ path's gates: forward 1e-4 (scale 1), every gradient within max(3 x fp32-oracle floor, 1e-3) of the
+    fp64 oracle evaluated at the CUDA path's own level-1 samples (inverse-CDF sampling is discontinuous: a flipped
+    sample changes that ray's gradient in the reference too)."""
+    import json
+    import os
+    N, cascade, seed = 256, [64, 128], 70
+    loss, rgbs, grads, own = _pp_cuda_step(seed, N, cascade, precision)
+    l32, rgb32, g32 = _pp_oracle_step(seed, N, cascade, torch.float32)
+    l64, rgb64, g64_free = _pp_oracle_step(seed, N, cascade, torch.float64)
+    _, _, g64 = _pp_oracle_step(seed, N, cascade, torch.float64, level1_override=own)
+    e0 = np.abs(rgbs[0] - rgb32[0]).max()
+    d1 = np.abs(rgbs[1] - rgb32[1]).max(1)
+    gap1 = np.abs(rgb32[1] - rgb64[1]).max(1)
+    print(f"pp step[{precision}] (64,128): level-0 rgb max err {e0:.2e}; level-1: {(d1 > 1e-4).sum()} of {N} rays off by > 1e-4 "
+          f"(max {d1.max():.2e}); fp32-vs-fp64 oracle: {(gap1 > 1e-4).sum()} rays, max {gap1.max():.2e}; loss {loss:.6f} vs {l32:.6f}")
+    assert e0 <= 1e-4
+    assert (d1 > 1e-4).sum() <= max(0.05 * N, 2 * (gap1 > 1e-4).sum()) and d1.max() <= 4 * gap1.max() + 1e-4
+    assert abs(loss - l32) <= 2e-4 * abs(l32)
+    rep, fails = gate_gradients(grads, g64, g32, g64_free)
+    n_events = sum(1 for r in rep.values() if r.get("relu_sign_event"))
+    worst = max(r["cuda_vs_fp64_at_own_samples"] / max(r["fp32_oracle_vs_fp64"], 1e-12) for r in rep.values())
+    print(f"pp step[{precision}]: {len(rep) - n_events} of {len(rep)} tensors meet the raw gate; {n_events} carry a rank-<=2 "
+          f"ReLU-sign event and meet it without it; worst raw (cuda err)/(fp32 oracle err) = {worst:.2f}; "
+          f"largest raw cuda err {max(r['cuda_vs_fp64_at_own_samples'] for r in rep.values()):.2e}")
+    os.makedirs("gpurun_out", exist_ok=True)
+    with open(f"gpurun_out/r2_pp_step_parity_{precision}.json", "w") as f:
+        json.dump({"N": N, "cascade": cascade, "precision": precision, "level1_rays_over_1e-4": int((d1 > 1e-4).sum()),
+                   "level1_max": float(d1.max()), "oracle_gap_rays_over_1e-4": int((gap1 > 1e-4).sum()),
+                   "tensors_with_relu_sign_event": n_events, "grads": rep}, f, indent=1)
+    assert not fails, fails
+    assert n_events <= 0.15 * len(rep), n_events
+
+
+@pytest.mark.parametrize("precision", ["bf16x3", "fp32"])
+def test_pp_fused_step_matches_autograd_path(precision):
+    """scnerf_pp_train_step (ONE C-ABI call: ddp_train_nerf.py:421-488,552) against the per-stage autograd path that
+    the oracle tests above pin: same injected draws -> same loss, same rendered colours, same gradients (the two paths
+    launch the same kernels; only the order of atomic accumulations differs).  Also the host-buffer variant and the
+    per-ray min_depth input."""
+    from scnerf_b200.nerfplusplus.engine import PPTrainStep
+    N, cascade, seed = 256, [64, 128], 70
+    loss_a, rgbs_a, grads_a, _ = _pp_cuda_step(seed, N, cascade, precision)
+    sel, cam_idx, target, rand = _pp_case(seed, N, cascade)
+    cam = make_cam(seed)
+    nets = [make_net(seed + 10, precision), make_net(seed + 12, precision)]
+    eng = PPTrainStep(cam, nets, N, cascade, camera_idx=cam_idx, precision=precision, keep_rgb=True)
+    R = {k: T(v).to(DEV) for k, v in rand.items()}
+    loss = eng.step_device(T(sel).to(DEV), T(target).to(DEV), rand=R)
+    torch.cuda.synchronize()
+    eng.check_sphere()
+    assert abs(float(loss) - loss_a) <= 2e-6 * abs(loss_a), (float(loss), loss_a)
+    for m in range(2):
+        assert np.abs(eng.rgb_dev[m].cpu().numpy() - rgbs_a[m]).max() <= 2e-6
+    worst = 0.0
+    for m, net in enumerate(nets):
+        for sub, mod in (("fg", net.fg_net), ("bg", net.bg_net)):
+            by_id = {id(p): n for n, p in mod.named_parameters()}
+            for i, p in enumerate(mod.field_tensors()):
+                e = relmax(eng.grads.views[f"net{m}.{sub}.{i}"], grads_a[f"net{m}.{sub}_net.{by_id[id(p)]}"])
+                worst = max(worst, e)
+                assert e <= 2e-4, (m, sub, by_id[id(p)], e)
+    for n in CAM_NAMES:
+        e = relmax(eng.grads.views["camera." + n], grads_a["cam." + n])
+        worst = max(worst, e)
+        assert e <= 2e-4, (n, e)
+    print(f"pp fused step[{precision}] vs autograd path: worst grad rel-to-max diff {worst:.2e}")
+    # pinned-host inputs: same loss; the loss is valid after a stream sync
+    lh = eng.step_host(T(sel), T(target), rand=R)
+    torch.cuda.synchronize()
+    assert abs(float(lh) - loss_a) <= 2e-6 * abs(loss_a)
+    # per-ray min_depth equal to the scalar -> identical; a larger near depth changes the level-0 samples
+    eng.min_depth_dev = torch.full((N,), 1e-4, device=DEV)
+    l2 = float(eng.step_device(rand=R)); torch.cuda.synchronize()
+    assert abs(l2 - loss_a) <= 2e-6 * abs(loss_a)
+    eng.min_depth_dev = torch.full((N,), 0.2, device=DEV)
+    l3 = float(eng.step_device(rand=R)); torch.cuda.synchronize()
+    assert abs(l3 - loss_a) > 1e-5 * abs(loss_a)
+    # drawing from the seed (no injected randoms) runs and gives a finite loss
+    eng.min_depth_dev = None
+    l4 = float(eng.step_device()); torch.cuda.synchronize()
+    assert np.isfinite(l4) and torch.isfinite(eng.grads.flat).all()

@@ -9,22 +9,7 @@ H, W, FOCAL = synth.FERN_H, synth.FERN_W, synth.FERN_FOCAL
 T = torch.from_numpy
 
 
-def build_modules(seed, device, mult=True, n_cams=synth.FERN_NCAM):
-    from scnerf_b200.camera_dict import camera_dict
-    from scnerf_b200.run_nerf_helpers import NeRF
-    args = synth.camera_args(multiplicative_noise=mult)
-    cam = camera_dict[args.camera_model](intrinsics=synth.intrinsic_init(),
-                                         extrinsics=list(synth.camera_poses(seed, n_cams)),
-                                         args=args, H=H, W=W)
-    with torch.no_grad():
-        for k, v in synth.camera_noise_state(seed, n_cams).items():
-            getattr(cam, k).copy_(T(v))
-    nets = []
-    for s in (seed, seed + 1):
-        net = NeRF(D=8, W=256, input_ch=63, output_ch=5, skips=[4], input_ch_views=27, use_viewdirs=True)
-        net.load_state_dict({k: T(v) for k, v in synth.mlp_state(s).items()})
-        nets.append(net.to(device))
-    return dict(cam=cam.to(device), coarse=nets[0], fine=nets[1], args=args)
+build_modules = synth.build_modules      # (lives next to the other synthetic-input builders; bench.py uses it too)
 
 
 def pytest_rand(N, Nc, Nf, perturb, std):
@@ -212,6 +197,8 @@ def cuda_c3_steps(device="cuda:0", precision="bf16x3"):
         for tag, m in (("coarse", net), ("fine", fine)):
             for name, p in m.named_parameters():
                 out[f"s{step}_ppin_{tag}_{name}"] = pin(p.detach().cpu().numpy(), rng)
+                if p.numel() <= 768:
+                    out[f"s{step}_p_{tag}_{name}"] = p.detach().cpu().numpy().copy()
         out[f"s{step}_total"] = float(total.detach())
     return out
 
