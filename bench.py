@@ -283,28 +283,33 @@ class NerfWorkload:
     def step(self, on_host):
         from scnerf_b200 import synth
         eng = self.eng
-        eng.step_host() if on_host else eng.step_device()
-        if self.wname == "c3":
-            from scnerf_b200.custom_optim import update_lrate
-            from scnerf_b200.get_rays import get_rays_kps_use_camera
-            from scnerf_b200.ray_dist_loss import proj_ray_dist_loss_single
-            C, cam = self.C, self.mods["cam"]
-            H, W = synth.FERN_H, synth.FERN_W
-            if on_host:
-                self.kps0.copy_(self.kps0_host, non_blocking=True); self.kps1.copy_(self.kps1_host, non_blocking=True)
-            i, j = C["pair"]
-            ri = get_rays_kps_use_camera(H=H, W=W, camera_model=cam, idx_in_camera_param=i, kps_list=self.kps0)
-            rj = get_rays_kps_use_camera(H=H, W=W, camera_model=cam, idx_in_camera_param=j, kps_list=self.kps1)
-            prd, _ = proj_ray_dist_loss_single(kps0_list=self.kps0, kps1_list=self.kps1, img_idx0=i, img_idx1=j, rays0=ri,
-                                               rays1=rj, mode="train", device=self.kps0.device, H=H, W=W, args=self.args,
-                                               camera_model=cam, method="NeRF", i_map=np.arange(synth.FERN_NCAM))
-            (C["prd_weight"] * prd).backward()                 # accumulates into the flat buffer (assign_grads)
+        if self.wname != "c3":
+            eng.step_host() if on_host else eng.step_device()
             self.grads.all_reduce_mean()
-            self.opt.step()
-            update_lrate(self.opt, C["lrate"], C["lrate_decay"], self.global_step)
-            self.global_step += 1
-        else:
-            self.grads.all_reduce_mean()
+            return
+        # configs[2]: the PRD term goes FIRST (its host-side asserts / n_match read synchronise the stream, as the
+        # reference's do: better while the GPU holds a few microseconds of work than behind the 12 ms render step);
+        # its camera gradients land in the flat buffer, the fused step accumulates on top, then all-reduce + Adam.
+        from scnerf_b200.custom_optim import update_lrate
+        from scnerf_b200.get_rays import get_rays_kps_use_camera
+        from scnerf_b200.ray_dist_loss import proj_ray_dist_loss_single
+        C, cam = self.C, self.mods["cam"]
+        H, W = synth.FERN_H, synth.FERN_W
+        self.grads.zero_()
+        if on_host:
+            self.kps0.copy_(self.kps0_host, non_blocking=True); self.kps1.copy_(self.kps1_host, non_blocking=True)
+        i, j = C["pair"]
+        ri = get_rays_kps_use_camera(H=H, W=W, camera_model=cam, idx_in_camera_param=i, kps_list=self.kps0)
+        rj = get_rays_kps_use_camera(H=H, W=W, camera_model=cam, idx_in_camera_param=j, kps_list=self.kps1)
+        prd, _ = proj_ray_dist_loss_single(kps0_list=self.kps0, kps1_list=self.kps1, img_idx0=i, img_idx1=j, rays0=ri,
+                                           rays1=rj, mode="train", device=self.kps0.device, H=H, W=W, args=self.args,
+                                           camera_model=cam, method="NeRF", i_map=np.arange(synth.FERN_NCAM))
+        (C["prd_weight"] * prd).backward()                 # accumulates into the flat buffer (assign_grads)
+        eng.step_host(zero=False) if on_host else eng.step_device(zero=False)
+        self.grads.all_reduce_mean()
+        self.opt.step()
+        update_lrate(self.opt, C["lrate"], C["lrate_decay"], self.global_step)
+        self.global_step += 1
 
 
 class NerfppWorkload:

@@ -73,6 +73,14 @@ typedef struct scnerf_camera_grads { /* any member may be NULL (requires_grad Fa
 /* K[4,4] and c2w[n_cams,4,4] — CameraModel.get_intrinsic / get_extrinsic (camera_model.py:166-190). */
 int scnerf_camera_matrices(const scnerf_camera* cam, float* K_out, float* E_out, void* stream);
 
+/* The camera quantities the PRD loss projects with (model/ray_dist_loss.py:51-65,113-126), for the image pair (i0, i1):
+ * K4[4] = [fx_sign * fx, fy, cx, cy] (fx_sign = -1 for method "NeRF", :116-118) and E2[2,3,4] = the two camera-to-world
+ * blocks; the backward accumulates d(K4), d(E2) into the camera gradients (intrinsics_noise / extrinsics_noise). */
+int scnerf_camera_pair_fwd(const scnerf_camera* cam, int64_t i0, int64_t i1, float fx_sign, float* K4, float* E2,
+                           void* stream);
+int scnerf_camera_pair_bwd(const scnerf_camera* cam, int64_t i0, int64_t i1, float fx_sign, const float* d_K4,
+                           const float* d_E2, const scnerf_camera_grads* g, void* stream);
+
 /* Pixel -> world ray.  Replaces NeRF/get_rays.py:
  *   :93-148  get_rays_kps_use_camera        (cam != NULL, kps != NULL)
  *   :26-72   get_rays_full_image_use_camera (cam != NULL, kps == NULL: ray i is pixel (i%W, i/W))

@@ -142,6 +142,8 @@ SIGNATURES = {
     "scnerf_tc_selftest": (_I, [vp, vp, vp, C.c_int32, C.c_int32, C.c_int32, vp, _SZ, vp]),
     "scnerf_searchsorted_f32": (_I, [vp, vp, vp, _I64, _I64, _I64, _I64, _I, vp]),
     "scnerf_camera_matrices": (_I, [_P(Camera), vp, vp, vp]),
+    "scnerf_camera_pair_fwd": (_I, [_P(Camera), _I64, _I64, C.c_float, vp, vp, vp]),
+    "scnerf_camera_pair_bwd": (_I, [_P(Camera), _I64, _I64, C.c_float, vp, vp, _P(CameraGrads), vp]),
     "scnerf_raygen_fwd": (_I, [_P(RaygenArgs), vp, vp, vp]),
     "scnerf_raygen_bwd": (_I, [_P(RaygenArgs), vp, vp, _P(CameraGrads), vp]),
     "scnerf_rayprep_fwd": (_I, [_P(RayprepArgs), vp, vp, vp, vp]),

@@ -67,8 +67,8 @@ int scnerf_debug_mma_bench(int32_t mode, int32_t iters, long long* dev_out, int3
 
 int scnerf_debug_slab_plan(int32_t which, int32_t index, int64_t* out9) {
   SCNERF_CHECK_ARG(out9 != nullptr, "slab_plan: null output");
-  static const eng::Plan plans[5] = {fused::make_fwd_plan<3, 4>(), fpipe::make_plan<3, 4>(), fpipe::make_plan<3, 6>(),
-                                     dgrad::make_plan<64>(), dpipe::make_plan()};
+  static const eng::Plan plans[5] = {fpipe::make_plan<3, 4>(), fpipe::make_plan<3, 4>(), fpipe::make_plan<3, 6>(),
+                                     dgrad::make_plan<96>(), dpipe::make_plan()};      // (0 = 1 since the serial forward was retired)
   SCNERF_CHECK_ARG(which >= 0 && which < 5, "slab_plan: unknown plan %d", which);
   const eng::Plan& P = plans[which];
   for (int i = 0; i < 9; ++i) out9[i] = 0;
@@ -113,6 +113,28 @@ int scnerf_camera_matrices(const scnerf_camera* cam, float* K_out, float* E_out,
   SCNERF_CHECK_ARG(cam && cam->intrinsics_initial && cam->extrinsics_initial, "camera: null params");
   SCNERF_LAUNCH(camera_matrices_kernel, (unsigned)cdiv(std::max(cam->n_cams, 1), 64), 64, 0, stream,
                 *cam, K_out, E_out);
+  return 0;
+}
+
+static int camera_pair_check(const scnerf_camera* cam, int64_t i0, int64_t i1) {
+  SCNERF_CHECK_ARG(cam && cam->intrinsics_initial && cam->extrinsics_initial, "camera_pair: needs the learnable camera");
+  SCNERF_CHECK_ARG(i0 >= 0 && i0 < cam->n_cams && i1 >= 0 && i1 < cam->n_cams, "camera_pair: camera index out of range");
+  return 0;
+}
+int scnerf_camera_pair_fwd(const scnerf_camera* cam, int64_t i0, int64_t i1, float fx_sign, float* K4, float* E2,
+                           void* stream) {
+  int rc = camera_pair_check(cam, i0, i1);
+  if (rc) return rc;
+  SCNERF_CHECK_ARG(K4 && E2, "camera_pair_fwd: null outputs");
+  SCNERF_LAUNCH(camera_pair_fwd_kernel, 1, 32, 0, stream, *cam, i0, i1, fx_sign, K4, E2);
+  return 0;
+}
+int scnerf_camera_pair_bwd(const scnerf_camera* cam, int64_t i0, int64_t i1, float fx_sign, const float* d_K4,
+                           const float* d_E2, const scnerf_camera_grads* g, void* stream) {
+  int rc = camera_pair_check(cam, i0, i1);
+  if (rc) return rc;
+  SCNERF_CHECK_ARG(g, "camera_pair_bwd: null grads");
+  SCNERF_LAUNCH(camera_pair_bwd_kernel, 1, 32, 0, stream, *cam, i0, i1, fx_sign, d_K4, d_E2, *g);
   return 0;
 }
 
@@ -223,10 +245,12 @@ size_t scnerf_field_workspace_bytes(const scnerf_mlp* m, int64_t P, int32_t trai
 static int field_fwd_dispatch(const scnerf_mlp& m, int precision, const float* rays, int ray_cols,
                               const float* z, const float* pts, const float* viewdirs, int64_t N,
                               int S, const FieldBufs& B, float* raw, void* stream,
-                              const TcFwdImages* imgs = nullptr) {
+                              const TcFwdImages* imgs = nullptr, const CompositeArgs* comp = nullptr,
+                              bool* comp_done = nullptr, bool raw_needed = true) {
+  if (comp_done) *comp_done = false;
   if (precision == SCNERF_PRECISION_FP32)
     return field_simt_fwd(m, rays, ray_cols, z, pts, viewdirs, N, S, B, raw, stream);
-  return field_tc_fwd(m, precision, rays, ray_cols, z, pts, viewdirs, N, S, B, raw, stream, imgs);
+  return field_tc_fwd(m, precision, rays, ray_cols, z, pts, viewdirs, N, S, B, raw, stream, imgs, comp, comp_done, raw_needed);
 }
 
 int scnerf_field_fwd(const scnerf_mlp* m, const float* pts, const float* viewdirs, int64_t N, int64_t S,
@@ -367,16 +391,18 @@ size_t scnerf_render_workspace_bytes(const scnerf_render_cfg* cfg, const scnerf_
   return ar.off + 256;
 }
 
-static int composite_launch(const scnerf_render_cfg& cfg, const float* raw, int rc, const float* z,
-                            const float* rays, const float* noise, uint32_t stream_id, int64_t N, int S,
-                            float* rgb, float* disp, float* acc, float* weights, float* depth,
-                            void* stream) {
+static CompositeArgs composite_args(const scnerf_render_cfg& cfg, const float* raw, int rc, const float* z,
+                                    const float* rays, const float* noise, uint32_t stream_id, int64_t N, int S,
+                                    float* rgb, float* disp, float* acc, float* weights, float* depth) {
   CompositeArgs a{};
   a.raw = raw; a.raw_cols = rc; a.z = z; a.rays_d = rays + 3; a.d_stride = cfg.ray_cols;
   a.noise = noise; a.noise_std = cfg.raw_noise_std; a.seed = cfg.seed; a.rng_stream = stream_id;
   a.white_bkgd = cfg.white_bkgd; a.N = N; a.S = S;
   a.rgb_map = rgb; a.disp_map = disp; a.acc_map = acc; a.weights = weights; a.depth_map = depth;
-  SCNERF_LAUNCH(composite_fwd_kernel, (unsigned)cdiv(N, 4), 128, 0, stream, a);
+  return a;
+}
+static int composite_launch(const CompositeArgs& a, void* stream) {
+  SCNERF_LAUNCH(composite_fwd_kernel, (unsigned)cdiv(a.N, 4), 128, 0, stream, a);
   return 0;
 }
 
@@ -403,14 +429,22 @@ int scnerf_render_rays_fwd(const scnerf_render_cfg* cfg, const float* rays, int6
 
   SCNERF_LAUNCH(stratified_kernel, (unsigned)cdiv(N * Nc, 256), 256, 0, stream, rays, cfg->ray_cols, N, Nc,
                 cfg->lindisp, cfg->perturb > 0, rnd->t_rand, cfg->seed, w.z_c);
-  rc = field_fwd_dispatch(mc, cfg->precision, rays, cfg->ray_cols, w.z_c, nullptr, nullptr, N, Nc, w.fb_c,
-                          w.raw_c, stream, w.tc_train ? &w.im_c : nullptr);
-  if (rc) return rc;
+  // Inference (no backward to feed): the alpha-composite runs inside the field kernel's epilogue and `raw` leaves the
+  // kernel only when the caller asked for it (retraw, last level).  Training keeps raw for composite_bwd.
   const bool two = Nf > 0;
-  rc = composite_launch(*cfg, w.raw_c, rcn, w.z_c, rays, rnd->noise0, RNG_NOISE0, N, Nc,
-                        two ? out->rgb0 : out->rgb_map, two ? out->disp0 : out->disp_map,
-                        two ? out->acc0 : out->acc_map, w.w_c, w.depth_c, stream);
+  const bool fuse = !cfg->training && rcn == 4;
+  bool fused_c = false;
+  CompositeArgs ca = composite_args(*cfg, w.raw_c, rcn, w.z_c, rays, rnd->noise0, RNG_NOISE0, N, Nc,
+                                    two ? out->rgb0 : out->rgb_map, two ? out->disp0 : out->disp_map,
+                                    two ? out->acc0 : out->acc_map, w.w_c, w.depth_c);
+  const bool keep_raw_c = !two && cfg->retraw && out->raw;
+  rc = field_fwd_dispatch(mc, cfg->precision, rays, cfg->ray_cols, w.z_c, nullptr, nullptr, N, Nc, w.fb_c,
+                          w.raw_c, stream, w.tc_train ? &w.im_c : nullptr, fuse ? &ca : nullptr, &fused_c, keep_raw_c);
   if (rc) return rc;
+  if (!fused_c) {
+    rc = composite_launch(ca, stream);
+    if (rc) return rc;
+  }
   if (two) SCNERF_CHECK_ARG(out->rgb0 && out->disp0 && out->acc0, "render: N_importance>0 needs rgb0/disp0/acc0");
   const float* z_last = w.z_c; const float* raw_last = w.raw_c; const float* w_last = w.w_c;
   const float* depth_last = w.depth_c;
@@ -424,12 +458,17 @@ int scnerf_render_rays_fwd(const scnerf_render_cfg* cfg, const float* rays, int6
     a.sort_n = next_pow2(St);
     size_t smem = sizeof(float) * (2 * (Nc - 1) + a.sort_n);
     SCNERF_LAUNCH(sample_pdf_kernel, (unsigned)N, 128, smem, stream, a);
+    bool fused_f = false;
+    CompositeArgs cf = composite_args(*cfg, w.raw_f, rcn, w.z_f, rays, rnd->noise1, RNG_NOISE1, N, St, out->rgb_map,
+                                      out->disp_map, out->acc_map, w.w_f, w.depth_f);
     rc = field_fwd_dispatch(mf, cfg->precision, rays, cfg->ray_cols, w.z_f, nullptr, nullptr, N, St, w.fb_f,
-                            w.raw_f, stream, w.tc_train ? &w.im_f : nullptr);
+                            w.raw_f, stream, w.tc_train ? &w.im_f : nullptr, fuse ? &cf : nullptr, &fused_f,
+                            cfg->retraw && out->raw);
     if (rc) return rc;
-    rc = composite_launch(*cfg, w.raw_f, rcn, w.z_f, rays, rnd->noise1, RNG_NOISE1, N, St, out->rgb_map,
-                          out->disp_map, out->acc_map, w.w_f, w.depth_f, stream);
-    if (rc) return rc;
+    if (!fused_f) {
+      rc = composite_launch(cf, stream);
+      if (rc) return rc;
+    }
     z_last = w.z_f; raw_last = w.raw_f; w_last = w.w_f; depth_last = w.depth_f; S_last = St;
   }
   // forward copies of acc for the backward (disp gradient) live in the user outputs; keep our own

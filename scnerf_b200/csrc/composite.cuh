@@ -32,10 +32,9 @@ __device__ __forceinline__ float sigma_noise(const CompositeArgs& a, int64_t g) 
   return n * a.noise_std;
 }
 
-__global__ void __launch_bounds__(128) composite_fwd_kernel(CompositeArgs a) {
-  const int lane = threadIdx.x & 31;
-  const int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (r >= a.N) return;
+// One ray, one warp: `raw_ray` points at the ray's [S, raw_cols] raw values — global memory for the stand-alone kernel,
+// shared memory when the fused field forward composites a ray group from its own epilogue (fpipe::field_fwd_pipe_kernel).
+__device__ __forceinline__ void composite_ray(const CompositeArgs& a, int64_t r, int lane, const float* raw_ray, int raw_cols) {
   const float* d = a.rays_d + r * a.d_stride;
   const float dn = sqrtf(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
   float carry = 1.f;  // prod_{j<chunk start} (1 - alpha_j + 1e-10)
@@ -48,7 +47,7 @@ __global__ void __launch_bounds__(128) composite_fwd_kernel(CompositeArgs a) {
       zs = a.z[g];
       float dist = (s + 1 < a.S) ? a.z[g + 1] - zs : 1e10f;
       dist *= dn;
-      const float* rw = a.raw + g * a.raw_cols;
+      const float* rw = raw_ray + (int64_t)s * raw_cols;
       float sg = rw[3] + sigma_noise(a, g);
       alpha = 1.f - expf(-fmaxf(sg, 0.f) * dist);
       cr = 1.f / (1.f + expf(-rw[0]));
@@ -76,6 +75,13 @@ __global__ void __launch_bounds__(128) composite_fwd_kernel(CompositeArgs a) {
     a.acc_map[r] = acc_w;
     if (a.depth_map) a.depth_map[r] = acc_z;
   }
+}
+
+__global__ void __launch_bounds__(128) composite_fwd_kernel(CompositeArgs a) {
+  const int lane = threadIdx.x & 31;
+  const int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (r >= a.N) return;
+  composite_ray(a, r, lane, a.raw + r * a.S * a.raw_cols, a.raw_cols);
 }
 
 struct CompositeBwdArgs {

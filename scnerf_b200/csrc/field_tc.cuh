@@ -327,49 +327,7 @@ inline int device_sm_count() {
   return n;
 }
 
-// one-time (per device) upload of the slab plans into __constant__ / __device__ symbols
-inline int fwd_plan_init() {
-  static bool done[64] = {};
-  int dev = 0;
-  SCNERF_CUDA(cudaGetDevice(&dev));
-  if (dev < 64 && done[dev]) return 0;
-  static eng::Plan P = fused::make_fwd_plan<3>();   // (image offsets and sources do not depend on NSPLIT)
-  static eng::Plan P6 = fused::make_fwd_plan<3, 6>();
-  static fused::PlanSrc S, S6;
-  fused::build_fwd_plansrc<4>(S);
-  fused::build_fwd_plansrc<6>(S6);
-  if (fused::plan_image_bytes(P, 3) > TC_IMG_BYTES || fused::plan_image_bytes(P6, 3) > TC_IMG_BYTES)
-    return fail(SCNERF_ERR_WORKSPACE, "TC_IMG_BYTES too small");
-  SCNERF_CUDA(cudaMemcpyToSymbol(fused::d_plan_fwd, &P, sizeof(P)));
-  SCNERF_CUDA(cudaMemcpyToSymbol(fused::d_plansrc_fwd, &S, sizeof(S)));
-  SCNERF_CUDA(cudaMemcpyToSymbol(fused::d_plan_fwd6, &P6, sizeof(P6)));
-  SCNERF_CUDA(cudaMemcpyToSymbol(fused::d_plansrc_fwd6, &S6, sizeof(S6)));
-  SCNERF_CUDA(cudaFuncSetAttribute((fused::field_fused_fwd_kernel<1, 4>), cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   fused::Cfg<1, 4>::SMEM_BYTES));
-  SCNERF_CUDA(cudaFuncSetAttribute((fused::field_fused_fwd_kernel<3, 4>), cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   fused::Cfg<3, 4>::SMEM_BYTES));
-  SCNERF_CUDA(cudaFuncSetAttribute((fused::field_fused_fwd_kernel<1, 6>), cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   fused::Cfg<1, 6>::SMEM_BYTES));
-  SCNERF_CUDA(cudaFuncSetAttribute((fused::field_fused_fwd_kernel<3, 6>), cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   fused::Cfg<3, 6>::SMEM_BYTES));
-  if (dev < 64) done[dev] = true;
-  return 0;
-}
-// N-half pipelined forward (field_tc_fwd_pipe.cuh): on by default, SCNERF_FWD_PIPE=0 selects the serial kernel
-inline bool fwd_pipe_enabled() {
-  static int on = -1;
-  if (on < 0) { const char* e = getenv("SCNERF_FWD_PIPE"); on = e ? (atoi(e) != 0) : 1; }
-  return on != 0;
-}
-// SCNERF_EPI_ROLL=1 (default since round 2: training forward 3.99 -> 3.52 ms, dgrad 3.26 -> 3.13 ms per step,
-// profiles/r2a_ktimes_x3_roll*.txt) runs the repeated epilogue stages of the pipelined kernels from one copy of the
-// code (instruction-cache footprint; see fpipe::epi_half_rt); 2 also rolls the MMA issue loop (measured slower); 0 = fully unrolled
-inline int epi_roll_level() {        // 0 unrolled, 1 rolled epilogue (default), 2 + rolled MMA issue loop (split-bf16 forward)
-  static int lv = -1;
-  if (lv < 0) { const char* e = getenv("SCNERF_EPI_ROLL"); lv = e ? std::max(0, std::min(2, atoi(e))) : 1; }
-  return lv;
-}
-inline bool epi_roll_enabled() { return epi_roll_level() > 0; }
+// one-time (per device) upload of the slab plans into __device__ symbols
 template <int XS = 4>
 inline const eng::Plan& pipe_plan_host() {
   static eng::Plan P = fpipe::make_plan<3, XS>();   // (slab order, sizes and image offsets do not depend on NSPLIT)
@@ -391,31 +349,19 @@ inline int pipe_plan_init() {
   SCNERF_CUDA(cudaMemcpyToSymbol(fpipe::d_plansrc_pipe, &S, sizeof(S)));
   SCNERF_CUDA(cudaMemcpyToSymbol(fpipe::d_plan_pipe6, &P6, sizeof(P6)));
   SCNERF_CUDA(cudaMemcpyToSymbol(fpipe::d_plansrc_pipe6, &S6, sizeof(S6)));
-  SCNERF_CUDA(cudaFuncSetAttribute((fpipe::field_fwd_pipe_kernel<1, 4>), cudaFuncAttributeMaxDynamicSharedMemorySize,
+  // 3-D points: the rolled-epilogue build (ROLL = 1: stages 0-6 from one copy of the code, -0.6 ms per step, profiles/r2a_*);
+  // 4-D points (NeRF++ background): the unrolled build
+  SCNERF_CUDA(cudaFuncSetAttribute((fpipe::field_fwd_pipe_kernel<1, 4, 1>), cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    fpipe::Cfg<1, 4>::SMEM_BYTES));
-  SCNERF_CUDA(cudaFuncSetAttribute((fpipe::field_fwd_pipe_kernel<3, 4>), cudaFuncAttributeMaxDynamicSharedMemorySize,
+  SCNERF_CUDA(cudaFuncSetAttribute((fpipe::field_fwd_pipe_kernel<3, 4, 1>), cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    fpipe::Cfg<3, 4>::SMEM_BYTES));
-  SCNERF_CUDA(cudaFuncSetAttribute((fpipe::field_fwd_pipe_kernel<1, 6>), cudaFuncAttributeMaxDynamicSharedMemorySize,
+  SCNERF_CUDA(cudaFuncSetAttribute((fpipe::field_fwd_pipe_kernel<1, 6, 0>), cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    fpipe::Cfg<1, 6>::SMEM_BYTES));
-  SCNERF_CUDA(cudaFuncSetAttribute((fpipe::field_fwd_pipe_kernel<3, 6>), cudaFuncAttributeMaxDynamicSharedMemorySize,
+  SCNERF_CUDA(cudaFuncSetAttribute((fpipe::field_fwd_pipe_kernel<3, 6, 0>), cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    fpipe::Cfg<3, 6>::SMEM_BYTES));
-  if (epi_roll_enabled()) {     // experimental builds: touched only when asked for
-    SCNERF_CUDA(cudaFuncSetAttribute((fpipe::field_fwd_pipe_kernel<1, 4, 1>), cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     fpipe::Cfg<1, 4>::SMEM_BYTES));
-    SCNERF_CUDA(cudaFuncSetAttribute((fpipe::field_fwd_pipe_kernel<3, 4, 1>), cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     fpipe::Cfg<3, 4>::SMEM_BYTES));
-    SCNERF_CUDA(cudaFuncSetAttribute((fpipe::field_fwd_pipe_kernel<3, 4, 2>), cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     fpipe::Cfg<3, 4>::SMEM_BYTES));
-  }
   if (dev < 64) done[dev] = true;
   return 0;
 }
-template <int XS = 4>
-inline const eng::Plan& fwd_plan_host() {
-  static eng::Plan P = fused::make_fwd_plan<3, XS>();
-  return P;
-}
-
 inline fused::PackSrc make_pack_src(const scnerf_mlp& m) {
   fused::PackSrc src{};
   for (int i = 0; i < 8; ++i) {
@@ -459,21 +405,28 @@ inline void tc_bwd_bufs_alloc(Arena& ar, int64_t P, int nsplit, TcBwdBufs& G) {
   G.wimg = ar.get<uint8_t>(TC_IMG_BYTES);
 }
 
+// fused composite: a group of G consecutive 128-sample tiles must hold whole rays of S samples (G <= 3: 6 KB of smem)
+inline int comp_group_tiles(int S) {
+  int g = S, b = 128;
+  while (b) { int t = g % b; g = b; b = t; }      // gcd(S, 128)
+  return S / g;
+}
+inline bool comp_fusable(int S) {
+  static int on = -1;
+  if (on < 0) { const char* e = getenv("SCNERF_FUSE_COMPOSITE"); on = e ? (atoi(e) != 0) : 1; }
+  return on && S >= 1 && comp_group_tiles(S) <= fpipe::Cfg<3, 4>::COMP_MAX_G;
+}
 template <int NSPLIT, int XS = 4>
 inline int field_tc_fwd_impl(const scnerf_mlp& m, const float* rays, int ray_cols, const float* z,
                              const float* pts, const float* viewdirs, int64_t N, int S,
-                             const FieldBufs& B, float* raw, void* stream, const TcFwdImages* imgs = nullptr) {
+                             const FieldBufs& B, float* raw, void* stream, const TcFwdImages* imgs = nullptr,
+                             const CompositeArgs* comp = nullptr, bool* comp_done = nullptr, bool raw_needed = true) {
   using namespace fused;
   static_assert(C_TOTAL <= (int)TC_CBUF_FLOATS, "TC_CBUF_FLOATS too small");
-  const bool pipe = fwd_pipe_enabled();
-  int rc = pipe ? pipe_plan_init() : fwd_plan_init();
+  int rc = pipe_plan_init();
   if (rc) return rc;
   PackSrc src = make_pack_src(m);
-  if (pipe) {
-    SCNERF_LAUNCH((fpipe::pack_pipe_kernel<NSPLIT, XS>), dim3(1, (unsigned)pipe_plan_host<XS>().n_slabs), 256, 0, stream, src, B.tc_img);
-  } else {
-    SCNERF_LAUNCH((pack_fwd_kernel<NSPLIT, XS>), dim3(2, (unsigned)fwd_plan_host<XS>().n_slabs), 256, 0, stream, src, B.tc_img);
-  }
+  SCNERF_LAUNCH((fpipe::pack_pipe_kernel<NSPLIT, XS>), dim3(1, (unsigned)pipe_plan_host<XS>().n_slabs), 256, 0, stream, src, B.tc_img);
   SCNERF_LAUNCH(pack_consts_kernel, (unsigned)cdiv(C_TOTAL, 256), 256, 0, stream, src, B.tc_cbuf);
   Args a{};
   a.rays = rays; a.ray_cols = ray_cols; a.z = z; a.pts = pts; a.viewdirs = viewdirs;
@@ -496,19 +449,24 @@ inline int field_tc_fwd_impl(const scnerf_mlp& m, const float* rays, int ray_col
     a.dump_ped = B.F + 256; a.dump_ped_ld = (int)B.ldf;
   }
   a.dbg = tc_dbg_ptr(); a.dbg_tiles = tc_dbg_tiles();
+  if (comp_done) *comp_done = false;
+  if (comp && XS == 4 && comp_fusable(S)) {   // alpha-composite in the epilogue (inference): raw may stay out of HBM
+    a.comp_on = 1; a.comp_G = comp_group_tiles(S); a.comp = *comp;
+    if (!raw_needed) a.raw = nullptr;                 // nobody reads raw: it never reaches HBM
+    if (comp_done) *comp_done = true;
+  }
+  if (!raw) return fail(SCNERF_ERR_ARG, "field forward: null raw output");
   int grid = std::min(device_sm_count(), a.num_tiles);
-  if (pipe && XS == 4 && NSPLIT == 3 && epi_roll_level() >= 2)
-    SCNERF_LAUNCH((fpipe::field_fwd_pipe_kernel<3, 4, 2>), grid, 320, (fpipe::Cfg<3, 4>::SMEM_BYTES), stream, a);
-  else if (pipe && XS == 4 && epi_roll_enabled())
-    SCNERF_LAUNCH((fpipe::field_fwd_pipe_kernel<NSPLIT, 4, 1>), grid, 320, (fpipe::Cfg<NSPLIT, 4>::SMEM_BYTES), stream, a);
-  else if (pipe) SCNERF_LAUNCH((fpipe::field_fwd_pipe_kernel<NSPLIT, XS>), grid, 320, (fpipe::Cfg<NSPLIT, XS>::SMEM_BYTES), stream, a);
-  else SCNERF_LAUNCH((field_fused_fwd_kernel<NSPLIT, XS>), grid, 320, (Cfg<NSPLIT, XS>::SMEM_BYTES), stream, a);
+  SCNERF_LAUNCH((fpipe::field_fwd_pipe_kernel<NSPLIT, XS, (XS == 4 ? 1 : 0)>), grid, 320, (fpipe::Cfg<NSPLIT, XS>::SMEM_BYTES),
+                stream, a);
   return 0;
 }
 
 inline int field_tc_fwd(const scnerf_mlp& m, int precision, const float* rays, int ray_cols,
                         const float* z, const float* pts, const float* viewdirs, int64_t N, int S,
-                        const FieldBufs& B, float* raw, void* stream, const TcFwdImages* imgs = nullptr) {
+                        const FieldBufs& B, float* raw, void* stream, const TcFwdImages* imgs = nullptr,
+                        const CompositeArgs* comp = nullptr, bool* comp_done = nullptr, bool raw_needed = true) {
+  if (comp_done) *comp_done = false;
   if (!(m.D == 8 && m.W == 256 && m.skip == 4 && m.use_viewdirs && m.L_pos == 10 && m.L_dir == 4))
     return fail(SCNERF_ERR_UNSUPPORTED,
                 "tensor-core field path is specialised for the 8x256, skip-4, use_viewdirs network "
@@ -521,8 +479,8 @@ inline int field_tc_fwd(const scnerf_mlp& m, int precision, const float* rays, i
     return field_tc_fwd_impl<1, 6>(m, nullptr, 0, nullptr, pts, viewdirs, N, S, B, raw, stream, imgs);
   }
   if (precision == SCNERF_PRECISION_BF16X3)
-    return field_tc_fwd_impl<3>(m, rays, ray_cols, z, pts, viewdirs, N, S, B, raw, stream, imgs);
-  return field_tc_fwd_impl<1>(m, rays, ray_cols, z, pts, viewdirs, N, S, B, raw, stream, imgs);
+    return field_tc_fwd_impl<3>(m, rays, ray_cols, z, pts, viewdirs, N, S, B, raw, stream, imgs, comp, comp_done, raw_needed);
+  return field_tc_fwd_impl<1>(m, rays, ray_cols, z, pts, viewdirs, N, S, B, raw, stream, imgs, comp, comp_done, raw_needed);
 }
 
 // ---- tensor-core backward: dgrad chain -> per-ray reduce -> wgrad pass -> head gradients -----------
@@ -531,21 +489,13 @@ inline int bwd_plan_init() {
   int dev = 0;
   SCNERF_CUDA(cudaGetDevice(&dev));
   if (dev < 64 && done[dev]) return 0;
-  static eng::Plan P = dgrad::make_plan<64>();
+  // the serial dgrad chain serves the 96-wide d(PE) of 4-D points (NeRF++ background) only; 3-D points run the pipelined one
   static eng::Plan P96 = dgrad::make_plan<96>();
-  static fused::PlanSrc S, S96;
-  dgrad::build_plansrc<64>(S);
+  static fused::PlanSrc S96;
   dgrad::build_plansrc<96>(S96);
-  if (fused::plan_image_bytes(P, 3) > TC_IMG_BYTES || fused::plan_image_bytes(P96, 3) > TC_IMG_BYTES)
-    return fail(SCNERF_ERR_WORKSPACE, "TC_IMG_BYTES too small (dgrad)");
-  SCNERF_CUDA(cudaMemcpyToSymbol(dgrad::d_plan_dgrad, &P, sizeof(P)));
-  SCNERF_CUDA(cudaMemcpyToSymbol(dgrad::d_plansrc_dgrad, &S, sizeof(S)));
+  if (fused::plan_image_bytes(P96, 3) > TC_IMG_BYTES) return fail(SCNERF_ERR_WORKSPACE, "TC_IMG_BYTES too small (dgrad)");
   SCNERF_CUDA(cudaMemcpyToSymbol(dgrad::d_plan_dgrad96, &P96, sizeof(P96)));
   SCNERF_CUDA(cudaMemcpyToSymbol(dgrad::d_plansrc_dgrad96, &S96, sizeof(S96)));
-  SCNERF_CUDA(cudaFuncSetAttribute((dgrad::field_fused_dgrad_kernel<1, 64>), cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   dgrad::Cfg<1, 64>::SMEM_BYTES));
-  SCNERF_CUDA(cudaFuncSetAttribute((dgrad::field_fused_dgrad_kernel<3, 64>), cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   dgrad::Cfg<3, 64>::SMEM_BYTES));
   SCNERF_CUDA(cudaFuncSetAttribute((dgrad::field_fused_dgrad_kernel<1, 96>), cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    dgrad::Cfg<1, 96>::SMEM_BYTES));
   SCNERF_CUDA(cudaFuncSetAttribute((dgrad::field_fused_dgrad_kernel<3, 96>), cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -556,12 +506,6 @@ inline int bwd_plan_init() {
                                    wgrad::Cfg<3>::SMEM_BYTES));
   if (dev < 64) done[dev] = true;
   return 0;
-}
-// N-half pipelined dgrad (field_tc_dgrad_pipe.cuh, 3-D points): on by default, SCNERF_DGRAD_PIPE=0 selects the serial kernel
-inline bool dgrad_pipe_enabled() {
-  static int on = -1;
-  if (on < 0) { const char* e = getenv("SCNERF_DGRAD_PIPE"); on = e ? (atoi(e) != 0) : 1; }
-  return on != 0;
 }
 inline const eng::Plan& dpipe_plan_host() {
   static eng::Plan P = dpipe::make_plan();
@@ -578,26 +522,16 @@ inline int dpipe_plan_init() {
   if (fused::plan_image_bytes(P, 3) > TC_IMG_BYTES) return fail(SCNERF_ERR_WORKSPACE, "TC_IMG_BYTES too small (pipelined dgrad)");
   SCNERF_CUDA(cudaMemcpyToSymbol(dpipe::d_plan_dpipe, &P, sizeof(P)));
   SCNERF_CUDA(cudaMemcpyToSymbol(dpipe::d_plansrc_dpipe, &S, sizeof(S)));
-  SCNERF_CUDA(cudaFuncSetAttribute(dpipe::field_dgrad_pipe_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  SCNERF_CUDA(cudaFuncSetAttribute((dpipe::field_dgrad_pipe_kernel<1, 1>), cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    dpipe::Cfg<1>::SMEM_BYTES));
-  SCNERF_CUDA(cudaFuncSetAttribute(dpipe::field_dgrad_pipe_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  SCNERF_CUDA(cudaFuncSetAttribute((dpipe::field_dgrad_pipe_kernel<3, 1>), cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    dpipe::Cfg<3>::SMEM_BYTES));
-  if (epi_roll_enabled()) {     // experimental builds: touched only when asked for
-    SCNERF_CUDA(cudaFuncSetAttribute((dpipe::field_dgrad_pipe_kernel<1, 1>), cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     dpipe::Cfg<1>::SMEM_BYTES));
-    SCNERF_CUDA(cudaFuncSetAttribute((dpipe::field_dgrad_pipe_kernel<3, 1>), cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     dpipe::Cfg<3>::SMEM_BYTES));
-    SCNERF_CUDA(cudaFuncSetAttribute((dpipe::field_dgrad_pipe_kernel<1, 2>), cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     dpipe::Cfg<1>::SMEM_BYTES));
-    SCNERF_CUDA(cudaFuncSetAttribute((dpipe::field_dgrad_pipe_kernel<3, 2>), cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     dpipe::Cfg<3>::SMEM_BYTES));
-  }
   if (dev < 64) done[dev] = true;
   return 0;
 }
 inline int dgrad_n_slabs() {      // the same for both d(PE) widths (only N of two stages differs)
   static int n = -1;
-  if (n < 0) { static eng::Plan P = dgrad::make_plan<64>(); n = P.n_slabs; }
+  if (n < 0) { static eng::Plan P = dgrad::make_plan<96>(); n = P.n_slabs; }
   return n;
 }
 
@@ -621,13 +555,13 @@ inline int field_tc_bwd_impl(const scnerf_mlp& m, const scnerf_mlp& g, const flo
   const int64_t P = N * S;
   const int T = (int)cdiv(P, 128);
   fused::PackSrc src = make_pack_src(m);
-  const bool dp = XN == 64 && dgrad_pipe_enabled();
-  if (dp) {
+  constexpr bool dp = XN == 64;      // 3-D points: N-half pipelined chain; 4-D points: the serial chain (96-wide d(PE))
+  if constexpr (dp) {
     rc = dpipe_plan_init();
     if (rc) return rc;
     SCNERF_LAUNCH((dpipe::pack_dpipe_kernel<NSPLIT>), dim3(1, (unsigned)dpipe_plan_host().n_slabs), 256, 0, stream, src, G.wimg);
   } else {
-    SCNERF_LAUNCH((dgrad::pack_dgrad_kernel<NSPLIT, XN>), dim3(2, (unsigned)dgrad_n_slabs()), 256, 0, stream, src, G.wimg);
+    SCNERF_LAUNCH((dgrad::pack_dgrad_kernel<NSPLIT, 96>), dim3(2, (unsigned)dgrad_n_slabs()), 256, 0, stream, src, G.wimg);
   }
   SCNERF_LAUNCH(fused::pack_consts_kernel, (unsigned)cdiv(fused::C_TOTAL, 256), 256, 0, stream, src, B.tc_cbuf);
   dgrad::Args a{};
@@ -636,16 +570,12 @@ inline int field_tc_bwd_impl(const scnerf_mlp& m, const scnerf_mlp& g, const flo
   a.g_raw = g_raw; a.wimg = G.wimg; a.cbuf = B.tc_cbuf;
   for (int i = 0; i < 8; ++i) a.out_dz[i] = G.dz[i];
   a.relu_bits = I.relu_bits; a.out_dfeat = G.dfeat; a.out_dzv = G.dzv; a.g_pts = G.g_pts; a.g_vd = G.g_vd;
-  if (dp && epi_roll_level() >= 2)
-    SCNERF_LAUNCH((dpipe::field_dgrad_pipe_kernel<NSPLIT, 2>), std::min(device_sm_count(), T), 320,
-                  (dpipe::Cfg<NSPLIT>::SMEM_BYTES), stream, a);
-  else if (dp && epi_roll_enabled())
+  if constexpr (dp)
     SCNERF_LAUNCH((dpipe::field_dgrad_pipe_kernel<NSPLIT, 1>), std::min(device_sm_count(), T), 320,
                   (dpipe::Cfg<NSPLIT>::SMEM_BYTES), stream, a);
-  else if (dp) SCNERF_LAUNCH((dpipe::field_dgrad_pipe_kernel<NSPLIT>), std::min(device_sm_count(), T), 320,
-                             (dpipe::Cfg<NSPLIT>::SMEM_BYTES), stream, a);
-  else SCNERF_LAUNCH((dgrad::field_fused_dgrad_kernel<NSPLIT, XN>), std::min(device_sm_count(), T), 320,
-                     (dgrad::Cfg<NSPLIT, XN>::SMEM_BYTES), stream, a);
+  else
+    SCNERF_LAUNCH((dgrad::field_fused_dgrad_kernel<NSPLIT, 96>), std::min(device_sm_count(), T), 320,
+                  (dgrad::Cfg<NSPLIT, 96>::SMEM_BYTES), stream, a);
   if (XN == 96) {
     if (d_viewdirs)
       SCNERF_LAUNCH(dgrad::reduce_vd_grad_kernel, (unsigned)cdiv(N, 4), 128, 0, stream, G.g_vd, N, S, d_viewdirs);
@@ -659,7 +589,9 @@ inline int field_tc_bwd_impl(const scnerf_mlp& m, const scnerf_mlp& g, const flo
     // CTAs per job in proportion to the measured cycles per K=16 slot of each job (profiles/README.md, r1h):
     // J0 issues 12 N=64 MMAs, J8 also reduces d(alpha_linear.weight), J9 has the narrowest slab
     static const int weight[wgrad::NJOBS] = {1385, 1170, 1170, 1170, 1170, 1170, 1170, 1170, 1500, 1100};
-    const int ncta = std::max(device_sm_count(), wgrad::NJOBS);
+    static int ncta_env = -1;     // experiment knob: wgrad on fewer SMs (is it still HBM-bound?  profiles/README.md, round 2)
+    if (ncta_env < 0) { const char* e = getenv("SCNERF_WGRAD_CTAS"); ncta_env = e ? atoi(e) : 0; }
+    const int ncta = std::max(ncta_env > 0 ? std::min(ncta_env, device_sm_count()) : device_sm_count(), wgrad::NJOBS);
     int wsum = 0, used = 0, n[wgrad::NJOBS];
     for (int j = 0; j < wgrad::NJOBS; ++j) wsum += weight[j];
     for (int j = 0; j < wgrad::NJOBS; ++j) { n[j] = std::max(1, ncta * weight[j] / wsum); used += n[j]; }
@@ -708,8 +640,8 @@ inline int field_tc_bwd_impl(const scnerf_mlp& m, const scnerf_mlp& g, const flo
   }
   SCNERF_LAUNCH((wgrad::field_wgrad_kernel<NSPLIT>), (unsigned)w.cta0[wgrad::NJOBS], 320,
                 wgrad::Cfg<NSPLIT>::SMEM_BYTES, stream, w);
-  SCNERF_LAUNCH((wgrad::head_wgrad_img_kernel<(NSPLIT == 3 ? 2 : 1)>), (unsigned)std::min(T, 2 * device_sm_count()), 128, 0,
-                stream, I.hv, g_raw, P, T, g.rgb_w, g.rgb_b, g.alpha_b);
+  SCNERF_LAUNCH((wgrad::head_wgrad_img_kernel<(NSPLIT == 3 ? 2 : 1)>), (unsigned)std::min(T, 8 * device_sm_count()), 128, 0,
+                stream, I.hv, g_raw, P, T, g.rgb_w, g.rgb_b, g.alpha_b);   // 8 CTAs/SM: the loop is load-latency bound
   return 0;
 }
 inline int field_tc_bwd(const scnerf_mlp& m, const scnerf_mlp& g, int precision, const float* rays, int ray_cols,

@@ -187,7 +187,7 @@ __global__ void __launch_bounds__(320, 1) field_fused_dgrad_kernel(const __grid_
             f[j] = gr.x * cst[fused::C_WRGB + c0 + j] + gr.y * cst[fused::C_WRGB + 128 + c0 + j] +
                    gr.z * cst[fused::C_WRGB + 256 + c0 + j];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) f[j] = ((mvw[cc] >> j) & 1u) ? f[j] : 0.f;
+          for (int j = 0; j < 32; ++j) f[j] = eng::relu_bit(mvw[cc], j) ? f[j] : 0.f;
           uint32_t hi[16], lo[16];
           eng::split32<SPLIT, false>(f, hi, lo);
           tc::tmem_st16(T_AHI + lane_base + (uint32_t)(c0 >> 1), hi);
@@ -355,7 +355,7 @@ __global__ void __launch_bounds__(320, 1) field_fused_dgrad_kernel(const __grid_
             for (int j = 0; j < 32; ++j) f[j] = fmaf(gr.w, cst[fused::C_WALPHA + cu + j], f[j]);
           }
 #pragma unroll
-          for (int j = 0; j < 32; ++j) f[j] = ((mk[cc] >> j) & 1u) ? f[j] : 0.f;
+          for (int j = 0; j < 32; ++j) f[j] = eng::relu_bit(mk[cc], j) ? f[j] : 0.f;
           uint32_t hi[16], lo[16];
           eng::split32<SPLIT, false>(f, hi, lo);
           tc::tmem_st16(T_AHI + lane_base + (uint32_t)(cu >> 1), hi);

@@ -105,7 +105,6 @@ template <int NSPLIT_> struct Cfg {
   static constexpr int NSLOT = NSPLIT_ == 1 ? 6 : 4;
   static constexpr int SLOT_BYTES = 16384;
   static_assert(PLAN.n_slabs % (GROUP * NSLOT) == 0, "ring size must divide the slab-group count");
-  static constexpr int STD_A0 = 1, STD_A1 = 3, STD_B0 = 5, STD_B1 = 8;   // runs of identical stages (rolled MMA issue loop)
   static constexpr int LO_BYTES = NSPLIT_ == 3 ? 3 * 32768 : 0;
   static constexpr int OFF_RING = 0;
   static constexpr int OFF_LO = NSLOT * SLOT_BYTES;
@@ -193,7 +192,7 @@ __device__ __forceinline__ void epi_half(const Args& a, const float* cst, const 
         for (int j = 0; j < 32; ++j) f[j] = fmaf(gr.w, cst[fused::C_WALPHA + cu + j], f[j]);
       }
 #pragma unroll
-      for (int j = 0; j < 32; ++j) f[j] = ((mk[cc] >> j) & 1u) ? f[j] : 0.f;
+      for (int j = 0; j < 32; ++j) f[j] = eng::relu_bit(mk[cc], j) ? f[j] : 0.f;
       uint32_t hi[16], lo[16];
       eng::split32<SPLIT, false>(f, hi, lo);
       constexpr int buf_col = H == 0 ? ((T + 1) & 1) * 64 : 128;
@@ -276,7 +275,7 @@ __device__ __forceinline__ void epi_half_rt(const Args& a, const fpipe::PCtx& c,
     const int cu = H * 128 + cb;            // output column
     float f[32];
 #pragma unroll
-    for (int j = 0; j < 32; ++j) f[j] = ((mk[cc] >> j) & 1u) ? __uint_as_float(v[cc][j]) : 0.f;
+    for (int j = 0; j < 32; ++j) f[j] = eng::relu_bit(mk[cc], j) ? __uint_as_float(v[cc][j]) : 0.f;
     uint32_t hi[16], lo[16];
     eng::split32<SPLIT, false>(f, hi, lo);
     tc::tmem_st16(c.e.tmem_ahi + lane_base + buf_col + (uint32_t)(cb >> 1), hi);
@@ -301,7 +300,7 @@ __device__ __forceinline__ void epi_tile(const Args& a, const float* cst, const 
     epi_half<NSPLIT, (int)Ts, 1>(a, cst, c, lo_area, gx_s, out_s, lane_base, half, row, tile, p, valid, gr)), ...);
 }
 
-template <int NSPLIT, int ROLL = 0>     // ROLL: 0 fully unrolled (default), 1 rolled epilogue, 2 + rolled MMA issue loop
+template <int NSPLIT, int ROLL = 1>     // ROLL: 1 = trunk stages T2, T3, T5..T8 from one copy of the epilogue code (the build in use); 0 = unrolled
 __global__ void __launch_bounds__(320, 1) field_dgrad_pipe_kernel(const __grid_constant__ Args a) {
   using C = Cfg<NSPLIT>;
   constexpr bool SPLIT = NSPLIT == 3;
@@ -340,12 +339,12 @@ __global__ void __launch_bounds__(320, 1) field_dgrad_pipe_kernel(const __grid_c
   ctx.smem_lo = tc::smem_u32(lo_area);
   ctx.dbg = nullptr; ctx.dbg_tiles = 0;
 
+  const int tile_count = (int)blockIdx.x < a.num_tiles ? (a.num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
   if (warp == 0) {
-    if (lane == 0) eng::producer_loop<C>(ctx.e, a.wimg, a.num_tiles);
+    if (lane == 0) eng::producer_loop_n<C>(ctx.e, a.wimg, tile_count);
   } else if (warp == 1) {
     if (lane == 0) {
-      if constexpr (ROLL >= 2) fpipe::mma_loop_rolled<C>(ctx, a.num_tiles);
-      else fpipe::mma_loop<C>(ctx, a.num_tiles);
+      fpipe::mma_loop_r<C>(ctx, (int)blockIdx.x, a.num_tiles, (int)gridDim.x);
     }
   } else {
     const int quad = warp & 3, half = (warp - 2) >> 2;
@@ -369,7 +368,7 @@ __global__ void __launch_bounds__(320, 1) field_dgrad_pipe_kernel(const __grid_c
           f[j] = gr.x * cst[fused::C_WRGB + c0 + j] + gr.y * cst[fused::C_WRGB + 128 + c0 + j] +
                  gr.z * cst[fused::C_WRGB + 256 + c0 + j];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) f[j] = ((mv >> j) & 1u) ? f[j] : 0.f;
+        for (int j = 0; j < 32; ++j) f[j] = eng::relu_bit(mv, j) ? f[j] : 0.f;
         uint32_t hi[16], lo[16];
         eng::split32<SPLIT, false>(f, hi, lo);
         tc::tmem_st16(ctx.e.tmem_ahi + lane_base + (uint32_t)(c0 >> 1), hi);          // T0's A operand: P0

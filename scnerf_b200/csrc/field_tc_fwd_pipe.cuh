@@ -147,14 +147,15 @@ template <int NSPLIT_, int XS_ = 4> struct Cfg {
   static constexpr int NSLOT = NSPLIT_ == 1 ? 6 : (XS_ == 4 ? 4 : 3);
   static constexpr int SLOT_BYTES = 16384;
   static_assert(PLAN.n_slabs % (GROUP * NSLOT) == 0, "ring size must divide the slab-group count");
-  static constexpr int STD_A0 = 1, STD_A1 = 4, STD_B0 = 6, STD_B1 = 8;   // runs of identical stages (rolled MMA issue loop)
   static constexpr int LO_BYTES = NSPLIT_ == 3 ? 3 * 32768 : 0;
   static constexpr int OFF_RING = 0;
   static constexpr int OFF_A = NSLOT * SLOT_BYTES;
   static constexpr int OFF_LO = OFF_A + ALay<NSPLIT_, XS_>::BYTES;
   static constexpr int OFF_C = OFF_LO + LO_BYTES;
   static constexpr int OFF_OUT = OFF_C + ((C_TOTAL * 4 + 127) / 128) * 128;   // [128][4] head partial sums
-  static constexpr int OFF_BAR = OFF_OUT + 128 * 4 * 4;
+  static constexpr int COMP_MAX_G = 3;                            // fused composite: up to 3 tiles (384 samples) of raw values
+  static constexpr int OFF_COMP = OFF_OUT + 128 * 4 * 4;
+  static constexpr int OFF_BAR = OFF_COMP + COMP_MAX_G * 128 * 4 * 4;
   static constexpr int SMEM_BYTES = OFF_BAR + (2 * NSLOT + 6) * 8 + 16;
   static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB shared-memory limit");
 };
@@ -170,9 +171,16 @@ struct PCtx {
 //   0 MMA passed aq[0], 1 MMA passed aq[2], 2 MMA committed h0, 3 MMA committed h1,
 //   4 epilogue saw accf[0], 5 epilogue finished h0, 6 epilogue saw accf[1], 7 epilogue finished h1,
 //   8 + 4h: accumulator loads of half h done, 9 + 4h / 10 + 4h: quarter 2h / 2h+1 handed over
+// Compiled in only with -DSCNERF_TIMELINE (build.sh -DSCNERF_TIMELINE; tools/timeline_pipe.py needs such a build): even
+// predicated off, the stamps cost the single MMA-issuing thread a spill/reload pair around every clock read once the
+// kernel sat at its 168-register cap (round 2: 60 -> 992 bytes of spill code, +1 ms per step on the training forward).
 __device__ __forceinline__ void stamp(const PCtx& c, int tile_iter, int stage, int slot) {
+#ifdef SCNERF_TIMELINE
   if (c.dbg != nullptr && blockIdx.x == 0 && tile_iter < c.dbg_tiles)
     c.dbg[((size_t)tile_iter * NSTAGE + stage) * 16 + slot] = clock64();
+#else
+  (void)c; (void)tile_iter; (void)stage; (void)slot;
+#endif
 }
 
 template <class K, int I>
@@ -240,131 +248,25 @@ template <class K, size_t... Is>
 __device__ __forceinline__ void mma_tile(const PCtx& c, uint32_t tp, int tile_iter, std::index_sequence<Is...>) {
   (mma_step<K, (int)Is>(c, tp, tile_iter), ...);
 }
+// This CTA's tiles as a range.  The FORM of this loop matters: the issue thread's 336 unrolled steps leave ptxas no spare
+// register at the kernel's 168 cap, and a counted loop (`for it < count`) instead of this compare-against-end form made
+// it spill a register around every mbarrier wait of the issue thread (60 -> 976 bytes of spill code, measured +1 ms per
+// step on the training forward; bisected with -Xptxas -v, profiles/README.md round 2).
 template <class K>
-__device__ __forceinline__ void mma_loop(const PCtx& c, int num_tiles) {
+__device__ __forceinline__ void mma_loop_r(const PCtx& c, int first, int end, int stride) {
   uint32_t tp = 0;
   int it = 0;
-  for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, tp ^= 1u, ++it)
+  for (int tile = first; tile < end; tile += stride, tp ^= 1u, ++it)
     mma_tile<K>(c, tp, it, std::make_index_sequence<K::PLAN.n_slabs>{});
 }
 
-// ---- rolled MMA issue loop (experimental, ROLL >= 2, split-bf16 / 3-D points only) -------------------------------------
-// Stages 1-4 and 6-8 issue the same 34 half-slabs (bias + 16 hidden K-slabs, twice); they differ in the parity of the P
-// buffer, of the stage barriers and in where the weight ring stands.  The rolled loop issues them from ONE unrolled copy
-// of a stage with those three as run-time values (one add / and per descriptor), instead of 7 x 34 unrolled steps: the
-// issue thread's straight-line code shrinks from ~160 KB to ~60 KB.  Stage boundaries fall on ring-group boundaries
-// because GROUP = 2 and every stage has an even slab count.
-// K::STD_A0..STD_A1 and K::STD_B0..STD_B1 are the two runs of standard stages; K::STD_A0 is the template.
-template <class K> struct StdStage {
-  __host__ __device__ static constexpr int first_of(int st) { int i = 0; while (i < K::PLAN.n_slabs && K::PLAN.slab[i].stage != st) ++i; return i; }
-  __host__ __device__ static constexpr int count_of(int st) { int n = 0; for (int i = 0; i < K::PLAN.n_slabs; ++i) n += K::PLAN.slab[i].stage == st; return n; }
-  static constexpr int TEMPLATE = K::STD_A0;
-  static constexpr int FIRST = first_of(TEMPLATE);
-  static constexpr int COUNT = count_of(TEMPLATE);
-  __host__ __device__ static constexpr bool same_as_template(int st) {
-    const int f = first_of(st);
-    if (count_of(st) != COUNT) return false;
-    for (int i = 0; i < COUNT; ++i) {
-      const eng::SlabDef a = K::PLAN.slab[FIRST + i], b = K::PLAN.slab[f + i];
-      if (b.stage != st || a.n != b.n || a.acc_col != b.acc_col || a.a_kind != b.a_kind || a.flags != b.flags || a.pad != b.pad) return false;
-      // operand addresses may differ only by the parity of the P buffer
-      const int dp = ((st & 1) - (TEMPLATE & 1));
-      if (a.a_kind == eng::A_MIX && a.a_off < 128 && (b.a_off != a.a_off + dp * 64 || b.a_lo_delta * 16 != a.a_lo_delta * 16 + dp * 32768)) return false;
-      if ((a.a_kind != eng::A_MIX || a.a_off >= 128) && (b.a_off != a.a_off || b.a_lo_delta != a.a_lo_delta)) return false;
-    }
-    return true;
-  }
-  __host__ __device__ static constexpr bool all_same() {
-    for (int st = K::STD_A0; st <= K::STD_A1; ++st) if (!same_as_template(st) || first_of(st) != FIRST + (st - K::STD_A0) * COUNT) return false;
-    for (int st = K::STD_B0; st <= K::STD_B1; ++st) if (!same_as_template(st) || first_of(st) != first_of(K::STD_B0) + (st - K::STD_B0) * COUNT) return false;
-    return true;
-  }
-  static_assert(FIRST % K::GROUP == 0 && COUNT % K::GROUP == 0 && first_of(K::STD_B0) % K::GROUP == 0,
-                "standard stages must start and end on ring-group boundaries");
-  static_assert(all_same(), "the standard stages must issue the same slab sequence in contiguous runs");
-};
-template <class K, int I1>
-__device__ __forceinline__ void mma_step_std(const PCtx& c, uint32_t tp, int tile_iter, int st, uint32_t g0) {
-  constexpr eng::SlabDef d = K::PLAN.slab[StdStage<K>::FIRST + I1];       // stage 1's slab as the template
-  constexpr bool SPLIT = K::NSPLIT == 3;
-  constexpr int g = I1 / K::GROUP;
-  constexpr bool wraps_odd = (((K::PLAN.n_slabs / K::GROUP) / K::NSLOT) & 1) != 0;
-  constexpr uint32_t in_slot = eng::group_bytes<K>(StdStage<K>::FIRST + g * K::GROUP, StdStage<K>::FIRST + I1);
-  const uint32_t G = g0 + (uint32_t)g;                                    // ring group number inside the tile
-  const uint32_t idx = G % (uint32_t)K::NSLOT, wrap = G / (uint32_t)K::NSLOT;
-  const uint32_t par = (uint32_t)st & 1u;
-  if constexpr ((d.flags & eng::F_STAGE_BEGIN) != 0) {
-    eng::mbar_wait_a(c.aq_addr, par);
-    tc::tc_fence_after();
-    stamp(c, tile_iter, st, 0);
-  }
-  if constexpr ((d.flags & eng::F_WAIT_Q1) != 0) { eng::mbar_wait_a(c.aq_addr + 8, par); tc::tc_fence_after(); }
-  if constexpr ((d.flags & eng::F_WAIT_Q2) != 0) { eng::mbar_wait_a(c.aq_addr + 16, par); tc::tc_fence_after(); stamp(c, tile_iter, st, 1); }
-  if constexpr ((d.flags & eng::F_WAIT_Q3) != 0) { eng::mbar_wait_a(c.aq_addr + 24, par); tc::tc_fence_after(); }
-  if constexpr (I1 % K::GROUP == 0) {
-    eng::mbar_wait_a(c.e.full_addr + idx * 8, (wrap & 1u) ^ (wraps_odd ? tp : 0u));
-    tc::tc_fence_after();
-  }
-  constexpr uint32_t idesc = tc::idesc_bf16_f32(TILE_M, d.n);
-  constexpr uint32_t LBO_B = (uint32_t)d.n * 16u;
-  const uint32_t slot = c.e.ring_addr + idx * (uint32_t)K::SLOT_BYTES + in_slot;
-  const uint64_t b_hi = eng::desc_at<LBO_B, 128>(slot);
-  const uint64_t b_lo = eng::desc_at<LBO_B, 128>(slot + (uint32_t)d.n * 32u);
-  const uint32_t acc = c.e.tmem_acc + d.acc_col;
-  constexpr uint32_t first = (d.flags & eng::F_ZERO_ACC) ? 0u : 1u;
-  if constexpr (d.a_kind == eng::A_MIX) {
-    // slabs of the P half follow the stage's parity (the template stage's is compiled in), Q slabs do not
-    constexpr bool in_p = d.a_off < 128;
-    constexpr uint32_t tpar = (uint32_t)(StdStage<K>::TEMPLATE & 1);
-    const uint32_t a_col = in_p ? (uint32_t)d.a_off - tpar * 64u + par * 64u : (uint32_t)d.a_off;
-    const uint32_t a_lo = in_p ? (uint32_t)d.a_lo_delta * 16u - tpar * 32768u + par * 32768u : (uint32_t)d.a_lo_delta * 16u;
-    tc::mma_ts(acc, c.e.tmem_ahi + a_col, b_hi, idesc, first);
-    if constexpr (SPLIT) {
-      tc::mma_ss(acc, eng::desc_at<2048, 128>(c.smem_lo + a_lo), b_hi, idesc, 1);
-      tc::mma_ts(acc, c.e.tmem_ahi + a_col, b_lo, idesc, 1);
-    }
-  } else {
-    const uint32_t a_addr = c.e.smem_a + (uint32_t)d.a_off * 16u;
-    const uint64_t a_hi = eng::desc_at<2048, 128>(a_addr);
-    tc::mma_ss(acc, a_hi, b_hi, idesc, first);
-    if constexpr (SPLIT) {
-      if constexpr ((d.flags & eng::F_HI_ONLY_A) == 0)
-        tc::mma_ss(acc, eng::desc_at<2048, 128>(a_addr + (uint32_t)d.a_lo_delta * 16u), b_hi, idesc, 1);
-      tc::mma_ss(acc, a_hi, b_lo, idesc, 1);
-    }
-  }
-  if constexpr (I1 % K::GROUP == K::GROUP - 1) eng::commit_a(c.e.empty_addr + idx * 8);
-  if constexpr ((d.flags & eng::F_STAGE_END) != 0) {
-    eng::commit_a(c.accf_addr + d.pad * 8);
-    stamp(c, tile_iter, st, 2 + d.pad);
-  }
-}
-template <class K, size_t... Is>
-__device__ __forceinline__ void mma_std_stage(const PCtx& c, uint32_t tp, int tile_iter, int st, uint32_t g0, std::index_sequence<Is...>) {
-  (mma_step_std<K, (int)Is>(c, tp, tile_iter, st, g0), ...);
-}
-template <class K, int I0, size_t... Is>
-__device__ __forceinline__ void mma_range(const PCtx& c, uint32_t tp, int tile_iter, std::index_sequence<Is...>) {
-  (mma_step<K, I0 + (int)Is>(c, tp, tile_iter), ...);
-}
-template <class K>
-__device__ __forceinline__ void mma_loop_rolled(const PCtx& c, int num_tiles) {
-  using SS = StdStage<K>;
-  constexpr int FA = SS::FIRST, N1 = SS::COUNT, FB = SS::first_of(K::STD_B0);
-  constexpr int EA = FA + (K::STD_A1 - K::STD_A0 + 1) * N1, EB = FB + (K::STD_B1 - K::STD_B0 + 1) * N1;
-  uint32_t tp = 0;
-  int it = 0;
-  for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, tp ^= 1u, ++it) {
-    mma_range<K, 0>(c, tp, it, std::make_index_sequence<FA>{});                        // stages before the first run
-#pragma unroll 1
-    for (int st = K::STD_A0; st <= K::STD_A1; ++st)
-      mma_std_stage<K>(c, tp, it, st, (uint32_t)((FA + (st - K::STD_A0) * N1) / K::GROUP), std::make_index_sequence<N1>{});
-    mma_range<K, EA>(c, tp, it, std::make_index_sequence<FB - EA>{});                  // the odd stage between the runs
-#pragma unroll 1
-    for (int st = K::STD_B0; st <= K::STD_B1; ++st)
-      mma_std_stage<K>(c, tp, it, st, (uint32_t)((FB + (st - K::STD_B0) * N1) / K::GROUP), std::make_index_sequence<N1>{});
-    mma_range<K, EB>(c, tp, it, std::make_index_sequence<K::PLAN.n_slabs - EB>{});     // the tail stages
-  }
+// Alpha-composite of the rays of one group from the raw values parked in shared memory (one warp per ray).  Kept OUT
+// of line: inlined into the persistent kernel it raised the epilogue's register pressure (72 -> 2 KB of spill code,
+// training forward 3.5 -> 4.6 ms per step); it runs once per ray group, a call costs nothing there.
+__device__ __noinline__ void composite_group(const CompositeArgs& ca, const float* comp_s, int64_t ray0, int n_rays, int S,
+                                             int ewarp, int lane) {
+  for (int rr = ewarp; rr < n_rays; rr += 8)
+    composite_ray(ca, ray0 + rr, lane, comp_s + (size_t)rr * S * 4, 4);
 }
 
 // Epilogue of N-half H of stage S for this warp's columns (compile-time stage parameters).
@@ -388,6 +290,7 @@ __device__ __forceinline__ void epi_half(const Args& a, const float* cst, const 
   for (int cc = 0; cc < nchunk; ++cc) tc::tmem_ld32(c.e.tmem_acc + lane_base + H * 128 + cw + cc * CSTEP, v[cc]);
   tc::tmem_ld_wait();
   if (threadIdx.x == 64) stamp(c, tile_iter, S, 8 + 4 * H);
+  uint32_t mbits[nchunk];                   // ReLU-mask words of this warp's chunks (training), see eng::relu_mask16
 #pragma unroll
   for (int cc = 0; cc < nchunk; ++cc) {
     const int cu = cbase + cc * CSTEP;      // layer-output column of v[cc][0]
@@ -412,9 +315,11 @@ __device__ __forceinline__ void epi_half(const Args& a, const float* cst, const 
         rgb[2] = fmaf(t, cst[C_WRGB + 256 + cu + j], rgb[2]);
       }
     }
+    if (S == 9 && a.img_out[9].base == nullptr) mbits[cc] = eng::relu_mask32f(v[cc]);
     if (S != 9 || a.img_out[9].base != nullptr) {
       uint32_t hi[16], lo[16];
-      eng::split32<SPLIT, d.relu != 0>(f, hi, lo);
+      if constexpr (d.relu != 0) eng::split32_relu<SPLIT>(f, hi, lo, mbits[cc]);
+      else eng::split32<SPLIT, false>(f, hi, lo);
       if constexpr (S != 9) {
         // next stage's A operand: columns [0,128) -> P[(S+1)&1], [128,256) -> Q
         const int cb = cw + cc * CSTEP;     // column inside the 128-wide buffer
@@ -447,12 +352,7 @@ __device__ __forceinline__ void epi_half(const Args& a, const float* cst, const 
       constexpr int L = S == 9 ? 8 : S;
       uint32_t* mw = reinterpret_cast<uint32_t*>(a.relu_bits + ((size_t)(tile * 9 + L) * 2 + H) * 128 + row) + (cw >> 5);   // chunk cc -> word (cw + cc * CSTEP) / 32
 #pragma unroll
-      for (int cc = 0; cc < nchunk; ++cc) {
-        uint32_t bits = 0;
-#pragma unroll
-        for (int j = 0; j < 32; ++j) bits |= (__uint_as_float(v[cc][j]) > 0.f ? 1u : 0u) << j;
-        mw[cc * (CSTEP / 32)] = bits;
-      }
+      for (int cc = 0; cc < nchunk; ++cc) mw[cc * (CSTEP / 32)] = mbits[cc];
     }
   }
 }
@@ -480,6 +380,7 @@ __device__ __forceinline__ void epi_half_rt(const Args& a, const PCtx& c, uint8_
   const uint32_t buf_lo = H == 0 ? par * 32768u : 65536u;
   float* const dump_s = a.dump[S];
   const bool has_img = a.img_out[S].base != nullptr;
+  uint32_t mbits[2];                        // ReLU-mask words of this warp's two chunks (eng::relu_mask16)
 #pragma unroll
   for (int cc = 0; cc < 2; ++cc) {
     const int cu = cbase + cc * 64;         // layer-output column of v[cc][0]
@@ -492,7 +393,7 @@ __device__ __forceinline__ void epi_half_rt(const Args& a, const PCtx& c, uint8_
       for (int j = 0; j < 32; ++j) dp[j] = fmaxf(f[j], 0.f);
     }
     uint32_t hi[16], lo[16];
-    eng::split32<SPLIT, true>(f, hi, lo);
+    eng::split32_relu<SPLIT>(f, hi, lo, mbits[cc]);
     const int cb = cw + cc * 64;            // column inside the 128-wide buffer
     tc::tmem_st16(c.e.tmem_ahi + lane_base + buf_col + (uint32_t)(cb >> 1), hi);
     if constexpr (SPLIT) {
@@ -512,13 +413,8 @@ __device__ __forceinline__ void epi_half_rt(const Args& a, const PCtx& c, uint8_
   if (threadIdx.x == 64) stamp(c, tile_iter, S, 5 + 2 * H);
   if (a.relu_bits != nullptr) {      // after the hand-off: off the MMA's critical path (layout: see epi_half)
     uint32_t* mw = reinterpret_cast<uint32_t*>(a.relu_bits + ((size_t)(tile * 9 + S) * 2 + H) * 128 + row) + (cw >> 5);
-#pragma unroll
-    for (int cc = 0; cc < 2; ++cc) {
-      uint32_t bits = 0;
-#pragma unroll
-      for (int j = 0; j < 32; ++j) bits |= (__uint_as_float(v[cc][j]) > 0.f ? 1u : 0u) << j;
-      mw[cc * 2] = bits;
-    }
+    mw[0] = mbits[0];
+    mw[2] = mbits[1];
   }
 }
 template <int NSPLIT, size_t... Ss>
@@ -529,7 +425,7 @@ __device__ __forceinline__ void epi_tile(const Args& a, const float* cst, const 
     epi_half<NSPLIT, (int)Ss, 1>(a, cst, c, lo_area, lane_base, half, row, tile, p, valid, alpha, rgb, tile_iter)), ...);
 }
 
-template <int NSPLIT, int XS = 4, int ROLL = 0>     // ROLL: 0 fully unrolled (default), 1 rolled epilogue, 2 + rolled MMA issue loop
+template <int NSPLIT, int XS = 4, int ROLL = 0>     // ROLL: 0 fully unrolled epilogue (4-D points), 1 stages 0-6 from one copy of the code (3-D points)
 __global__ void __launch_bounds__(320, 1) field_fwd_pipe_kernel(const __grid_constant__ Args a) {
   using C = Cfg<NSPLIT, XS>;
   using L = ALay<NSPLIT, XS>;
@@ -539,6 +435,7 @@ __global__ void __launch_bounds__(320, 1) field_fwd_pipe_kernel(const __grid_con
   uint8_t* lo_area = psm + C::OFF_LO;
   float* cst = reinterpret_cast<float*>(psm + C::OFF_C);
   float* out_s = reinterpret_cast<float*>(psm + C::OFF_OUT);
+  float* comp_s = reinterpret_cast<float*>(psm + C::OFF_COMP);      // [comp_G * 128][4] raw values of the current ray group
   uint64_t* full = reinterpret_cast<uint64_t*>(psm + C::OFF_BAR);
   uint64_t* empty = full + C::NSLOT;
   uint64_t* accf = empty + C::NSLOT;      // [2]
@@ -575,20 +472,23 @@ __global__ void __launch_bounds__(320, 1) field_fwd_pipe_kernel(const __grid_con
   ctx.smem_lo = tc::smem_u32(lo_area);
   ctx.dbg = a.dbg; ctx.dbg_tiles = a.dbg_tiles;
 
+  int tile_first, tile_count, tile_stride;
+  fused::cta_tiles(a, tile_first, tile_count, tile_stride);
+  // (one loop form for both tile mappings: a second instantiation of the 336-step unrolled issue code made ptxas spill
+  //  inside the MMA-issuing thread — 60 -> 1972 bytes — and cost the training forward 1 ms per step)
   if (warp == 0) {
-    if (lane == 0) eng::producer_loop<C>(ctx.e, a.wimg, a.num_tiles);
+    if (lane == 0) eng::producer_loop_n<C>(ctx.e, a.wimg, tile_count);
   } else if (warp == 1) {
     if (lane == 0) {
-      if constexpr (ROLL >= 2 && NSPLIT == 3 && XS == 4) mma_loop_rolled<C>(ctx, a.num_tiles);
-      else mma_loop<C>(ctx, a.num_tiles);
+      mma_loop_r<C>(ctx, tile_first, tile_first + tile_count * tile_stride, tile_stride);
     }
   } else {
     // ===================== epilogue: 8 warps, 2 per TMEM lane quadrant =============================
     const int quad = warp & 3, half = (warp - 2) >> 2;
     const int row = quad * 32 + lane;
     const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
-    int tile_iter = 0;
-    for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x, ++tile_iter) {
+    for (int tile_iter = 0; tile_iter < tile_count; ++tile_iter) {
+      const int tile = tile_first + tile_iter * tile_stride;
       const int64_t p = (int64_t)tile * TILE_M + row;
       const bool valid = p < a.P;
       float* dpe = a.dump_pe ? a.dump_pe + p * a.dump_pe_ld : nullptr;
@@ -671,12 +571,23 @@ __global__ void __launch_bounds__(320, 1) field_fwd_pipe_kernel(const __grid_con
       atomicAdd(out_s + row * 4 + 3, alpha);
       tc::tc_fence_before();
       asm volatile("bar.sync 1, 256;" ::: "memory");
-      if (half == 0 && valid) {
+      if (half == 0) {
         const float4 o = *reinterpret_cast<const float4*>(out_s + row * 4);
-        *reinterpret_cast<float4*>(a.raw + p * 4) =
-            make_float4(o.x + cst[C_SCAL + 1], o.y + cst[C_SCAL + 2], o.z + cst[C_SCAL + 3], o.w + cst[C_SCAL]);
+        const float4 r4 = make_float4(o.x + cst[C_SCAL + 1], o.y + cst[C_SCAL + 2], o.z + cst[C_SCAL + 3], o.w + cst[C_SCAL]);
+        if (valid && a.raw != nullptr) *reinterpret_cast<float4*>(a.raw + p * 4) = r4;
+        if (a.comp_on) *reinterpret_cast<float4*>(comp_s + ((tile_iter % a.comp_G) * TILE_M + row) * 4) = r4;
       }
       asm volatile("bar.sync 1, 256;" ::: "memory");   // out_s is re-zeroed by the next tile's prologue
+      if (a.comp_on && ((tile_iter % a.comp_G) == a.comp_G - 1 || tile_iter == tile_count - 1)) {
+        // the group's rays are complete: alpha-composite them from shared memory, one warp per ray (render.py:302-355)
+        const int g_first = tile - (tile_iter % a.comp_G);                  // first tile of this group
+        const int64_t p0 = (int64_t)g_first * TILE_M;
+        const int64_t p1 = (int64_t)(tile + 1) * TILE_M < a.P ? (int64_t)(tile + 1) * TILE_M : a.P;
+        const int n_rays = (int)((p1 - p0) / a.S);
+        const int64_t ray0 = p0 / a.S;
+        composite_group(a.comp, comp_s, ray0, n_rays, a.S, warp - 2, lane);
+        asm volatile("bar.sync 1, 256;" ::: "memory");   // comp_s is rewritten by the next group
+      }
     }
   }
   tc::tc_fence_before();

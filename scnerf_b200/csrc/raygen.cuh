@@ -325,6 +325,56 @@ __global__ void camera_matrices_kernel(scnerf_camera c, float* K_out, float* E_o
   }
 }
 
+// K4 = [fx_sign*fx, fy, cx, cy] and the two camera-to-world [3,4] blocks the PRD loss projects with
+// (model/ray_dist_loss.py:51-65,113-126), straight from the learnable parameters — and their backward into the camera
+// gradients.  The reference (and the first version here) builds get_intrinsic() / get_extrinsic() for ALL cameras with
+// ~60 eager torch kernels per call and back-propagates through them; this is one tiny launch each way.
+__global__ void camera_pair_fwd_kernel(scnerf_camera c, int64_t i0, int64_t i1, float fx_sign, float* __restrict__ K4,
+                                       float* __restrict__ E2) {
+  const int t = threadIdx.x;
+  if (t == 2) {
+    Intr K = load_intrinsics(c);
+    K4[0] = fx_sign * K.fx; K4[1] = K.fy; K4[2] = K.cx; K4[3] = K.cy;
+  }
+  if (t < 2) {
+    Pose P;
+    pose_from_params(c, t == 0 ? i0 : i1, P);
+    float* E = E2 + t * 12;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) { E[j * 4 + 0] = P.x[j]; E[j * 4 + 1] = P.y[j]; E[j * 4 + 2] = P.z[j]; E[j * 4 + 3] = P.t[j]; }
+  }
+}
+__global__ void camera_pair_bwd_kernel(scnerf_camera c, int64_t i0, int64_t i1, float fx_sign, const float* __restrict__ gK4,
+                                       const float* __restrict__ gE2, scnerf_camera_grads G) {
+  const int t = threadIdx.x;
+  if (t == 2 && G.intrinsics_noise && gK4) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      float init = c.intrinsics_initial[k];
+      float s = c.intrinsics_noise_scale * (c.multiplicative_noise ? init : 1.f);
+      atomicAdd(G.intrinsics_noise + k, gK4[k] * (k == 0 ? fx_sign : 1.f) * s);
+    }
+  }
+  if (t < 2 && G.extrinsics_noise && gE2) {
+    const int64_t ci = t == 0 ? i0 : i1;
+    Pose P;
+    pose_from_params(c, ci, P);
+    const float* g = gE2 + t * 12;
+    float gx[3], gy[3], gz[3], gt[3], g_a[3], g_b[3];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) { gx[j] = g[j * 4 + 0]; gy[j] = g[j * 4 + 1]; gz[j] = g[j * 4 + 2]; gt[j] = g[j * 4 + 3]; }
+    pose_bwd(P, gx, gy, gz, g_a, g_b);
+    float* ge = G.extrinsics_noise + ci * 9;
+    const float s = c.extrinsics_noise_scale;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      atomicAdd(ge + j, s * g_a[j]);
+      atomicAdd(ge + 3 + j, s * g_b[j]);
+      atomicAdd(ge + 6 + j, s * gt[j]);
+    }
+  }
+}
+
 // ---- per-step ray batch: NeRF/run_nerf.py:368-398 — from a slice of the shuffled global
 // ray indices to pixel coordinates (x, y), per-ray train-image index and target colours, in one pass.
 // The reference does this with numpy on the host and three H2D copies every step.

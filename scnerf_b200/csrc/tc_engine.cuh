@@ -62,8 +62,12 @@ struct Ctx {
   int dbg_tiles;
 };
 __device__ __forceinline__ void dbg_stamp(const Ctx& c, int tile_iter, int stage, int n_stages, int slot) {
+#ifdef SCNERF_TIMELINE      // (see fpipe::stamp)
   if (c.dbg != nullptr && blockIdx.x == 0 && tile_iter < c.dbg_tiles)
     c.dbg[((size_t)tile_iter * n_stages + stage) * 4 + slot] = clock64();
+#else
+  (void)c; (void)tile_iter; (void)stage; (void)n_stages; (void)slot;
+#endif
 }
 
 __device__ __forceinline__ void mbar_wait_a(uint32_t addr, uint32_t parity) {
@@ -121,6 +125,13 @@ template <class K>
 __device__ __forceinline__ void producer_loop(const Ctx& c, const uint8_t* __restrict__ wimg, int num_tiles) {
   uint32_t tp = 0;
   for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, tp ^= 1u)
+    producer_tile<K>(c, wimg, tp, std::make_index_sequence<K::PLAN.n_slabs>{});
+}
+
+template <class K>
+__device__ __forceinline__ void producer_loop_n(const Ctx& c, const uint8_t* __restrict__ wimg, int count) {
+  uint32_t tp = 0;
+  for (int it = 0; it < count; ++it, tp ^= 1u)
     producer_tile<K>(c, wimg, tp, std::make_index_sequence<K::PLAN.n_slabs>{});
 }
 
@@ -211,6 +222,48 @@ __device__ __forceinline__ void split32(const float (&f)[32], uint32_t (&hi)[16]
     }
   }
 }
+
+// ReLU + split + mask word in one pass (the forward's hidden layers).  hi = bf16(max(x, 0)) by cvt.rn.relu; the packed
+// compare m = (hi > 0) (0xffff per true half) then serves twice: it zeroes the lo halves of the clamped columns
+// (lo = bf16(x - hi) & m: one LOP3 per PAIR instead of an FMNMX per element on the residual's input) and it is the ReLU
+// mask the dgrad reads (bit j = column 2j, bit 16 + j = column 2j + 1).
+template <bool SPLIT>
+__device__ __forceinline__ void split32_relu(const float (&f)[32], uint32_t (&hi)[16], uint32_t (&lo)[16], uint32_t& bits) {
+  bits = 0;
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    hi[j] = cvt_relu_bf16x2(f[2 * j], f[2 * j + 1]);
+    uint32_t m;
+    asm("set.gt.u32.bf16x2 %0, %1, %2;" : "=r"(m) : "r"(hi[j]), "r"(0u));
+    bits |= m & (0x00010001u << j);
+    if (SPLIT) lo[j] = cvt_bf16x2(f[2 * j] - bf16lo_f(hi[j]), f[2 * j + 1] - bf16hi_f(hi[j])) & m;
+  }
+}
+
+// ---- ReLU masks (forward -> dgrad): one 32-bit word per 32 consecutive output columns of a row ----------------------
+// Bit layout follows the packed bf16 pairs the epilogue already holds: bit j = column 2j, bit 16 + j = column 2j + 1.
+// The forward derives the word from the post-ReLU hi halves with one packed compare per PAIR (set.gt.u32.bf16x2 gives
+// 0xffff per true half) and one LOP3 — the per-element FSETP + SEL + add chain of the first version was 28 % of the
+// training epilogue's instructions (160 of ~560 per thread and half-stage, cuobjdump).  bf16 keeps fp32's exponent
+// range, so "hi > 0" and "x > 0" differ only for |x| < 2^-133.
+__device__ __forceinline__ uint32_t relu_mask16(const uint32_t (&hi)[16]) {
+  uint32_t bits = 0;
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    uint32_t m;
+    asm("set.gt.u32.bf16x2 %0, %1, %2;" : "=r"(m) : "r"(hi[j]), "r"(0u));
+    bits |= m & (0x00010001u << j);
+  }
+  return bits;
+}
+// the same word from 32 fp32 values (paths that do not form the packed pairs)
+__device__ __forceinline__ uint32_t relu_mask32f(const uint32_t (&v)[32]) {
+  uint32_t bits = 0;
+#pragma unroll
+  for (int j = 0; j < 32; ++j) bits |= (__uint_as_float(v[j]) > 0.f ? 1u : 0u) << ((j >> 1) + ((j & 1) << 4));
+  return bits;
+}
+__device__ __forceinline__ bool relu_bit(uint32_t w, int j) { return ((w >> ((j >> 1) + ((j & 1) << 4))) & 1u) != 0u; }
 
 // ---- tile-image dumps (the wgrad kernel's operand format) ---------------------------------------------
 // A [128 samples x F features] bf16 tile is stored as 8 K16-slabs (16 samples each); inside a slab the

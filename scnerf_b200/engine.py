@@ -61,12 +61,13 @@ class TrainStep:
         self.h2d_bytes = N * (16 + 8 + 12)
         self.d2h_bytes = 4
 
-    def _call(self, on_host):
+    def _call(self, on_host, zero=True):
         cam = self.cam.c_struct()
         mc = self.net_c.c_struct()
         mf = self.net_f.c_struct() if self.net_f is not None else None
         self.cfg.seed = (self.cfg.seed + 1) & 0xFFFFFFFFFFFFFFFF
-        self.grads.zero_()
+        if zero:
+            self.grads.zero_()
         _lib.check(self.lib.scnerf_train_step(
             C.byref(cam), C.byref(self.g_cam), C.byref(self.cfg), self.ndc, self.near, self.far,
             C.byref(mc), C.byref(mf) if mf is not None else None, C.byref(self.g_c),
@@ -84,18 +85,19 @@ class TrainStep:
         for n in self.cam.LEARNABLE:
             getattr(self.cam, n).grad = self.grads.views["camera." + n]
 
-    def step_device(self, kps=None, idx=None, target=None):
+    def step_device(self, kps=None, idx=None, target=None, zero=True):
         """Inputs already in HBM (copied into the staging tensors if given).  Returns the device
-        loss tensor; gradients are in ``self.grads`` (flat, per-parameter views)."""
+        loss tensor; gradients are in ``self.grads`` (flat, per-parameter views).  ``zero=False`` accumulates on top of
+        what the buffer holds (e.g. the PRD term's camera gradients, computed first)."""
         if kps is not None:
             self.kps_dev.copy_(kps); self.idx_dev.copy_(idx); self.target_dev.copy_(target)
-        self._call(False)
+        self._call(False, zero)
         return self.loss_dev
 
-    def step_host(self, kps=None, idx=None, target=None):
+    def step_host(self, kps=None, idx=None, target=None, zero=True):
         """Inputs in pinned host memory; H2D copies and the D2H loss read are part of the call.
         The loss is valid in ``self.loss_host`` after the stream is synchronised."""
         if kps is not None:
             self.kps_host.copy_(kps); self.idx_host.copy_(idx); self.target_host.copy_(target)
-        self._call(True)
+        self._call(True, zero)
         return self.loss_host

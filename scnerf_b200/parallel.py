@@ -24,10 +24,14 @@ class FlatGrads:
         self.flat.zero_()
 
     def all_reduce_mean(self, group=None):
-        """Sum over ranks then divide by world size (what DDP does, one collective)."""
+        """Mean over ranks (what DDP does), one collective.  NCCL averages inside the all-reduce (ReduceOp.AVG): no
+        separate division kernel on the critical path; gloo (CPU tests) sums and divides."""
         if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
-            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group)
-            self.flat.div_(dist.get_world_size(group))
+            if self.flat.is_cuda and dist.get_backend(group) == "nccl":
+                dist.all_reduce(self.flat, op=dist.ReduceOp.AVG, group=group)
+            else:
+                dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group)
+                self.flat.div_(dist.get_world_size(group))
         return self.flat
 
     def assign_to(self, named_params):

@@ -57,6 +57,40 @@ class _PRDLoss(torch.autograd.Function):
         return (*[x.reshape(shape) for x in outs], gK, gE, None, None, None, None, None)
 
 
+class _CameraPair(torch.autograd.Function):
+    """(K4, E2) of an image pair straight from the learnable camera parameters — one launch forward, one backward —
+    instead of get_intrinsic() / get_extrinsic() over all cameras in eager torch (model/ray_dist_loss.py:59-65)."""
+
+    @staticmethod
+    def forward(ctx, camera_model, i0, i1, fx_sign, intr_noise, extr_noise):
+        import ctypes as C
+        lib = _lib.load()
+        cam = camera_model.c_struct()
+        dev = camera_model.intrinsics_initial.device
+        K4 = torch.empty(4, device=dev, dtype=torch.float32)
+        E2 = torch.empty(2, 3, 4, device=dev, dtype=torch.float32)
+        _lib.check(lib.scnerf_camera_pair_fwd(C.byref(cam), int(i0), int(i1), float(fx_sign), _lib.ptr(K4), _lib.ptr(E2),
+                                              _lib.stream()), "camera_pair_fwd")
+        ctx.cm, ctx.idx, ctx.fx_sign = camera_model, (int(i0), int(i1)), float(fx_sign)
+        return K4, E2
+
+    @staticmethod
+    def backward(ctx, gK, gE):
+        import ctypes as C
+        lib = _lib.load()
+        cm = ctx.cm
+        cam = cm.c_struct()
+        g = _lib.CameraGrads()
+        g_intr = torch.zeros_like(cm.intrinsics_noise) if ctx.needs_input_grad[4] else None
+        g_extr = torch.zeros_like(cm.extrinsics_noise) if ctx.needs_input_grad[5] else None
+        g.intrinsics_noise, g.extrinsics_noise = _lib.ptr(g_intr), _lib.ptr(g_extr)
+        gK = _lib.f32(gK) if gK is not None else None
+        gE = _lib.f32(gE) if gE is not None else None
+        _lib.check(lib.scnerf_camera_pair_bwd(C.byref(cam), ctx.idx[0], ctx.idx[1], ctx.fx_sign, _lib.ptr(gK), _lib.ptr(gE),
+                                              C.byref(g), _lib.stream()), "camera_pair_bwd")
+        return None, None, None, None, g_intr, g_extr
+
+
 def proj_ray_dist_loss_single(kps0_list, kps1_list, img_idx0, img_idx1, rays0, rays1, mode, device, H, W, args,
                               camera_model=None, intrinsic=None, extrinsic=None, eps=1e-10, i_map=None,
                               method="NeRF"):
@@ -65,16 +99,20 @@ def proj_ray_dist_loss_single(kps0_list, kps1_list, img_idx0, img_idx1, rays0, r
     assert method in ["NeRF", "NeRF++"]
     assert kps0_list[:, 0].max() < W and kps1_list[:, 0].max() < W
     assert kps0_list[:, 1].max() < H and kps1_list[:, 1].max() < H
+    fused_KE = None
     if mode == "train":
         if camera_model is not None:                       # :51-65
             assert intrinsic is None
             assert extrinsic is None
             assert i_map is not None
-            intrinsic = camera_model.get_intrinsic().to(device)
-            extrinsic = camera_model.get_extrinsic()
             i0 = np.where(i_map == img_idx0)[0][0]
             i1 = np.where(i_map == img_idx1)[0][0]
-            extrinsic = extrinsic[[i0, i1]].to(device)
+            if hasattr(camera_model, "c_struct") and camera_model.intrinsics_initial.is_cuda:
+                fused_KE = _CameraPair.apply(camera_model, i0, i1, -1.0 if method == "NeRF" else 1.0,
+                                             camera_model.intrinsics_noise, camera_model.extrinsics_noise)
+            else:
+                intrinsic = camera_model.get_intrinsic().to(device)
+                extrinsic = camera_model.get_extrinsic()[[i0, i1]].to(device)
         else:                                              # :67-76
             assert intrinsic is not None
             assert extrinsic is not None
@@ -94,9 +132,12 @@ def proj_ray_dist_loss_single(kps0_list, kps1_list, img_idx0, img_idx1, rays0, r
         extrinsic = extrinsic[[img_idx0, img_idx1]].to(device)
     rays0_o, rays0_d = rays0
     rays1_o, rays1_d = rays1
-    fx = -intrinsic[0][0] if method == "NeRF" else intrinsic[0][0]        # :113-118 (NeRF's flipped x axis)
-    K4 = torch.stack([fx, intrinsic[1][1], intrinsic[0][2], intrinsic[1][2]]).to(torch.float32)
-    E2 = extrinsic[:, :3, :4].to(torch.float32).contiguous()
+    if fused_KE is not None:
+        K4, E2 = fused_KE
+    else:
+        fx = -intrinsic[0][0] if method == "NeRF" else intrinsic[0][0]        # :113-118 (NeRF's flipped x axis)
+        K4 = torch.stack([fx, intrinsic[1][1], intrinsic[0][2], intrinsic[1][2]]).to(torch.float32)
+        E2 = extrinsic[:, :3, :4].to(torch.float32).contiguous()
     loss, n_match = _PRDLoss.apply(rays0_o, rays0_d, rays1_o, rays1_d, K4, E2, kps0_list, kps1_list, eps,
                                    args.proj_ray_dist_threshold, mode == "train")
     if mode == "train":

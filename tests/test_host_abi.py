@@ -252,9 +252,7 @@ def test_pipelined_slab_plans(which, name, ring_multiples):
         assert mine[-1]["flags"] & F_STAGE_END                     # nothing is issued after the stage's last commit
 
 
-def test_serial_plans_unchanged_by_the_pipelined_ones():
-    """The serial kernels' tables (kept for SCNERF_*_PIPE=0 and the 96-wide d(PE) dgrad) still fit their rings."""
-    n, st, _, slabs = _plan(0)
-    assert (n, st) == (168, 10) and all(s["n"] in (256, 128, 16) for s in slabs)
+def test_serial_dgrad_plan_for_4d_points():
+    """The serial dgrad chain remains for the 96-wide d(PE) of the NeRF++ background network: its table still fits its ring."""
     n, st, _, slabs = _plan(3)
-    assert (n, st) == (176, 11)
+    assert (n, st) == (176, 11) and all(s["n"] in (256, 96, 32) for s in slabs)

@@ -24,7 +24,7 @@ for ev in prof.events():
         name = ev.name.split("(")[0].replace("scnerf::", "")
         rows.setdefault(name, []).append(ev.device_time if hasattr(ev, "device_time") else ev.cuda_time)
 tot = sum(sum(v) for v in rows.values()) / STEPS
-print(f"{prec} pipe={os.environ.get('SCNERF_FWD_PIPE', '1')} dpipe={os.environ.get('SCNERF_DGRAD_PIPE', '1')}: sum of kernel times per step {tot / 1000:.3f} ms")
+print(f"{prec}: sum of kernel times per step {tot / 1000:.3f} ms")
 for name, v in sorted(rows.items(), key=lambda kv: -sum(kv[1])):
     if sum(v) / STEPS < 20:
         continue

@@ -15,8 +15,10 @@ for r in rows[2:]:
     wr = float(r[ci["dram__bytes_write.sum"]]) * scale[units[ci["dram__bytes_write.sum"]]]
     dur = float(r[ci["gpu__time_duration.sum"]])
     key = f"{name}/{suffix}"
-    if key in out and out[key]["dram_bytes"] >= rd + wr:   # keep the largest launch (the fine pass)
-        continue
+    if key in out and out[key]["dram_bytes"] >= 1.02 * (rd + wr) and out[key]["source"] == os.path.basename(rep):
+        continue                                           # within one capture keep the largest launch (the fine pass)
+    if key in out and out[key]["source"] != os.path.basename(rep) and out[key]["dram_bytes"] >= 2 * (rd + wr):
+        continue                                           # a coarse-pass launch of a newer capture does not replace a fine-pass entry
     out[key] = {"dram_bytes": rd + wr, "dram_read": rd, "dram_write": wr,
                 "duration": dur, "duration_unit": units[ci["gpu__time_duration.sum"]], "source": os.path.basename(rep)}
     print(key, out[key])
