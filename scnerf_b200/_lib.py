@@ -11,7 +11,7 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libscnerf_b200.so")
+LIB_PATH = os.environ.get("SCNERF_LIB") or os.path.join(_HERE, "csrc", "libscnerf_b200.so")   # SCNERF_LIB: e.g. a -DSCNERF_TIMELINE build
 MAX_DEPTH = 16
 PRECISION = {"fp32": 0, "bf16x3": 1, "bf16": 2}
 

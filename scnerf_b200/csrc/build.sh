@@ -3,6 +3,9 @@
 set -euo pipefail
 cd "$(dirname "$0")"
 NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
+# OUT=libscnerf_b200_timeline.so bash build.sh -DSCNERF_TIMELINE   builds the variant with the in-kernel timeline stamps
+# (tools/timeline_pipe.py, run with SCNERF_LIB=<that file>); the product build carries none.
+OUT=${OUT:-libscnerf_b200.so}
 $NVCC -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 \
-  -Xcompiler -fPIC -shared -o libscnerf_b200.so api.cu "$@"
-echo "built $(pwd)/libscnerf_b200.so"
+  -Xcompiler -fPIC -shared -o $OUT api.cu "$@"
+echo "built $(pwd)/$OUT"
