@@ -211,8 +211,19 @@ __device__ __forceinline__ void mma_step(const PCtx& c, uint32_t tp, int tile_it
     tc::tc_fence_after();
   }
   if constexpr (I % K::GROUP == 0) {
+#ifdef SCNERF_TIMELINE
+    // slots 11 / 15: cycles the issue thread spent waiting for weight slabs (ring full barriers) in N-half 0 / 1 of this stage
+    const long long tw0 = clock64();
+#endif
     eng::mbar_wait_a(c.e.full_addr + idx * 8, (uint32_t)(wrap & 1) ^ (wraps_odd ? tp : 0u));
     tc::tc_fence_after();
+#ifdef SCNERF_TIMELINE
+    if (c.dbg != nullptr && blockIdx.x == 0 && tile_iter < c.dbg_tiles) {
+      long long* w = c.dbg + ((size_t)tile_iter * NSTAGE + d.stage) * 16 + 11 + 4 * d.pad;
+      const long long dt = clock64() - tw0;
+      *w = ((d.flags & eng::F_ZERO_ACC) != 0 ? 0 : *w) + dt;
+    }
+#endif
   }
   constexpr uint32_t idesc = tc::idesc_bf16_f32(TILE_M, d.n);
   constexpr uint32_t LBO_B = (uint32_t)d.n * 16u;

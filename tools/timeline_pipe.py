@@ -37,8 +37,8 @@ print(prec, "TRAIN" if TRAIN else "INFER", "stage: mma_a1 mma_a2 commit0 commit1
 for t in range(1, 3):
     for s in range(10):
         r = b[t, s] - t0
-        print(f"tile {t} stage {s}: " + " ".join(f"{int(x):8d}" for x in r[:4]) + " | " + " ".join(f"{int(x):8d}" for x in r[4:]) +
+        print(f"tile {t} stage {s}: " + " ".join(f"{int(x):8d}" for x in r[:4]) + " | " + " ".join(f"{int(x):8d}" for x in r[4:11]) +
               f" | mma h0 {int(r[2] - r[0]):6d} h1 {int(r[3] - r[2]):6d} epi0 {int(r[5] - r[4]):6d} epi1 {int(r[7] - r[6]):6d}"
               f" | epi0 quarters handed over at +{int(r[9] - r[4]):5d} +{int(r[10] - r[4]):5d}"
-              f" | epi1 at +{int(r[13] - r[6]):5d} +{int(r[14] - r[6]):5d}")
+              f" | epi1 at +{int(r[13] - r[6]):5d} +{int(r[14] - r[6]):5d} | weight-ring waits h0 {int(b[t, s, 11]):5d} h1 {int(b[t, s, 15]):5d}")
     print(f"tile {t} total cycles: {b[t + 1, 0, 0] - b[t, 0, 0]}")
