@@ -32,7 +32,8 @@ else:
 torch.cuda.synchronize()
 lib.scnerf_debug_timeline(None, 0)
 b = buf.cpu().numpy()
-t0 = b[b > 0].min()
+stamps = np.delete(b, [11, 15], axis=2)      # slots 11 / 15 are cycle counts, not stamps
+t0 = stamps[stamps > 0].min()
 print(prec, "TRAIN" if TRAIN else "INFER", "stage: mma_a1 mma_a2 commit0 commit1 | epi_accf0 epi_a1 epi_accf1 epi_a2   (cycles from the first stamp)")
 for t in range(1, 3):
     for s in range(10):
