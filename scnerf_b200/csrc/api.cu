@@ -68,7 +68,7 @@ int scnerf_debug_mma_bench(int32_t mode, int32_t iters, long long* dev_out, int3
 int scnerf_debug_slab_plan(int32_t which, int32_t index, int64_t* out9) {
   SCNERF_CHECK_ARG(out9 != nullptr, "slab_plan: null output");
   static const eng::Plan plans[5] = {fpipe::make_plan<3, 4>(), fpipe::make_plan<3, 4>(), fpipe::make_plan<3, 6>(),
-                                     dgrad::make_plan<96>(), dpipe::make_plan()};      // (0 = 1 since the serial forward was retired)
+                                     dpipe::make_plan<96>(), dpipe::make_plan<64>()};  // (0 = 1 since the serial forward was retired; 3 was the serial 4-D dgrad)
   SCNERF_CHECK_ARG(which >= 0 && which < 5, "slab_plan: unknown plan %d", which);
   const eng::Plan& P = plans[which];
   for (int i = 0; i < 9; ++i) out9[i] = 0;

@@ -489,17 +489,6 @@ inline int bwd_plan_init() {
   int dev = 0;
   SCNERF_CUDA(cudaGetDevice(&dev));
   if (dev < 64 && done[dev]) return 0;
-  // the serial dgrad chain serves the 96-wide d(PE) of 4-D points (NeRF++ background) only; 3-D points run the pipelined one
-  static eng::Plan P96 = dgrad::make_plan<96>();
-  static fused::PlanSrc S96;
-  dgrad::build_plansrc<96>(S96);
-  if (fused::plan_image_bytes(P96, 3) > TC_IMG_BYTES) return fail(SCNERF_ERR_WORKSPACE, "TC_IMG_BYTES too small (dgrad)");
-  SCNERF_CUDA(cudaMemcpyToSymbol(dgrad::d_plan_dgrad96, &P96, sizeof(P96)));
-  SCNERF_CUDA(cudaMemcpyToSymbol(dgrad::d_plansrc_dgrad96, &S96, sizeof(S96)));
-  SCNERF_CUDA(cudaFuncSetAttribute((dgrad::field_fused_dgrad_kernel<1, 96>), cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   dgrad::Cfg<1, 96>::SMEM_BYTES));
-  SCNERF_CUDA(cudaFuncSetAttribute((dgrad::field_fused_dgrad_kernel<3, 96>), cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   dgrad::Cfg<3, 96>::SMEM_BYTES));
   SCNERF_CUDA(cudaFuncSetAttribute(wgrad::field_wgrad_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    wgrad::Cfg<1>::SMEM_BYTES));
   SCNERF_CUDA(cudaFuncSetAttribute(wgrad::field_wgrad_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -507,32 +496,35 @@ inline int bwd_plan_init() {
   if (dev < 64) done[dev] = true;
   return 0;
 }
+// N-half pipelined dgrad chain: XN = 64 (3-D points) and XN = 96 (4-D points of the NeRF++ background network)
+template <int XN>
 inline const eng::Plan& dpipe_plan_host() {
-  static eng::Plan P = dpipe::make_plan();
+  static eng::Plan P = dpipe::make_plan<XN>();
   return P;
 }
+template <int XN>
 inline int dpipe_plan_init() {
   static bool done[64] = {};
   int dev = 0;
   SCNERF_CUDA(cudaGetDevice(&dev));
   if (dev < 64 && done[dev]) return 0;
-  const eng::Plan& P = dpipe_plan_host();
+  const eng::Plan& P = dpipe_plan_host<XN>();
   static fused::PlanSrc S;
-  dpipe::build_plansrc(S);
+  dpipe::build_plansrc<XN>(S);
   if (fused::plan_image_bytes(P, 3) > TC_IMG_BYTES) return fail(SCNERF_ERR_WORKSPACE, "TC_IMG_BYTES too small (pipelined dgrad)");
-  SCNERF_CUDA(cudaMemcpyToSymbol(dpipe::d_plan_dpipe, &P, sizeof(P)));
-  SCNERF_CUDA(cudaMemcpyToSymbol(dpipe::d_plansrc_dpipe, &S, sizeof(S)));
-  SCNERF_CUDA(cudaFuncSetAttribute((dpipe::field_dgrad_pipe_kernel<1, 1>), cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   dpipe::Cfg<1>::SMEM_BYTES));
-  SCNERF_CUDA(cudaFuncSetAttribute((dpipe::field_dgrad_pipe_kernel<3, 1>), cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   dpipe::Cfg<3>::SMEM_BYTES));
+  if (XN == 64) {
+    SCNERF_CUDA(cudaMemcpyToSymbol(dpipe::d_plan_dpipe, &P, sizeof(P)));
+    SCNERF_CUDA(cudaMemcpyToSymbol(dpipe::d_plansrc_dpipe, &S, sizeof(S)));
+  } else {
+    SCNERF_CUDA(cudaMemcpyToSymbol(dpipe::d_plan_dpipe96, &P, sizeof(P)));
+    SCNERF_CUDA(cudaMemcpyToSymbol(dpipe::d_plansrc_dpipe96, &S, sizeof(S)));
+  }
+  SCNERF_CUDA(cudaFuncSetAttribute((dpipe::field_dgrad_pipe_kernel<1, XN>), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (dpipe::Cfg<1, XN>::SMEM_BYTES)));
+  SCNERF_CUDA(cudaFuncSetAttribute((dpipe::field_dgrad_pipe_kernel<3, XN>), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (dpipe::Cfg<3, XN>::SMEM_BYTES)));
   if (dev < 64) done[dev] = true;
   return 0;
-}
-inline int dgrad_n_slabs() {      // the same for both d(PE) widths (only N of two stages differs)
-  static int n = -1;
-  if (n < 0) { static eng::Plan P = dgrad::make_plan<96>(); n = P.n_slabs; }
-  return n;
 }
 
 inline void wgrad_unit(wgrad::Unit& u, int a_img, int a_half, int b_img, int n, int acc_col, float* out, int ld,
@@ -555,14 +547,9 @@ inline int field_tc_bwd_impl(const scnerf_mlp& m, const scnerf_mlp& g, const flo
   const int64_t P = N * S;
   const int T = (int)cdiv(P, 128);
   fused::PackSrc src = make_pack_src(m);
-  constexpr bool dp = XN == 64;      // 3-D points: N-half pipelined chain; 4-D points: the serial chain (96-wide d(PE))
-  if constexpr (dp) {
-    rc = dpipe_plan_init();
-    if (rc) return rc;
-    SCNERF_LAUNCH((dpipe::pack_dpipe_kernel<NSPLIT>), dim3(1, (unsigned)dpipe_plan_host().n_slabs), 256, 0, stream, src, G.wimg);
-  } else {
-    SCNERF_LAUNCH((dgrad::pack_dgrad_kernel<NSPLIT, 96>), dim3(2, (unsigned)dgrad_n_slabs()), 256, 0, stream, src, G.wimg);
-  }
+  rc = dpipe_plan_init<XN>();
+  if (rc) return rc;
+  SCNERF_LAUNCH((dpipe::pack_dpipe_kernel<NSPLIT, XN>), dim3(1, (unsigned)dpipe_plan_host<XN>().n_slabs), 256, 0, stream, src, G.wimg);
   SCNERF_LAUNCH(fused::pack_consts_kernel, (unsigned)cdiv(fused::C_TOTAL, 256), 256, 0, stream, src, B.tc_cbuf);
   dgrad::Args a{};
   a.rays = rays; a.ray_cols = ray_cols; a.z = z; a.P = P; a.S = S; a.num_tiles = T;
@@ -570,12 +557,8 @@ inline int field_tc_bwd_impl(const scnerf_mlp& m, const scnerf_mlp& g, const flo
   a.g_raw = g_raw; a.wimg = G.wimg; a.cbuf = B.tc_cbuf;
   for (int i = 0; i < 8; ++i) a.out_dz[i] = G.dz[i];
   a.relu_bits = I.relu_bits; a.out_dfeat = G.dfeat; a.out_dzv = G.dzv; a.g_pts = G.g_pts; a.g_vd = G.g_vd;
-  if constexpr (dp)
-    SCNERF_LAUNCH((dpipe::field_dgrad_pipe_kernel<NSPLIT, 1>), std::min(device_sm_count(), T), 320,
-                  (dpipe::Cfg<NSPLIT>::SMEM_BYTES), stream, a);
-  else
-    SCNERF_LAUNCH((dgrad::field_fused_dgrad_kernel<NSPLIT, 96>), std::min(device_sm_count(), T), 320,
-                  (dgrad::Cfg<NSPLIT, 96>::SMEM_BYTES), stream, a);
+  SCNERF_LAUNCH((dpipe::field_dgrad_pipe_kernel<NSPLIT, XN>), std::min(device_sm_count(), T), 320,
+                (dpipe::Cfg<NSPLIT, XN>::SMEM_BYTES), stream, a);
   if (XN == 96) {
     if (d_viewdirs)
       SCNERF_LAUNCH(dgrad::reduce_vd_grad_kernel, (unsigned)cdiv(N, 4), 128, 0, stream, G.g_vd, N, S, d_viewdirs);

@@ -1,7 +1,7 @@
 // Fused field backward (data-gradient chain), N-half PIPELINED variant (sm_100a, tcgen05).
 //
-// Same maths, masks, images and outputs as field_tc_dgrad.cuh (3-D points, 64-wide d(PE)); the schedule is
-// the one of field_tc_fwd_pipe.cuh: every transposed-weight GEMM runs as two 128-column N-halves into two
+// XN = 64: 3-D points formed from (rays, z), 63-channel encoding; XN = 96: explicit 4-D points (NeRF++ background network),
+// 84-channel encoding.  The schedule is the one of field_tc_fwd_pipe.cuh: every transposed-weight GEMM runs as two 128-column N-halves into two
 // accumulators, the epilogue hands the next stage's A operand (dZ) over in 64-column quarters, the first A
 // half is double-buffered (P0/P1), the second is single (Q), and in split-bf16 the lo operand lives in shared
 // memory.  Ten stages per tile:
@@ -12,6 +12,11 @@
 //   T5..T8  g_h3 .. g_h0                                T9  d(PE) = dZ0 * W0  (64 columns, one pass)
 //
 //   TMEM: acc0 [0,128)  acc1 [128,256)  A_hi: P0 [256,320)  P1 [320,384)  Q [384,448)  ACCX [448,512)
+//
+// XN = 96: the skip share of d(PE) is 96 columns wide and ACCX has 64, so T4 runs it as a SIDE PASS between its two halves:
+//   h0 (acc0) | side: dZ5 * W5[:, :84] -> acc1[0,96) , commit side[0] | h1 (acc1), first slab waits side[1]
+// and the epilogue parks the side result in shared memory (side[0] -> 48 KB gx_s -> side[1]) BEFORE it converts h0, so the
+// h1 pass starts ~0.5 K cycles after the side pass ends and T5's operand quarters are still ready when h1 is done.
 //
 // Graph = NeRF.forward's autograd graph (NeRF/run_nerf_helpers.py:105-128) + Embedder (:24-72).
 #pragma once
@@ -31,11 +36,11 @@ using fused::SrcDef;
 using dgrad::Args;
 constexpr int NSTAGE = 10;
 constexpr int ACCX_COL = 448;
-constexpr int IN_CH = 63, XN = 64;
 
-// f(stage, h, N, acc_col, j, first_in_pass, last_in_pass, wsel, col0, valid_n, nk)
-template <class F>
+// f(stage, h, N, acc_col, j, first_in_pass, last_in_pass, wsel, col0, valid_n, nk);  h = 2: side pass (XN = 96, T4)
+template <int XN = 64, class F>
 __host__ __device__ constexpr void for_each_slab(F&& f) {
+  constexpr int IN_CH = XN == 64 ? 63 : 84;
   // T0: views layer, K = 128
   for (int j = 0; j < 8; ++j) f(0, 0, 128, 0, j, j == 0, j == 7, 9, 0, 128, 8);
   for (int j = 0; j < 8; ++j) f(0, 1, 128, 128, j, j == 0, false, 9, 128, 128, 8);
@@ -44,12 +49,16 @@ __host__ __device__ constexpr void for_each_slab(F&& f) {
   for (int t = 1; t <= 8; ++t) {
     const int c0 = t == 4 ? IN_CH : 0;
     for (int j = 0; j < 16; ++j) f(t, 0, 128, 0, j, j == 0, j == 15, wsel[t], c0, 128, 16);
-    for (int j = 0; j < 16; ++j) f(t, 1, 128, 128, j, j == 0, t == 4 ? false : j == 15, wsel[t], c0 + 128, 128, 16);
-    if (t == 4)
+    if (t == 4 && XN == 96)
+      for (int j = 0; j < 16; ++j) f(t, 2, XN, 128, j, j == 0, j == 15, 5, 0, IN_CH, 16);
+    for (int j = 0; j < 16; ++j)
+      f(t, 1, 128, 128, j, j == 0, (t == 4 && XN == 64) ? false : j == 15, wsel[t], c0 + 128, 128, 16);
+    if (t == 4 && XN == 64)
       for (int j = 0; j < 16; ++j) f(t, 1, XN, ACCX_COL, j, j == 0, j == 15, 5, 0, IN_CH, 16);
   }
   for (int j = 0; j < 16; ++j) f(9, 0, XN, 0, j, j == 0, j == 15, 0, 0, IN_CH, 16);
 }
+template <int XN>
 struct PlanFiller {
   eng::Plan P{};
   int n = 0;
@@ -57,32 +66,39 @@ struct PlanFiller {
   __host__ __device__ constexpr void operator()(int s, int h, int N, int acc_col, int j, bool first, bool last,
                                                 int, int, int, int nk) {
     eng::SlabDef e{};
-    e.n = (uint16_t)N; e.acc_col = (uint16_t)acc_col; e.stage = (uint8_t)s; e.pad = (uint8_t)h; e.img_off = off;
+    e.n = (uint16_t)N; e.acc_col = (uint16_t)acc_col; e.stage = (uint8_t)s; e.pad = (uint8_t)(h & 1); e.img_off = off;
     e.a_kind = eng::A_MIX;
     e.a_off = (uint16_t)fpipe::a_buf_col(s, j); e.a_lo_delta = (uint16_t)(fpipe::a_buf_lo(s, j) / 16);
-    uint8_t fl = 0;
+    uint16_t fl = 0;
     if (first) fl |= eng::F_ZERO_ACC;
     const bool pass0 = h == 0 && acc_col == 0;
     if (pass0 && j == 0) fl |= eng::F_STAGE_BEGIN;
     if (pass0 && (j == 4)) fl |= eng::F_WAIT_Q1;
     if (pass0 && (nk == 8 ? j == 0 : j == 8)) fl |= eng::F_WAIT_Q2;     // K = 128: the unused quarters' phases are
     if (pass0 && (nk == 8 ? j == 0 : j == 12)) fl |= eng::F_WAIT_Q3;    // consumed at the stage start
-    if (last) fl |= eng::F_STAGE_END;
-    if (last && s == NSTAGE - 1) fl |= eng::F_COMMIT_BOTH;
+    if (h == 2) {
+      if (last) fl |= eng::F_COMMIT_SIDE;                                // side pass: own barrier, not a stage half
+    } else {
+      if (last) fl |= eng::F_STAGE_END;
+      if (last && s == NSTAGE - 1) fl |= eng::F_COMMIT_BOTH;
+      if (XN == 96 && s == 4 && h == 1 && j == 0) fl |= eng::F_WAIT_SIDE;   // acc1 is re-initialised: side result parked
+    }
     e.flags = fl;
     P.slab[n++] = e;
     off += (uint32_t)N * 32u;
   }
 };
+template <int XN = 64>
 __host__ __device__ constexpr eng::Plan make_plan() {
-  PlanFiller f{};
-  for_each_slab(f);
+  PlanFiller<XN> f{};
+  for_each_slab<XN>(f);
   f.P.n_slabs = f.n; f.P.n_stages = NSTAGE;
   return f.P;
 }
+template <int XN = 64>
 inline void build_plansrc(PlanSrc& S) {
   int n = 0;
-  for_each_slab([&](int, int, int, int, int j, bool, bool, int wsel, int col0, int valid_n, int) {
+  for_each_slab<XN>([&](int, int, int, int, int j, bool, bool, int wsel, int col0, int valid_n, int) {
     SrcDef d{};
     d.wsel = (uint8_t)wsel; d.kind = 1; d.row0 = (uint16_t)(16 * j); d.col0 = (uint16_t)col0;
     d.valid_k = 16; d.valid_n = (uint16_t)valid_n;
@@ -92,15 +108,20 @@ inline void build_plansrc(PlanSrc& S) {
 
 __device__ eng::Plan d_plan_dpipe;
 __device__ PlanSrc d_plansrc_dpipe;
-template <int NSPLIT>
+__device__ eng::Plan d_plan_dpipe96;      // 4-D points
+__device__ PlanSrc d_plansrc_dpipe96;
+template <int NSPLIT, int XN = 64>
 __global__ void __launch_bounds__(256) pack_dpipe_kernel(fused::PackSrc src, uint8_t* __restrict__ img) {
   const int i = blockIdx.y;
-  if (i < d_plan_dpipe.n_slabs) fused::pack_slab_impl<NSPLIT>(d_plan_dpipe.slab[i], d_plansrc_dpipe.s[i], src, img);
+  const eng::Plan& P = XN == 64 ? d_plan_dpipe : d_plan_dpipe96;
+  const PlanSrc& S = XN == 64 ? d_plansrc_dpipe : d_plansrc_dpipe96;
+  if (i < P.n_slabs) fused::pack_slab_impl<NSPLIT>(P.slab[i], S.s[i], src, img);
 }
 
-template <int NSPLIT_> struct Cfg {
+template <int NSPLIT_, int XN_ = 64> struct Cfg {
   static constexpr int NSPLIT = NSPLIT_;
-  static constexpr eng::Plan PLAN = make_plan();
+  static constexpr int XN = XN_;
+  static constexpr eng::Plan PLAN = make_plan<XN_>();
   static constexpr int GROUP = NSPLIT_ == 1 ? 4 : 2;          // 312 slabs = 2 x 4 x 39 = 4 x 6 x 13
   static constexpr int NSLOT = NSPLIT_ == 1 ? 6 : 4;
   static constexpr int SLOT_BYTES = 16384;
@@ -109,10 +130,10 @@ template <int NSPLIT_> struct Cfg {
   static constexpr int OFF_RING = 0;
   static constexpr int OFF_LO = NSLOT * SLOT_BYTES;
   static constexpr int OFF_C = OFF_LO + LO_BYTES;
-  static constexpr int OFF_GX = OFF_C + ((fused::C_TOTAL * 4 + 127) / 128) * 128;   // [64][128] fp32 skip-branch d(PE)
-  static constexpr int OFF_OUT = OFF_GX + XN * 128 * 4;                               // [128][4]
+  static constexpr int OFF_GX = OFF_C + ((fused::C_TOTAL * 4 + 127) / 128) * 128;   // [XN][128] fp32 skip-branch d(PE)
+  static constexpr int OFF_OUT = OFF_GX + XN_ * 128 * 4;                              // [128][4]
   static constexpr int OFF_BAR = OFF_OUT + 128 * 4 * 4;
-  static constexpr int SMEM_BYTES = OFF_BAR + (2 * NSLOT + 6) * 8 + 16;
+  static constexpr int SMEM_BYTES = OFF_BAR + (2 * NSLOT + 8) * 8 + 16;             // full/empty, accf[2], aq[4], side[2]
   static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB shared-memory limit");
 };
 
@@ -136,15 +157,64 @@ __device__ __forceinline__ void pe_contract(const uint32_t (&v)[32], const float
   }
 }
 
+// 4-D points (84 channels: x(4), then per frequency sin(4), cos(4)): column i of d(PE) -> d(x)
+__device__ __forceinline__ void pe_contract4(int i, float g, const float (&x)[4], float (&gx)[4]) {
+  if (i < 4) gx[i] += g;
+  else if (i < 84) {
+    const int f = (i - 4) >> 3, r = (i - 4) & 7, c = r & 3;
+    const float fr = (float)(1 << f);
+    float sv, cv;
+    fused::sincos_cw(x[c] * fr, sv, cv);     // same evaluation as the forward's PE
+    gx[c] += (r < 4) ? fr * cv * g : -fr * sv * g;
+  }
+}
+// XN = 96, stage T4: park the side pass (skip share of d(PE), acc1 columns [0,96)) in shared memory and release acc1 for the
+// h1 pass.  This warp owns columns [32 half, +32) and [64 + 16 half, +16).
+__device__ __forceinline__ void side_drain(const fpipe::PCtx& c, float* gx_s, uint32_t lane_base, int half, int row,
+                                           uint32_t tile_par) {
+  eng::mbar_wait_a(c.aq_addr + 32, tile_par);
+  tc::tc_fence_after();
+  uint32_t va[32], vb[16];
+  const int ca = half * 32, cb = 64 + half * 16;
+  tc::tmem_ld32(c.e.tmem_acc + lane_base + 128 + ca, va);
+  tc::tmem_ld16(c.e.tmem_acc + lane_base + 128 + cb, vb);
+  tc::tmem_ld_wait();
+#pragma unroll
+  for (int j = 0; j < 32; ++j) gx_s[(ca + j) * TILE_M + row] = __uint_as_float(va[j]);
+#pragma unroll
+  for (int j = 0; j < 16; ++j) gx_s[(cb + j) * TILE_M + row] = __uint_as_float(vb[j]);
+  tc::tc_fence_before();
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(c.aq_addr + 40) : "memory");
+}
+
 // One N-half of one stage for this warp: chunk cc = columns [H*128 + cc*64 + half*32, +32).
-template <int NSPLIT, int T, int H>
+template <int NSPLIT, int T, int H, int XN = 64>
 __device__ __forceinline__ void epi_half(const Args& a, const float* cst, const fpipe::PCtx& c, uint8_t* lo_area,
                                          float* gx_s, float* out_s, uint32_t lane_base, int half, int row, int tile,
                                          int64_t p, bool valid, const float4& gr) {
   constexpr bool SPLIT = NSPLIT == 3;
   if constexpr (T == 9) {
     eng::mbar_wait_a(c.accf_addr + H * 8, (uint32_t)(T & 1));
-    if constexpr (H == 0) {
+    if constexpr (H == 0 && XN == 96) {
+      tc::tc_fence_after();
+      uint32_t va[32], vb[16];
+      const int ca = half * 32, cb = 64 + half * 16;
+      tc::tmem_ld32(c.e.tmem_acc + lane_base + ca, va);
+      tc::tmem_ld16(c.e.tmem_acc + lane_base + cb, vb);
+      tc::tmem_ld_wait();
+      float x[4] = {0.f, 0.f, 0.f, 0.f};
+      if (valid) {
+        const float4 q = *reinterpret_cast<const float4*>(a.pts + p * 4);
+        x[0] = q.x; x[1] = q.y; x[2] = q.z; x[3] = q.w;
+      }
+      float gx[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int j = 0; j < 32; ++j) pe_contract4(ca + j, __uint_as_float(va[j]) + gx_s[(ca + j) * TILE_M + row], x, gx);
+#pragma unroll
+      for (int j = 0; j < 16; ++j) pe_contract4(cb + j, __uint_as_float(vb[j]) + gx_s[(cb + j) * TILE_M + row], x, gx);
+#pragma unroll
+      for (int cc = 0; cc < 4; ++cc) atomicAdd(out_s + row * 4 + cc, gx[cc]);
+    } else if constexpr (H == 0) {
       // total d(PE row) = layer-0 share + skip share; contract with dPE/dx (Embedder backward)
       tc::tc_fence_after();
       uint32_t v[32];
@@ -220,8 +290,13 @@ __device__ __forceinline__ void epi_half(const Args& a, const float* cst, const 
         tc::tmem_ld_wait();
         float vd[3] = {0.f, 0.f, 0.f}, gv[3] = {0.f, 0.f, 0.f};
         if (valid) {
-          const float* ry = a.rays + (p / a.S) * a.ray_cols;
-          vd[0] = ry[8]; vd[1] = ry[9]; vd[2] = ry[10];
+          if constexpr (XN == 96) {
+            const float* vv = a.viewdirs + (p / a.S) * 3;
+            vd[0] = vv[0]; vd[1] = vv[1]; vd[2] = vv[2];
+          } else {
+            const float* ry = a.rays + (p / a.S) * a.ray_cols;
+            vd[0] = ry[8]; vd[1] = ry[9]; vd[2] = ry[10];
+          }
         }
 #pragma unroll
         for (int i = 0; i < 27; ++i) {
@@ -238,7 +313,7 @@ __device__ __forceinline__ void epi_half(const Args& a, const float* cst, const 
         if (valid) { a.g_vd[p * 3] = gv[0]; a.g_vd[p * 3 + 1] = gv[1]; a.g_vd[p * 3 + 2] = gv[2]; }
       }
     }
-    if constexpr (T == 4 && H == 1) {
+    if constexpr (T == 4 && H == 1 && XN == 64) {
       // skip share of d(PE) (ACCX, 64 columns): parked in shared memory until T9; same thread reads it back
       uint32_t w[32];
       const int c0 = half * 32;
@@ -292,17 +367,9 @@ __device__ __forceinline__ void epi_half_rt(const Args& a, const fpipe::PCtx& c,
     eng::dump32<SPLIT>(a.out_dz[8 - T], tile, row, cu, hi, lo, c.e.pol_stream);
   }
 }
-template <int NSPLIT, size_t... Ts>
-__device__ __forceinline__ void epi_tile(const Args& a, const float* cst, const fpipe::PCtx& c, uint8_t* lo_area,
-                                         float* gx_s, float* out_s, uint32_t lane_base, int half, int row, int tile,
-                                         int64_t p, bool valid, const float4& gr, std::index_sequence<Ts...>) {
-  ((epi_half<NSPLIT, (int)Ts, 0>(a, cst, c, lo_area, gx_s, out_s, lane_base, half, row, tile, p, valid, gr),
-    epi_half<NSPLIT, (int)Ts, 1>(a, cst, c, lo_area, gx_s, out_s, lane_base, half, row, tile, p, valid, gr)), ...);
-}
-
-template <int NSPLIT, int ROLL = 1>     // ROLL: 1 = trunk stages T2, T3, T5..T8 from one copy of the epilogue code (the build in use); 0 = unrolled
+template <int NSPLIT, int XN = 64>     // trunk stages T2, T3, T5..T8 run from one copy of the epilogue code (epi_half_rt)
 __global__ void __launch_bounds__(320, 1) field_dgrad_pipe_kernel(const __grid_constant__ Args a) {
-  using C = Cfg<NSPLIT>;
+  using C = Cfg<NSPLIT, XN>;
   constexpr bool SPLIT = NSPLIT == 3;
   extern __shared__ __align__(128) uint8_t qsm[];
   uint8_t* lo_area = qsm + C::OFF_LO;
@@ -312,14 +379,15 @@ __global__ void __launch_bounds__(320, 1) field_dgrad_pipe_kernel(const __grid_c
   uint64_t* full = reinterpret_cast<uint64_t*>(qsm + C::OFF_BAR);
   uint64_t* empty = full + C::NSLOT;
   uint64_t* accf = empty + C::NSLOT;      // [2]
-  uint64_t* aq = accf + 2;                // [4]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aq + 4);
+  uint64_t* aq = accf + 2;                // [4], then side[2] (XN = 96: side pass committed / side result parked)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aq + 6);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (tid == 0) {
     for (int i = 0; i < C::NSLOT; ++i) { tc::mbar_init(&full[i], 1); tc::mbar_init(&empty[i], 1); }
     tc::mbar_init(&accf[0], 1); tc::mbar_init(&accf[1], 1);
     for (int i = 0; i < 4; ++i) tc::mbar_init(&aq[i], 256);
+    tc::mbar_init(&aq[4], 1); tc::mbar_init(&aq[5], 256);
     tc::fence_mbar_init();
   }
   for (int i = tid; i < fused::C_TOTAL; i += blockDim.x) cst[i] = a.cbuf[i];
@@ -350,6 +418,7 @@ __global__ void __launch_bounds__(320, 1) field_dgrad_pipe_kernel(const __grid_c
     const int quad = warp & 3, half = (warp - 2) >> 2;
     const int row = quad * 32 + lane;
     const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
+    uint32_t tile_par = 0;                  // parity of the once-per-tile side barriers (XN = 96)
     for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
       const int64_t p = (int64_t)tile * TILE_M + row;
       const bool valid = p < a.P;
@@ -384,33 +453,31 @@ __global__ void __launch_bounds__(320, 1) field_dgrad_pipe_kernel(const __grid_c
       tc::tmem_st_wait();
       tc::tc_fence_before();
       for (int i = 0; i < 4; ++i) tc::mbar_arrive(&aq[i]);
-      if constexpr (ROLL >= 1) {
-        epi_half<NSPLIT, 0, 0>(a, cst, ctx, lo_area, gx_s, out_s, lane_base, half, row, tile, p, valid, gr);
-        epi_half<NSPLIT, 0, 1>(a, cst, ctx, lo_area, gx_s, out_s, lane_base, half, row, tile, p, valid, gr);
-        epi_half<NSPLIT, 1, 0>(a, cst, ctx, lo_area, gx_s, out_s, lane_base, half, row, tile, p, valid, gr);
-        epi_half<NSPLIT, 1, 1>(a, cst, ctx, lo_area, gx_s, out_s, lane_base, half, row, tile, p, valid, gr);
+      epi_half<NSPLIT, 0, 0, XN>(a, cst, ctx, lo_area, gx_s, out_s, lane_base, half, row, tile, p, valid, gr);
+      epi_half<NSPLIT, 0, 1, XN>(a, cst, ctx, lo_area, gx_s, out_s, lane_base, half, row, tile, p, valid, gr);
+      epi_half<NSPLIT, 1, 0, XN>(a, cst, ctx, lo_area, gx_s, out_s, lane_base, half, row, tile, p, valid, gr);
+      epi_half<NSPLIT, 1, 1, XN>(a, cst, ctx, lo_area, gx_s, out_s, lane_base, half, row, tile, p, valid, gr);
 #pragma unroll 1
-        for (int T = 2; T < 9; ++T) {
-          if (T == 4) {
-            epi_half<NSPLIT, 4, 0>(a, cst, ctx, lo_area, gx_s, out_s, lane_base, half, row, tile, p, valid, gr);
-            epi_half<NSPLIT, 4, 1>(a, cst, ctx, lo_area, gx_s, out_s, lane_base, half, row, tile, p, valid, gr);
-          } else {
-            epi_half_rt<NSPLIT, 0>(a, ctx, lo_area, lane_base, half, row, tile, T);
-            epi_half_rt<NSPLIT, 1>(a, ctx, lo_area, lane_base, half, row, tile, T);
-          }
+      for (int T = 2; T < 9; ++T) {
+        if (T == 4) {
+          if constexpr (XN == 96) side_drain(ctx, gx_s, lane_base, half, row, tile_par);
+          epi_half<NSPLIT, 4, 0, XN>(a, cst, ctx, lo_area, gx_s, out_s, lane_base, half, row, tile, p, valid, gr);
+          epi_half<NSPLIT, 4, 1, XN>(a, cst, ctx, lo_area, gx_s, out_s, lane_base, half, row, tile, p, valid, gr);
+        } else {
+          epi_half_rt<NSPLIT, 0>(a, ctx, lo_area, lane_base, half, row, tile, T);
+          epi_half_rt<NSPLIT, 1>(a, ctx, lo_area, lane_base, half, row, tile, T);
         }
-        epi_half<NSPLIT, 9, 0>(a, cst, ctx, lo_area, gx_s, out_s, lane_base, half, row, tile, p, valid, gr);
-        epi_half<NSPLIT, 9, 1>(a, cst, ctx, lo_area, gx_s, out_s, lane_base, half, row, tile, p, valid, gr);
-      } else {
-        epi_tile<NSPLIT>(a, cst, ctx, lo_area, gx_s, out_s, lane_base, half, row, tile, p, valid, gr,
-                         std::make_index_sequence<NSTAGE>{});
       }
+      epi_half<NSPLIT, 9, 0, XN>(a, cst, ctx, lo_area, gx_s, out_s, lane_base, half, row, tile, p, valid, gr);
+      epi_half<NSPLIT, 9, 1, XN>(a, cst, ctx, lo_area, gx_s, out_s, lane_base, half, row, tile, p, valid, gr);
       tc::tc_fence_before();
       asm volatile("bar.sync 1, 256;" ::: "memory");
       if (half == 0 && valid) {
-        a.g_pts[p * 3] = out_s[row * 4]; a.g_pts[p * 3 + 1] = out_s[row * 4 + 1]; a.g_pts[p * 3 + 2] = out_s[row * 4 + 2];
+        if constexpr (XN == 96) *reinterpret_cast<float4*>(a.g_pts + p * 4) = *reinterpret_cast<const float4*>(out_s + row * 4);
+        else { a.g_pts[p * 3] = out_s[row * 4]; a.g_pts[p * 3 + 1] = out_s[row * 4 + 1]; a.g_pts[p * 3 + 2] = out_s[row * 4 + 2]; }
       }
       asm volatile("bar.sync 1, 256;" ::: "memory");
+      tile_par ^= 1u;
     }
   }
   tc::tc_fence_before();

@@ -83,7 +83,7 @@ struct PlanFiller {
     const int nh = d.N / 2;
     eng::SlabDef e{};
     e.n = (uint16_t)nh; e.acc_col = (uint16_t)(h * 128); e.stage = (uint8_t)s; e.pad = (uint8_t)h; e.img_off = off;
-    uint8_t fl = 0;
+    uint16_t fl = 0;
     if (first) fl |= eng::F_ZERO_ACC;
     if (first && h == 0) fl |= eng::F_STAGE_BEGIN;                       // wait aq[0] (acc0 drained)
     if (h == 0 && ((s == 0 && first) || (kind == 3 && j == 4))) fl |= eng::F_WAIT_Q1;
@@ -107,12 +107,12 @@ __host__ __device__ constexpr eng::Plan make_plan() {
   // size divides the slab-group count and ring slot / parity stay compile-time
   const int n_pad = (PLAN_MULT - f.n % PLAN_MULT) % PLAN_MULT;
   if (n_pad > 0) {
-    f.P.slab[f.n - 1].flags = (uint8_t)(f.P.slab[f.n - 1].flags & ~eng::F_STAGE_END);
+    f.P.slab[f.n - 1].flags = (uint16_t)(f.P.slab[f.n - 1].flags & ~eng::F_STAGE_END);
     for (int k = 0; k < n_pad; ++k) {
       eng::SlabDef e{};
       e.n = 16; e.acc_col = 128; e.stage = (uint8_t)(NSTAGE - 1); e.pad = 1; e.img_off = f.off;
       e.a_kind = eng::A_SMEM; e.a_off = ALay<NSPLIT, XS>::ONES / 16;
-      e.flags = (uint8_t)(eng::F_HI_ONLY_A | (k == n_pad - 1 ? eng::F_STAGE_END : 0));
+      e.flags = (uint16_t)(eng::F_HI_ONLY_A | (k == n_pad - 1 ? eng::F_STAGE_END : 0));
       f.P.slab[f.n++] = e;
       f.off += 16u * 32u;
     }
@@ -210,6 +210,10 @@ __device__ __forceinline__ void mma_step(const PCtx& c, uint32_t tp, int tile_it
     eng::mbar_wait_a(c.aq_addr + 24, (uint32_t)(d.stage & 1));
     tc::tc_fence_after();
   }
+  if constexpr ((d.flags & eng::F_WAIT_SIDE) != 0) {     // side[1] (8 bytes after aq[3] + side[0]): side result parked by the epilogue
+    eng::mbar_wait_a(c.aq_addr + 40, tp);
+    tc::tc_fence_after();
+  }
   if constexpr (I % K::GROUP == 0) {
 #ifdef SCNERF_TIMELINE
     // slots 11 / 15: cycles the issue thread spent waiting for weight slabs (ring full barriers) in N-half 0 / 1 of this stage
@@ -249,6 +253,7 @@ __device__ __forceinline__ void mma_step(const PCtx& c, uint32_t tp, int tile_it
     }
   }
   if constexpr (I % K::GROUP == K::GROUP - 1) eng::commit_a(c.e.empty_addr + idx * 8);
+  if constexpr ((d.flags & eng::F_COMMIT_SIDE) != 0) eng::commit_a(c.aq_addr + 32);    // side[0]: side pass complete
   if constexpr ((d.flags & eng::F_STAGE_END) != 0) {
     eng::commit_a(c.accf_addr + d.pad * 8);
     if constexpr ((d.flags & eng::F_COMMIT_BOTH) != 0) eng::commit_a(c.accf_addr + (d.pad ^ 1) * 8);   // stage without a second N-half

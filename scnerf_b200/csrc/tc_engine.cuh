@@ -22,8 +22,12 @@ constexpr int TILE_M = 128;
 constexpr int MAX_SLABS = 352;   // the N-half pipelined forward issues 336 half-slabs per tile
 
 enum : uint8_t { A_TMEM = 0, A_SMEM = 1, A_MIX = 2 };   // A_MIX: hi in TMEM (a_off), lo in shared memory (a_lo_delta)
-enum : uint8_t { F_ZERO_ACC = 1, F_STAGE_END = 2, F_HI_ONLY_A = 4, F_STAGE_BEGIN = 8,
-                 F_WAIT_Q1 = 16, F_WAIT_Q2 = 32, F_WAIT_Q3 = 64, F_COMMIT_BOTH = 128 };   // pipelined plans: A-ready barriers of column quarters 1..3 (F_STAGE_BEGIN = quarter 0)
+enum : uint16_t { F_ZERO_ACC = 1, F_STAGE_END = 2, F_HI_ONLY_A = 4, F_STAGE_BEGIN = 8,
+                  F_WAIT_Q1 = 16, F_WAIT_Q2 = 32, F_WAIT_Q3 = 64, F_COMMIT_BOTH = 128,   // pipelined plans: A-ready barriers of column quarters 1..3 (F_STAGE_BEGIN = quarter 0)
+                  // side pass that borrows accumulator half 1 (dgrad of 4-D points, 96-wide skip share of d(PE)): its last slab
+                  // commits to the side barrier INSTEAD of accf[pad]; the pass that re-initialises the half waits until the
+                  // epilogue has parked the side result (one use per tile: parity = tile parity)
+                  F_COMMIT_SIDE = 256, F_WAIT_SIDE = 512 };
 
 struct SlabDef {
   uint16_t n;          // rows of the B slab (= GEMM N), multiple of 16
@@ -31,8 +35,8 @@ struct SlabDef {
   uint16_t a_off;      // A_TMEM: column offset inside the A_hi / A_lo regions (8 per k16)
                        // A_SMEM: byte offset / 16 of the hi slab inside the smem A area
   uint16_t a_lo_delta; // A_SMEM: byte distance / 16 from the hi to the lo image
+  uint16_t flags;
   uint8_t a_kind;
-  uint8_t flags;
   uint8_t stage;
   uint8_t pad;         // pipelined plans: which accumulator-half barrier F_STAGE_END commits to
   uint32_t img_off;    // byte offset of the slab in the NSPLIT==1 weight image (x2 for NSPLIT==3)

@@ -174,6 +174,7 @@ def test_checkpoint_layout(tmp_path):
 
 # ---- slab plans of the N-half pipelined tensor-core kernels (host-side tables, no GPU needed) ----------------
 F_ZERO_ACC, F_STAGE_END, F_HI_ONLY_A, F_STAGE_BEGIN, F_WAIT_Q1, F_WAIT_Q2, F_WAIT_Q3, F_COMMIT_BOTH = 1, 2, 4, 8, 16, 32, 64, 128
+F_COMMIT_SIDE, F_WAIT_SIDE = 256, 512
 A_TMEM, A_SMEM, A_MIX = 0, 1, 2
 
 
@@ -193,7 +194,8 @@ def _plan(which):
 
 @pytest.mark.parametrize("which,name,ring_multiples", [(1, "pipelined forward (3-D points)", (8, 24)),
                                                        (2, "pipelined forward (4-D points)", (6, 24)),
-                                                       (4, "pipelined dgrad", (8, 24))])
+                                                       (4, "pipelined dgrad (3-D points)", (8, 24)),
+                                                       (3, "pipelined dgrad (4-D points)", (8, 24))])
 def test_pipelined_slab_plans(which, name, ring_multiples):
     """Hazard invariants of the N-half pipelined schedules (csrc/field_tc_fwd_pipe.cuh, field_tc_dgrad_pipe.cuh):
     every K-slab that reads operand quarter q is issued after this stage's wait on quarter barrier q; an accumulator
@@ -214,8 +216,20 @@ def test_pipelined_slab_plans(which, name, ring_multiples):
         waited = set()
         zeroed = set()
         commits = []
+        side = "none"                                  # side pass borrowing acc1 (4-D dgrad, T4): none -> open -> committed -> parked
         for s in mine:
             fl = s["flags"]
+            if fl & F_WAIT_SIDE:
+                assert side == "committed" and (fl & F_ZERO_ACC) and s["acc_col"] == 128, (name, st, "side wait misplaced", s)
+                side = "parked"
+            elif s["acc_col"] == 128 and side in ("open", "committed"):
+                assert side == "open" and not (fl & F_ZERO_ACC), (name, st, "acc1 touched while it holds the side result", s)
+            if (fl & F_ZERO_ACC) and s["acc_col"] == 128 and s["n"] == 96:
+                assert side == "none" and 0 in zeroed, (name, st, "side pass must follow the h0 pass")
+                side = "open"
+            if fl & F_COMMIT_SIDE:
+                assert side == "open" and not (fl & F_STAGE_END), (name, st, s)
+                side = "committed"
             for q, bit in enumerate((F_STAGE_BEGIN, F_WAIT_Q1, F_WAIT_Q2, F_WAIT_Q3)):
                 if fl & bit:
                     assert q not in waited, (name, st, "barrier waited twice", q)
@@ -247,12 +261,8 @@ def test_pipelined_slab_plans(which, name, ring_multiples):
                 commits.append(s["pad"])
                 if fl & F_COMMIT_BOTH:
                     commits.append(s["pad"] ^ 1)
+        assert side in ("none", "parked"), (name, st, side)        # a side pass is always drained inside its stage
+        assert (side == "parked") == (which == 3 and st == 4)
         assert waited == {0, 1, 2, 3}, (name, st, waited)          # every barrier advances once per stage
         assert sorted(commits) == [0, 1], (name, st, commits)      # both accumulator-half barriers fire once
         assert mine[-1]["flags"] & F_STAGE_END                     # nothing is issued after the stage's last commit
-
-
-def test_serial_dgrad_plan_for_4d_points():
-    """The serial dgrad chain remains for the 96-wide d(PE) of the NeRF++ background network: its table still fits its ring."""
-    n, st, _, slabs = _plan(3)
-    assert (n, st) == (176, 11) and all(s["n"] in (256, 96, 32) for s in slabs)
