@@ -55,25 +55,14 @@ struct Ctx {
   uint32_t ring_addr;      // shared address of ring slot 0
   uint32_t full_addr;      // shared address of full[0]   (8 bytes apart)
   uint32_t empty_addr;     // shared address of empty[0]
-  uint32_t acc_full_addr, a_ready_addr;
-  uint32_t tmem_acc, tmem_ahi, tmem_alo;
+  uint32_t acc_full_addr, a_ready_addr;   // (unused since the serial schedules were retired; the pipelined kernels keep their
+  uint32_t tmem_acc, tmem_ahi, tmem_alo;  //  barriers in fpipe::PCtx)
   uint32_t smem_a;         // shared address of the smem A area
   uint64_t pol_keep;       // L2 evict_last  (weight slabs: re-read by every SM for every tile)
   uint64_t pol_stream;     // L2 evict_first (write-once / read-once tile images)
-  long long* dbg;          // optional timeline (CTA 0 only): [tile][stage][4] clock64 stamps
-                           //   0: MMA thread passed a_ready   1: MMA thread issued the stage's last commit
-                           //   2: epilogue (warp 2) saw acc_full   3: epilogue (warp 2) arrived on a_ready
+  long long* dbg;          // (unused: the timeline stamps are fpipe::stamp)
   int dbg_tiles;
 };
-__device__ __forceinline__ void dbg_stamp(const Ctx& c, int tile_iter, int stage, int n_stages, int slot) {
-#ifdef SCNERF_TIMELINE      // (see fpipe::stamp)
-  if (c.dbg != nullptr && blockIdx.x == 0 && tile_iter < c.dbg_tiles)
-    c.dbg[((size_t)tile_iter * n_stages + stage) * 4 + slot] = clock64();
-#else
-  (void)c; (void)tile_iter; (void)stage; (void)n_stages; (void)slot;
-#endif
-}
-
 __device__ __forceinline__ void mbar_wait_a(uint32_t addr, uint32_t parity) {
   uint32_t ok;
   do {
@@ -126,77 +115,13 @@ __device__ __forceinline__ void producer_tile(const Ctx& c, const uint8_t* __res
   (producer_step<K, (int)Is>(c, wimg, tp), ...);
 }
 template <class K>
-__device__ __forceinline__ void producer_loop(const Ctx& c, const uint8_t* __restrict__ wimg, int num_tiles) {
-  uint32_t tp = 0;
-  for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, tp ^= 1u)
-    producer_tile<K>(c, wimg, tp, std::make_index_sequence<K::PLAN.n_slabs>{});
-}
-
-template <class K>
 __device__ __forceinline__ void producer_loop_n(const Ctx& c, const uint8_t* __restrict__ wimg, int count) {
   uint32_t tp = 0;
   for (int it = 0; it < count; ++it, tp ^= 1u)
     producer_tile<K>(c, wimg, tp, std::make_index_sequence<K::PLAN.n_slabs>{});
 }
 
-template <class K, int I>
-__device__ __forceinline__ void mma_step(const Ctx& c, uint32_t tp, int tile_iter) {
-  constexpr SlabDef d = K::PLAN.slab[I];
-  constexpr bool SPLIT = K::NSPLIT == 3;
-  constexpr int G = I / K::GROUP;
-  constexpr int idx = G % K::NSLOT, wrap = G / K::NSLOT;
-  constexpr bool wraps_odd = (((K::PLAN.n_slabs / K::GROUP) / K::NSLOT) & 1) != 0;
-  constexpr bool stages_odd = (K::PLAN.n_stages & 1) != 0;
-  constexpr uint32_t in_slot = group_bytes<K>(G * K::GROUP, I);   // offset of this slab inside its slot
-  if constexpr ((d.flags & F_STAGE_BEGIN) != 0) {   // A operand of this stage written, accumulator drained
-    mbar_wait_a(c.a_ready_addr, (uint32_t)(d.stage & 1) ^ (stages_odd ? tp : 0u));
-    tc::tc_fence_after();
-    dbg_stamp(c, tile_iter, d.stage, K::PLAN.n_stages, 0);
-  }
-  if constexpr (I % K::GROUP == 0) {
-    mbar_wait_a(c.full_addr + idx * 8, (uint32_t)(wrap & 1) ^ (wraps_odd ? tp : 0u));
-    tc::tc_fence_after();
-  }
-  constexpr uint32_t idesc = tc::idesc_bf16_f32(TILE_M, d.n);
-  constexpr uint32_t LBO_B = (uint32_t)d.n * 16u;
-  const uint32_t slot = c.ring_addr + idx * K::SLOT_BYTES + in_slot;
-  const uint64_t b_hi = desc_at<LBO_B, 128>(slot);
-  const uint64_t b_lo = desc_at<LBO_B, 128>(slot + (uint32_t)d.n * 32u);
-  const uint32_t acc = c.tmem_acc + d.acc_col;
-  constexpr uint32_t first = (d.flags & F_ZERO_ACC) ? 0u : 1u;
-  if constexpr (d.a_kind == A_TMEM) {
-    tc::mma_ts(acc, c.tmem_ahi + d.a_off, b_hi, idesc, first);
-    if constexpr (SPLIT) {
-      if constexpr ((d.flags & F_HI_ONLY_A) == 0) tc::mma_ts(acc, c.tmem_alo + d.a_off, b_hi, idesc, 1);
-      tc::mma_ts(acc, c.tmem_ahi + d.a_off, b_lo, idesc, 1);
-    }
-  } else {
-    const uint32_t a_addr = c.smem_a + (uint32_t)d.a_off * 16u;
-    const uint64_t a_hi = desc_at<2048, 128>(a_addr);
-    tc::mma_ss(acc, a_hi, b_hi, idesc, first);
-    if constexpr (SPLIT) {
-      if constexpr ((d.flags & F_HI_ONLY_A) == 0)
-        tc::mma_ss(acc, desc_at<2048, 128>(a_addr + (uint32_t)d.a_lo_delta * 16u), b_hi, idesc, 1);
-      tc::mma_ss(acc, a_hi, b_lo, idesc, 1);
-    }
-  }
-  if constexpr (I % K::GROUP == K::GROUP - 1) commit_a(c.empty_addr + idx * 8);
-  if constexpr ((d.flags & F_STAGE_END) != 0) {
-    commit_a(c.acc_full_addr);
-    dbg_stamp(c, tile_iter, d.stage, K::PLAN.n_stages, 1);
-  }
-}
-template <class K, size_t... Is>
-__device__ __forceinline__ void mma_tile(const Ctx& c, uint32_t tp, int tile_iter, std::index_sequence<Is...>) {
-  (mma_step<K, (int)Is>(c, tp, tile_iter), ...);
-}
-template <class K>
-__device__ __forceinline__ void mma_loop(const Ctx& c, int num_tiles) {
-  uint32_t tp = 0;
-  int it = 0;
-  for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, tp ^= 1u, ++it)
-    mma_tile<K>(c, tp, it, std::make_index_sequence<K::PLAN.n_slabs>{});
-}
+// (The MMA issue loop lives with the pipelined schedules: fpipe::mma_step / mma_loop_r in field_tc_fwd_pipe.cuh.)
 
 // ---- epilogue helpers ----------------------------------------------------------------------------------
 // pack two fp32 into bf16x2 (first argument -> low half), optionally with ReLU
@@ -296,23 +221,6 @@ __device__ __forceinline__ void dump32(const ImgDump& d, int tile, uint32_t k, u
     if (SPLIT && d.nhalf == 2)
       tc::st_v4_hint(p + d.F * 32u + g * 256, make_uint4(lo[4 * g], lo[4 * g + 1], lo[4 * g + 2], lo[4 * g + 3]), pol);
   }
-}
-
-// Dump `nchunk` x 32 features starting at feature c0 of this thread's row straight from the TMEM A
-// operand (packed bf16 pairs: hi region [+ lo region]) into a tile image.  Called by the epilogue warps
-// while the tensor pipe runs the NEXT stage, so the HBM stores are off the stage's critical path.
-template <bool SPLIT, int NCHUNK>
-__device__ __forceinline__ void dump_from_tmem(const ImgDump& d, int tile, uint32_t row, uint32_t t_ahi,
-                                               uint32_t t_alo, uint32_t lane_base, uint32_t c0, uint64_t pol) {
-  uint32_t hi[NCHUNK][16], lo[NCHUNK][16];
-#pragma unroll
-  for (int cc = 0; cc < NCHUNK; ++cc) {
-    tc::tmem_ld16(t_ahi + lane_base + ((c0 + cc * 32) >> 1), hi[cc]);
-    if (SPLIT) tc::tmem_ld16(t_alo + lane_base + ((c0 + cc * 32) >> 1), lo[cc]);
-  }
-  tc::tmem_ld_wait();
-#pragma unroll
-  for (int cc = 0; cc < NCHUNK; ++cc) dump32<SPLIT>(d, tile, row, c0 + cc * 32, hi[cc], lo[cc], pol);
 }
 
 }  // namespace eng
