@@ -248,7 +248,7 @@ class NerfWorkload:
     def __init__(self, wname, rays, rank, dev, precision):
         from scnerf_b200 import synth
         from scnerf_b200.engine import TrainStep
-        self.w, self.wname, self.N = WORKLOADS[wname], wname, rays
+        self.w, self.wname, self.N, self.precision = WORKLOADS[wname], wname, rays, precision
         w = self.w
         self.mods = synth.build_modules(0, dev)                           # identical replicas on every rank
         kps, idx, target = synth.pixel_batch(1000 + rank, rays)           # each rank draws its own rays
@@ -279,6 +279,24 @@ class NerfWorkload:
             self.api = ("scnerf_train_step(host buffers) + get_rays_kps_use_camera / proj_ray_dist_loss_single on pinned-host "
                         "matches + CustomAdamOptimizer.step (scnerf_adam_step)")
         self.loss_host = eng.loss_host
+
+    def inference_step(self):
+        """Forward only, as `render_path` calls it (no_grad `batchify_rays`, NeRF/render.py:398-413): ray packing done once,
+        then coarse + hierarchical sampling + fine with the alpha-composite fused into the field kernel's epilogue."""
+        from scnerf_b200 import synth
+        from scnerf_b200.render import batchify_rays
+        if not hasattr(self, "inf_rays"):
+            from scnerf_b200.get_rays import get_rays_kps_use_camera
+            from scnerf_b200.render import _pack_rays
+            cam, eng, H, W = self.mods["cam"], self.eng, synth.FERN_H, synth.FERN_W
+            with torch.no_grad():
+                o, d = get_rays_kps_use_camera(H=H, W=W, camera_model=cam, idx_in_camera_param=eng.idx_dev, kps_list=eng.kps_dev)
+                self.inf_rays = _pack_rays(H, W, o, d, cam, None, True, True, 0., 1.)
+            self.inf_kw = dict(network_fn=self.mods["coarse"], network_query_fn=None, N_samples=self.w["Nc"],
+                               N_importance=self.w["Nf"], network_fine=self.mods["fine"], perturb=0., raw_noise_std=0.,
+                               precision=self.precision)
+        with torch.no_grad():
+            return batchify_rays(self.inf_rays, self.N, **self.inf_kw)
 
     def step(self, on_host):
         from scnerf_b200 import synth
@@ -446,6 +464,25 @@ def main():
     ms_e2e = timed(True, args.steps)
     loss = float(wl.loss_host)
 
+    # forward-only (inference) throughput of the same batch (SURVEY 8d asks for it next to the training metric): outside
+    # the timed training region, device-resident rays
+    ms_inf = None
+    if hasattr(wl, "inference_step"):
+        for _ in range(3):
+            wl.inference_step()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        n_inf = max(10, min(args.steps, 50))
+        for _ in range(n_inf):
+            wl.inference_step()
+        e1.record()
+        barrier()
+        t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_inf = float(t) / n_inf
+
     burst, sustained, hbm, src = measured_peaks()
     kernels, other_ms, tj = kernel_breakdown(lib, wl, 5, w, burst, sustained, hbm, src)
     if rank != 0:
@@ -499,6 +536,13 @@ def main():
         "clocks": clk.summary(),
         "roofline": roof,
     }
+    if ms_inf is not None:
+        fwd_tf = evals_flop_per_ray(w) * rays / (ms_inf * 1e-3) / 1e12
+        line["inference"] = {"value": rays_total / (ms_inf * 1e-3), "unit": "rays/s", "ms_per_batch": ms_inf,
+                             "algorithmic_tflops": fwd_tf, "frac_of_burst": fwd_tf / burst,
+                             "frac_of_3mma_ceiling_burst": 3.0 * fwd_tf / burst,
+                             "api": "no_grad batchify_rays (render_path's call), perturb=0, raw_noise_std=0, device-resident rays; "
+                                    "coarse + sample_pdf + fine, alpha-composite fused into the field kernel"}
     if world == 1 and not args.no_cpu_baseline:
         rps, sec, done = time_cpu_reference(args.workload, 1, 1, budget_s=25.0)
         th = cpu_threads()
