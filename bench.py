@@ -415,6 +415,7 @@ def main():
     ap.add_argument("--precision", default=os.environ.get("SCNERF_PRECISION", "bf16x3"),
                     help="bf16x3 (default: split-bf16 tensor-core path, the parity-grade mode) | bf16 | fp32")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-inference", action="store_true", help="skip the forward-only section (ncu launch lists of the timed step)")
     args = ap.parse_args()
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
     local = int(os.environ.get("LOCAL_RANK", 0))
@@ -467,7 +468,7 @@ def main():
     # forward-only (inference) throughput of the same batch (SURVEY 8d asks for it next to the training metric): outside
     # the timed training region, device-resident rays
     ms_inf = None
-    if hasattr(wl, "inference_step"):
+    if hasattr(wl, "inference_step") and not args.no_inference:
         for _ in range(3):
             wl.inference_step()
         barrier()
