@@ -259,9 +259,7 @@ __global__ void __launch_bounds__(256) head_wgrad_kernel(const float* __restrict
                                                          float* __restrict__ dW,
                                                          float* __restrict__ db) {
   int64_t p0 = (int64_t)blockIdx.x * rows_per_block, p1 = min(P, p0 + rows_per_block);
-  float acc[HEAD_MAX], accb[HEAD_MAX];
-#pragma unroll
-  for (int o = 0; o < HEAD_MAX; ++o) { acc[o] = 0.f; accb[o] = 0.f; }
+  float acc[HEAD_MAX];
   for (int k = threadIdx.x; k < K; k += blockDim.x) {
 #pragma unroll
     for (int o = 0; o < HEAD_MAX; ++o) acc[o] = 0.f;
