@@ -365,24 +365,36 @@ __global__ void __launch_bounds__(128) head_wgrad_img_kernel(eng::ImgDump hv, co
     for (int e = 0; e < 8; ++e) acc[c][e] = 0.f;
   float sb[4] = {0.f, 0.f, 0.f, 0.f};
   for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-    for (int ks = 0; ks < 8; ++ks)
+    // 16 samples per thread and tile, in batches of 4 whose loads (d(raw) row + hi/lo chunk: 48 B) are all issued before
+    // the first use: the loop is load-latency bound (0.28 -> see profiles/README.md round 2)
+#pragma unroll 1
+    for (int b = 0; b < 4; ++b) {
+      float4 gr[4];
+      uint4 ch[4], cl[4];
 #pragma unroll
-      for (int i = 0; i < 2; ++i) {
-        const int kk = ks * 16 + q * 2 + i;
+      for (int u = 0; u < 4; ++u) {
+        const int s16 = b * 4 + u;                       // 0..15 -> (ks, i)
+        const int kk = (s16 >> 1) * 16 + q * 2 + (s16 & 1);
         const int64_t p = (int64_t)tile * 128 + kk;
-        if (p >= P) continue;
-        const float4 gr = *reinterpret_cast<const float4*>(g_raw + p * 4);
+        const bool ok = p < P;
+        gr[u] = ok ? *reinterpret_cast<const float4*>(g_raw + p * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        ch[u] = ok ? *reinterpret_cast<const uint4*>(hv.chunk(tile, kk, g * 8, 0)) : make_uint4(0u, 0u, 0u, 0u);
+        if (NH == 2) cl[u] = ok ? *reinterpret_cast<const uint4*>(hv.chunk(tile, kk, g * 8, 1)) : make_uint4(0u, 0u, 0u, 0u);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
         float h[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-        add_chunk(*reinterpret_cast<const uint4*>(hv.chunk(tile, kk, g * 8, 0)), 1.f, h);
-        if (NH == 2) add_chunk(*reinterpret_cast<const uint4*>(hv.chunk(tile, kk, g * 8, 1)), 1.f, h);
+        add_chunk(ch[u], 1.f, h);
+        if (NH == 2) add_chunk(cl[u], 1.f, h);
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
-          acc[0][e] = fmaf(gr.x, h[e], acc[0][e]);
-          acc[1][e] = fmaf(gr.y, h[e], acc[1][e]);
-          acc[2][e] = fmaf(gr.z, h[e], acc[2][e]);
+          acc[0][e] = fmaf(gr[u].x, h[e], acc[0][e]);
+          acc[1][e] = fmaf(gr[u].y, h[e], acc[1][e]);
+          acc[2][e] = fmaf(gr[u].z, h[e], acc[2][e]);
         }
-        if (g == 0) { sb[0] += gr.x; sb[1] += gr.y; sb[2] += gr.z; sb[3] += gr.w; }
+        if (g == 0) { sb[0] += gr[u].x; sb[1] += gr[u].y; sb[2] += gr[u].z; sb[3] += gr[u].w; }
       }
+    }
   }
 #pragma unroll
   for (int c = 0; c < 3; ++c)

@@ -7,6 +7,9 @@ sample_pdf indices bit-exact (sample_pdf pipeline: ties within 1 ulp of a CDF kn
 and reported); gradients judged against the fp32 noise floor measured with an
 fp64 oracle run (the reference's own fp32 camera gradients sit 3e-3..9e-3 of max|g| from fp64).
 """
+import json
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -209,6 +212,8 @@ def test_sample_pdf_golden(lib, golden):
             err = abs(float(s[r, c] - g[f"{tag}_samples"][r, c]))
             assert err <= allowed, f"{tag}: unexplained sample mismatch at {(r, c)}: {err:.2e} > {allowed:.2e} (denom {den:.3e})"
         print(f"sample_pdf {tag}: {len(flips)} knot flips, {len(big)} samples off by >1e-5 (of {64 * 128})")
+        _record(f"sample_pdf/{tag}", {"samples": 64 * 128, "knot_flips_vs_reference_golden": int(len(flips)),
+                                      "samples_off_by_1e-5": int(len(big)), "indices_vs_sequential_order_oracle": "bit-exact"})
         assert len(flips) <= 0.01 * 64 * 128
 
 
@@ -273,12 +278,24 @@ def _oracle_gap_c2mini(seed, kps, idx, perturb, std, wb):
     return float((outs[0] - outs[1]).abs().max())
 
 
+def _record(key, value):
+    """Counts the tests used to only print: merged into gpurun_out/r2_parity_counts.json, which the GPU run
+    brings back (-> profiles/)."""
+    os.makedirs("gpurun_out", exist_ok=True)
+    path = "gpurun_out/r2_parity_counts.json"
+    data = json.load(open(path)) if os.path.exists(path) else {}
+    data[key] = value
+    with open(path, "w") as f:
+        json.dump(data, f, indent=1, sort_keys=True)
+
+
 def _check_rays(a, ref, gap, what):
     """>= 95 % of rays within 1e-4 (scale 1); the rest bounded by the batch's own fp32-vs-fp64 gap."""
     a = a.detach().cpu().numpy() if isinstance(a, torch.Tensor) else np.asarray(a)
     d = np.abs(a.reshape(a.shape[0], -1).astype(np.float64) - np.asarray(ref, np.float64).reshape(a.shape[0], -1)).max(1)
     nbad = int((d > 1e-4).sum())
     print(f"{what}: {nbad} of {len(d)} rays off by > 1e-4 (max {d.max():.2e}; reference fp32-vs-fp64 gap {gap:.2e})")
+    _record(f"rays/{what}", {"rays": int(len(d)), "over_1e-4": nbad, "max": float(d.max()), "oracle_fp32_vs_fp64_gap": float(gap)})
     assert nbad <= max(1, int(0.05 * len(d))), what
     assert d.max() <= 4.0 * gap + 1e-4, what   # one jumped fine sample on an opaque ray moves rgb/acc by ~1e-3
 
