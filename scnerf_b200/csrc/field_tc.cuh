@@ -623,8 +623,10 @@ inline int field_tc_bwd_impl(const scnerf_mlp& m, const scnerf_mlp& g, const flo
   }
   SCNERF_LAUNCH((wgrad::field_wgrad_kernel<NSPLIT>), (unsigned)w.cta0[wgrad::NJOBS], 320,
                 wgrad::Cfg<NSPLIT>::SMEM_BYTES, stream, w);
-  SCNERF_LAUNCH((wgrad::head_wgrad_img_kernel<(NSPLIT == 3 ? 2 : 1)>), (unsigned)std::min(T, 8 * device_sm_count()), 128, 0,
-                stream, I.hv, g_raw, P, T, g.rgb_w, g.rgb_b, g.alpha_b);   // 8 CTAs/SM: the loop is load-latency bound
+  static int head_ctas = -1;    // CTAs per SM of the head-gradient kernel (each CTA ends with 388 atomics onto the same addresses)
+  if (head_ctas < 0) { const char* e = getenv("SCNERF_HEAD_WGRAD_CTAS_PER_SM"); head_ctas = e ? std::max(1, atoi(e)) : 4; }   // 4: profiles/r2v_head_wgrad_grid.txt (8: 0.27 ms, 4: 0.20, 2: 0.22, 16: 0.42)
+  SCNERF_LAUNCH((wgrad::head_wgrad_img_kernel<(NSPLIT == 3 ? 2 : 1)>), (unsigned)std::min(T, head_ctas * device_sm_count()), 128, 0,
+                stream, I.hv, g_raw, P, T, g.rgb_w, g.rgb_b, g.alpha_b);   // the loop is load-latency bound
   return 0;
 }
 inline int field_tc_bwd(const scnerf_mlp& m, const scnerf_mlp& g, int precision, const float* rays, int ray_cols,
