@@ -218,6 +218,9 @@ int scnerf_posenc_fwd(const float* x, int64_t P, int32_t L, float* out, void* st
 /* run_network + NeRF.forward, create_nerf.py:18-32 + run_nerf_helpers.py:105-128:
  * pts[N,S,3], viewdirs[N,3]|NULL -> raw[N,S,4|output_ch]. */
 size_t scnerf_field_workspace_bytes(const scnerf_mlp* m, int64_t P, int32_t training);
+/* Workspace of scnerf_field_fwd for a given precision: the tensor-core precisions keep the activations in TMEM and need
+ * only the packed weight image (a few MB, independent of P); fp32 needs the [P, W] activation buffers. */
+size_t scnerf_field_infer_workspace_bytes(const scnerf_mlp* m, int64_t P, int32_t precision);
 int scnerf_field_fwd(const scnerf_mlp* m, const float* pts, const float* viewdirs, int64_t N,
                      int64_t S, float* raw, int32_t precision, void* workspace,
                      size_t workspace_bytes, void* stream);

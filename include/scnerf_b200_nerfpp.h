@@ -97,6 +97,12 @@ int scnerf_pp_depth_bwd(const float* d_depth, const float* coef, int64_t N, int6
  * Backward outputs (any may be NULL): d_rays[N,ray_cols] += (columns o, d, viewdirs), d_z[N,S]
  * overwrite (d_pts . d), d_pts[N,S,pts_dim] overwrite, d_viewdirs[N,3] +=.
  * ---------------------------------------------------------------------------------------------- */
+/* No-grad twin of scnerf_field_train_fwd (same arguments, same raw[N,S,4]): no tile images or activations are kept, so the
+ * workspace is the packed weight image only for the tensor-core precisions (render_single_image, ddp_train_nerf.py:135-256). */
+size_t scnerf_field_infer_rays_workspace_bytes(const scnerf_mlp* m, int64_t N, int64_t S, int32_t precision);
+int scnerf_field_infer_fwd(const scnerf_mlp* m, const float* rays, int32_t ray_cols, const float* z,
+                           const float* pts, const float* viewdirs, int64_t N, int64_t S, float* raw,
+                           int32_t precision, void* workspace, size_t workspace_bytes, void* stream);
 size_t scnerf_field_train_workspace_bytes(const scnerf_mlp* m, int64_t N, int64_t S, int32_t precision);
 int scnerf_field_train_fwd(const scnerf_mlp* m, const float* rays, int32_t ray_cols, const float* z,
                            const float* pts, const float* viewdirs, int64_t N, int64_t S, float* raw,

@@ -155,6 +155,7 @@ SIGNATURES = {
                                     _P(RenderGradsIn), _P(Mlp), _P(Mlp), vp, vp, _SZ, vp]),
     "scnerf_posenc_fwd": (_I, [vp, _I64, C.c_int32, vp, vp]),
     "scnerf_field_workspace_bytes": (_SZ, [_P(Mlp), _I64, C.c_int32]),
+    "scnerf_field_infer_workspace_bytes": (_SZ, [_P(Mlp), _I64, C.c_int32]),
     "scnerf_field_fwd": (_I, [_P(Mlp), vp, vp, _I64, _I64, vp, C.c_int32, vp, _SZ, vp]),
     "scnerf_raw2outputs_fwd": (_I, [vp, C.c_int32, vp, vp, C.c_int32, vp, C.c_int32, _I64, _I64,
                                     vp, vp, vp, vp, vp, vp]),
@@ -185,6 +186,8 @@ SIGNATURES = {
     "scnerf_pp_perturb_samples_bwd": (_I, [vp, vp, _I64, _I64, vp, vp]),
     "scnerf_pp_depth_bwd": (_I, [vp, vp, _I64, _I64, vp, vp]),
     "scnerf_field_train_workspace_bytes": (_SZ, [_P(Mlp), _I64, _I64, C.c_int32]),
+    "scnerf_field_infer_rays_workspace_bytes": (_SZ, [_P(Mlp), _I64, _I64, C.c_int32]),
+    "scnerf_field_infer_fwd": (_I, [_P(Mlp), vp, C.c_int32, vp, vp, vp, _I64, _I64, vp, C.c_int32, vp, _SZ, vp]),
     "scnerf_field_train_fwd": (_I, [_P(Mlp), vp, C.c_int32, vp, vp, vp, _I64, _I64, vp, C.c_int32, vp, _SZ, vp]),
     "scnerf_field_train_bwd": (_I, [_P(Mlp), _P(Mlp), vp, C.c_int32, vp, vp, vp, _I64, _I64, vp, vp, vp, vp, vp,
                                     C.c_int32, vp, _SZ, vp]),

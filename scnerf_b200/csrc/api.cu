@@ -241,6 +241,13 @@ size_t scnerf_field_workspace_bytes(const scnerf_mlp* m, int64_t P, int32_t trai
   field_bufs_alloc(ar, *m, P, training != 0, B);
   return ar.off + 256;
 }
+size_t scnerf_field_infer_workspace_bytes(const scnerf_mlp* m, int64_t P, int32_t precision) {
+  if (!m) return 0;
+  Arena ar(nullptr, 0);
+  FieldBufs B;
+  field_bufs_alloc(ar, *m, P, false, B, precision != SCNERF_PRECISION_FP32);
+  return ar.off + 256;
+}
 
 static int field_fwd_dispatch(const scnerf_mlp& m, int precision, const float* rays, int ray_cols,
                               const float* z, const float* pts, const float* viewdirs, int64_t N,
@@ -263,7 +270,8 @@ int scnerf_field_fwd(const scnerf_mlp* m, const float* pts, const float* viewdir
   if (N * S == 0) return 0;
   Arena ar(workspace, workspace_bytes);
   FieldBufs B;
-  field_bufs_alloc(ar, *m, N * S, false, B);
+  // tensor-core precisions keep every activation in TMEM: only the packed weight image and constants live here
+  field_bufs_alloc(ar, *m, N * S, false, B, precision != SCNERF_PRECISION_FP32);
   if (!workspace || !ar.ok())
     return fail(SCNERF_ERR_WORKSPACE, "field_fwd: workspace %zu < %zu bytes", workspace_bytes, ar.off);
   return field_fwd_dispatch(*m, precision, nullptr, 0, nullptr, pts, viewdirs, N, (int)S, B, raw, stream);
@@ -358,7 +366,7 @@ static void render_ws_layout(Arena& ar, const scnerf_render_cfg& cfg, const scne
     field_grad_bufs_alloc(ar, m, N * std::max(Nc, St), w.gb);
   } else {
     w.g_raw = nullptr;
-    field_bufs_alloc(ar, m, N * std::max(Nc, St), false, w.fb_c);
+    field_bufs_alloc(ar, m, N * std::max(Nc, St), false, w.fb_c, cfg.precision != SCNERF_PRECISION_FP32);
     w.fb_f = w.fb_c;
   }
 }

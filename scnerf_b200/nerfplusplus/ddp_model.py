@@ -54,7 +54,7 @@ def depth2pts_outside(ray_o, ray_d, depth):
 
 class _NerfNetFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, net, ray_o, ray_d, fg_z_max, fg_z_vals, bg_z_vals, *params):
+    def forward(ctx, net, grad_enabled, ray_o, ray_d, fg_z_max, fg_z_vals, bg_z_vals, *params):
         lib = _lib.load()
         st = _lib.stream()
         lead = ray_d.shape[:-1]
@@ -66,15 +66,18 @@ class _NerfNetFn(torch.autograd.Function):
         dev = o.device
         E = lambda *s: torch.empty(*s, device=dev, dtype=torch.float32)
         prec = _lib.PRECISION[net.precision]
-        training = any(ctx.needs_input_grad)
+        # (needs_input_grad reflects requires_grad even under torch.no_grad(): the caller's grad mode comes in explicitly)
+        training = bool(grad_enabled) and any(ctx.needs_input_grad)
+        ws_bytes = lib.scnerf_field_train_workspace_bytes if training else lib.scnerf_field_infer_rays_workspace_bytes
+        field_fwd = lib.scnerf_field_train_fwd if training else lib.scnerf_field_infer_fwd   # no-grad: nothing is kept
         m_fg, m_bg = net.fg_net.c_struct(pts_dim=3), net.bg_net.c_struct(pts_dim=4)
         rays = E(N, 11)
         _lib.check(lib.scnerf_pp_pack_rays(_lib.ptr(o), _lib.ptr(d), N, _lib.ptr(rays), st), "pp_pack_rays")
         # ---- foreground
-        nb = lib.scnerf_field_train_workspace_bytes(m_fg, N, Sf, prec)
+        nb = ws_bytes(m_fg, N, Sf, prec)
         ws_fg = torch.empty(nb, device=dev, dtype=torch.uint8)
         raw_fg = E(N, Sf, 4)
-        _lib.check(lib.scnerf_field_train_fwd(m_fg, _lib.ptr(rays), 11, _lib.ptr(fz), None, None, N, Sf, _lib.ptr(raw_fg),
+        _lib.check(field_fwd(m_fg, _lib.ptr(rays), 11, _lib.ptr(fz), None, None, N, Sf, _lib.ptr(raw_fg),
                                               prec, _lib.ptr(ws_fg), nb, st), "field_train_fwd(fg)")
         fg_w, fg_rgb, fg_depth, lam = E(N, Sf), E(N, 3), E(N), E(N)
         _lib.check(lib.scnerf_pp_composite_fg_fwd(_lib.ptr(raw_fg), _lib.ptr(fz), _lib.ptr(zmax), _lib.ptr(d), N, Sf,
@@ -85,10 +88,10 @@ class _NerfNetFn(torch.autograd.Function):
         _lib.check(lib.scnerf_pp_bg_points_fwd(_lib.ptr(o), _lib.ptr(d), _lib.ptr(bz), N, Sb, _lib.ptr(pts4), None, st),
                    "pp_bg_points")
         vd = rays[:, 8:11].contiguous()
-        nbb = lib.scnerf_field_train_workspace_bytes(m_bg, N, Sb, prec)
+        nbb = ws_bytes(m_bg, N, Sb, prec)
         ws_bg = torch.empty(nbb, device=dev, dtype=torch.uint8)
         raw_bg = E(N, Sb, 4)
-        _lib.check(lib.scnerf_field_train_fwd(m_bg, None, 0, None, _lib.ptr(pts4), _lib.ptr(vd), N, Sb, _lib.ptr(raw_bg), prec,
+        _lib.check(field_fwd(m_bg, None, 0, None, _lib.ptr(pts4), _lib.ptr(vd), N, Sb, _lib.ptr(raw_bg), prec,
                                               _lib.ptr(ws_bg), nbb, st), "field_train_fwd(bg)")
         bg_w, bg_rgb, bg_depth, rgb = E(N, Sb), E(N, 3), E(N), E(N, 3)
         _lib.check(lib.scnerf_pp_composite_bg_fwd(_lib.ptr(raw_bg), _lib.ptr(bz), _lib.ptr(lam), _lib.ptr(fg_rgb), N, Sb,
@@ -147,7 +150,7 @@ class _NerfNetFn(torch.autograd.Function):
                    "pp_pack_rays_bwd")
         so, sd, sm, sz = ctx.shapes
         ctx.t = None
-        return (None, g_o.reshape(so), g_d.reshape(sd), d_zmax.reshape(sm), d_fz.reshape(sz), None, *g_fg, *g_bg)
+        return (None, None, g_o.reshape(so), g_d.reshape(sd), d_zmax.reshape(sm), d_fz.reshape(sz), None, *g_fg, *g_bg)
 
 
 class NerfNet(nn.Module):
@@ -168,7 +171,7 @@ class NerfNet(nn.Module):
 
     def forward(self, ray_o, ray_d, fg_z_max, fg_z_vals, bg_z_vals):
         params = self.fg_net.field_tensors() + self.bg_net.field_tensors()
-        outs = _NerfNetFn.apply(self, ray_o, ray_d, fg_z_max, fg_z_vals, bg_z_vals, *params)
+        outs = _NerfNetFn.apply(self, torch.is_grad_enabled(), ray_o, ray_d, fg_z_max, fg_z_vals, bg_z_vals, *params)
         keys = ("rgb", "fg_weights", "bg_weights", "fg_rgb", "fg_depth", "bg_rgb", "bg_depth", "bg_lambda")
         return OrderedDict(zip(keys, outs))
 

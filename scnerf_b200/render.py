@@ -98,7 +98,10 @@ class _RenderRays(torch.autograd.Function):
         dev = rays.device
         nc = len(net_c.field_tensors())
         p_c, p_f = params[:nc], params[nc:]
-        training = any(ctx.needs_input_grad)   # (grad mode is always off inside forward)
+        # needs_input_grad is filled from the inputs' requires_grad even under torch.no_grad(), and grad mode is always
+        # off inside forward: the caller's grad mode is captured by render_rays (opt["grad"]).  Without it every no-grad
+        # render ran the TRAINING forward (tile images, 4 MB of workspace per ray, no fused composite).
+        training = bool(opt.get("grad", True)) and any(ctx.needs_input_grad)
         cfg = _lib.RenderCfg()
         cfg.N_samples, cfg.N_importance, cfg.ray_cols = opt["N_samples"], opt["N_importance"], cols
         cfg.lindisp, cfg.white_bkgd = int(opt["lindisp"]), int(opt["white_bkgd"])
@@ -202,7 +205,8 @@ def render_rays(ray_batch, network_fn, network_query_fn, N_samples, retraw=False
     dev = ray_batch.device
     opt = dict(N_samples=int(N_samples), N_importance=int(N_importance), lindisp=bool(lindisp),
                white_bkgd=bool(white_bkgd), perturb=float(perturb), raw_noise_std=float(raw_noise_std),
-               retraw=bool(retraw), precision=precision or _lib.default_precision(), seed=_seed())
+               retraw=bool(retraw), precision=precision or _lib.default_precision(), seed=_seed(),
+               grad=torch.is_grad_enabled())
     if pytest:
         if perturb > 0.:
             opt["t_rand"] = _np_rand((N, N_samples), dev)

@@ -299,6 +299,77 @@ def test_render_lindisp_no_ndc_vs_oracle(lib, precision):
     _record(f"grads/lindisp no-ndc {precision}: tensors above the fp32 floor", worst)
 
 
+def test_render_full_image_branches_and_render_path(lib):
+    """The four ray-source branches of `render` that take no precomputed rays (NeRF/render.py:33-101: trained camera on a
+    train image, trained camera + aligned test pose, noisy pinhole, ground-truth pinhole) and `render_path` on top of them
+    (:143-183): each equals the explicit composition get_rays_full_image_* -> render(rays=...) bit for bit, returns
+    [H, W, .]-shaped maps, and keeps the reference's asserts on illegal argument combinations.  A 24-row strip keeps the
+    full-image cost at 12 K rays (the camera's residual grids are defined on the full 378 x 504 frame)."""
+    from scnerf_b200.get_rays import get_rays_full_image_no_camera, get_rays_full_image_use_camera
+    from scnerf_b200.render import render, render_path
+    mods = build_modules(14, DEV)
+    cam = mods["cam"]
+    poses = T(synth.camera_poses(14)).to(DEV)                       # [n, 4, 4]
+    K = T(synth.intrinsic_init()).to(DEV)
+    i_map = np.arange(poses.shape[0]) + 3                           # image ids of the train split
+    kw = dict(network_fn=mods["coarse"], network_query_fn=None, N_samples=64, N_importance=128, network_fine=mods["fine"],
+              perturb=0., raw_noise_std=0., use_viewdirs=True, ndc=True, near=0., far=1.)
+    Hs = H                                                          # full frame (the strip is taken from the result)
+
+    def explicit(o, d, camera_model, focal):
+        return render(Hs, W, 1 << 15, rays=(o, d), camera_model=camera_model, noisy_focal=focal, mode="train", **kw)
+
+    torch.cuda.synchronize()
+    torch.cuda.reset_peak_memory_stats()
+    with torch.no_grad():
+        cases = []
+        # (:33-50) trained camera, image of the train split
+        got = render(Hs, W, 1 << 15, camera_model=cam, mode="train", image_idx=int(i_map[2]), i_map=i_map,
+                     noisy_extrinsic=poses, **kw)
+        o, d = get_rays_full_image_use_camera(H=Hs, W=W, camera_model=cam, extrinsic=poses[2])
+        cases.append(("camera/train", got, explicit(o, d, cam, None)))
+        # (:52-67) trained camera, aligned test pose
+        got = render(Hs, W, 1 << 15, camera_model=cam, mode="test", transform_align=poses[1], **kw)
+        o, d = get_rays_full_image_use_camera(H=Hs, W=W, camera_model=cam, extrinsic=poses[1])
+        cases.append(("camera/test", got, explicit(o, d, cam, None)))
+        # (:69-83) noisy pinhole
+        got = render(Hs, W, 1 << 15, mode="train", noisy_focal=FOCAL, noisy_extrinsic=poses, image_idx=4, **kw)
+        o, d = get_rays_full_image_no_camera(H=Hs, W=W, focal=FOCAL, extrinsic=poses[4])
+        cases.append(("pinhole/train", got, explicit(o, d, None, FOCAL)))
+        # (:85-101) ground-truth pinhole
+        got = render(Hs, W, 1 << 15, mode="val", gt_intrinsic=K, gt_extrinsic=poses, image_idx=0, **kw)
+        o, d = get_rays_full_image_no_camera(H=Hs, W=W, focal=float(K[0][0]), extrinsic=poses[0])
+        cases.append(("pinhole/val", got, explicit(o, d, None, float(K[0][0]))))
+        for tag, a, b in cases:
+            assert a[0].shape[:2] in ((Hs, W), (W, Hs)) or a[0].numel() == Hs * W * 3, (tag, a[0].shape)
+            for x, y in zip(a[:3], b[:3]):
+                assert torch.equal(x.reshape(-1), y.reshape(-1)), tag
+            assert set(a[3]) == set(b[3]) == {"rgb0", "disp0", "acc0", "z_std"}, (tag, set(a[3]))
+        # render_path over two test poses = the per-image renders stacked (numpy, [n, H, W, 3])
+        rgbs, disps = render_path(poses[:2], [Hs, W, None], 1 << 15, dict(kw), "test", camera_model=cam,
+                                  transform_align=poses[:2])
+        assert rgbs.shape == (2, Hs, W, 3) and disps.shape == (2, Hs, W)
+        # no-grad rendering must run the INFERENCE forward (activations in TMEM, composite fused): 32768-ray chunks of a
+        # 190 K-ray image stay far below the 4 MB per ray the training workspace needs (a regression here once made every
+        # no-grad render run the training forward: torch.no_grad() does not clear ctx.needs_input_grad)
+        peak = torch.cuda.max_memory_allocated() / 2 ** 30
+        _record("inference/full-image render peak memory GiB (190512 rays, chunk 32768)", round(peak, 3))
+        assert peak < 4.0, f"no-grad render allocated {peak:.1f} GiB: training-mode workspace?"
+        ref = cases[1][1][0].reshape(Hs, W, 3).cpu().numpy()
+        assert np.array_equal(rgbs[1], ref)
+    # the reference's asserts on illegal combinations survive (render.py:25,40-43,59-60,75-76,90-92)
+    with pytest.raises(AssertionError):
+        render(Hs, W, 1 << 15, camera_model=cam, mode=None, **kw)
+    with pytest.raises(AssertionError):
+        render(Hs, W, 1 << 15, camera_model=cam, mode="train", image_idx=999, i_map=i_map, noisy_extrinsic=poses, **kw)
+    with pytest.raises(AssertionError):
+        render(Hs, W, 1 << 15, camera_model=cam, mode="test", noisy_focal=FOCAL, transform_align=poses[0], **kw)
+    with pytest.raises(AssertionError):
+        render(Hs, W, 1 << 15, mode="train", noisy_focal=None, noisy_extrinsic=poses, image_idx=0, **kw)
+    with pytest.raises(AssertionError):
+        render(Hs, W, 1 << 15, mode="val", gt_intrinsic=K, gt_extrinsic=None, image_idx=0, **kw)
+
+
 def unwrap_named(net):
     from scnerf_b200.run_nerf_helpers import unwrap
     return unwrap(net).named_parameters()
