@@ -26,6 +26,33 @@ def default_precision():
         raise ValueError(f"SCNERF_PRECISION={p!r}: expected one of {sorted(PRECISION)}")
     return p
 
+
+_warned_shapes = set()
+
+
+def resolve_precision(precision, *nets):
+    """The precision a call runs at.  An explicit ``precision`` is taken as is (an unsupported network shape then fails
+    loudly in the library).  The DEFAULT adapts to the network: the tcgen05 kernels are specialised for the reference's
+    standard 8 x 256 / skip 4 / view-direction network, every other shape (``--netdepth``, ``--netwidth``, no
+    ``--use_viewdirs``, other ``--multires``) runs on the fp32 CUDA-core kernels, announced once per shape."""
+    if precision is not None:
+        return precision
+    p = default_precision()
+    if p != "fp32":
+        for net in nets:
+            if net is not None and not net.tensor_core_shape():
+                icv = getattr(net, "input_ch_views", getattr(net, "input_ch_viewdirs", None))
+                key = (net.D, net.W, tuple(net.skips), bool(net.use_viewdirs), net.input_ch, icv)
+                if key not in _warned_shapes:
+                    _warned_shapes.add(key)
+                    import warnings
+                    warnings.warn(f"scnerf_b200: network shape D={net.D} W={net.W} skips={list(net.skips)} "
+                                  f"use_viewdirs={bool(net.use_viewdirs)} input_ch={net.input_ch}/{icv} is not "
+                                  f"the one the tensor-core kernels are specialised for: running it on the fp32 CUDA-core "
+                                  f"kernels (exact fp32, slower); pass precision= explicitly to override", stacklevel=3)
+                return "fp32"
+    return p
+
 _f = C.POINTER(C.c_float)
 vp = C.c_void_p
 

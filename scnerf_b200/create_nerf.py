@@ -41,7 +41,7 @@ def run_network(inputs, viewdirs, fn, embed_fn, embeddirs_fn, netchunk=1024 * 64
     m = net.c_struct()
     rc = 4 if net.use_viewdirs else net.output_ch
     raw = torch.empty(N, S, rc, device=pts.device, dtype=torch.float32)
-    prec = _lib.PRECISION[precision or _lib.default_precision()]
+    prec = _lib.PRECISION[_lib.resolve_precision(precision, net)]
     nbytes = lib.scnerf_field_infer_workspace_bytes(C.byref(m), N * S, prec)
     ws = torch.empty(nbytes, dtype=torch.uint8, device=pts.device)
     _lib.check(lib.scnerf_field_fwd(C.byref(m), _lib.ptr(pts), _lib.ptr(vd), N, S, _lib.ptr(raw), prec, _lib.ptr(ws), nbytes,

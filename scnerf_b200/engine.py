@@ -26,7 +26,7 @@ class TrainStep:
         cfg.ray_cols = 11 if self.net_c.use_viewdirs else 8
         cfg.lindisp, cfg.white_bkgd = int(lindisp), int(white_bkgd)
         cfg.perturb, cfg.raw_noise_std = int(perturb > 0), float(raw_noise_std)
-        cfg.training, cfg.precision, cfg.seed = 1, _lib.PRECISION[precision or _lib.default_precision()], int(seed)
+        cfg.training, cfg.precision, cfg.seed = 1, _lib.PRECISION[_lib.resolve_precision(precision, self.net_c, self.net_f)], int(seed)
         self.cfg = cfg
         named = [("coarse." + str(i), t) for i, t in enumerate(self.net_c.field_tensors())]
         if self.net_f is not None:

@@ -167,7 +167,7 @@ class NerfNet(nn.Module):
         self.bg_net = MLPNet(D=args.netdepth, W=args.netwidth, input_ch=self.bg_embedder_position.out_dim,
                              input_ch_viewdirs=self.bg_embedder_viewdir.out_dim, use_viewdirs=args.use_viewdirs)
         # "bf16x3" (default: tcgen05, split-bf16, parity-grade) | "fp32" (CUDA cores) | "bf16" (tcgen05, single pass)
-        self.precision = precision or _lib.default_precision()
+        self.precision = _lib.resolve_precision(precision, self.fg_net, self.bg_net)
 
     def forward(self, ray_o, ray_d, fg_z_max, fg_z_vals, bg_z_vals):
         params = self.fg_net.field_tensors() + self.bg_net.field_tensors()

@@ -47,6 +47,12 @@ class MLPNet(nn.Module):
         self.rgb_layers = nn.Sequential(nn.Linear(256 + input_ch_viewdirs, W // 2), nn.ReLU(),
                                         nn.Linear(W // 2, 3), nn.Sigmoid())
 
+    def tensor_core_shape(self):
+        """True for the shape the tcgen05 kernels are specialised for: 8 x 256, skip 4, view directions, 10 / 4 frequencies
+        (63 channels for the foreground's 3-D points, 84 for the background's 4-D ones)."""
+        return (self.D == 8 and self.W == 256 and self.skips == [4] and bool(self.use_viewdirs)
+                and self.input_ch in (63, 84) and self.input_ch_viewdirs == 27)
+
     def field_tensors(self):
         """Parameters in the order of scnerf_mlp: trunk, views (rgb_layers.0), feature (base_remap),
         alpha (sigma), rgb (rgb_layers.2)."""

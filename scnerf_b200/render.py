@@ -205,7 +205,7 @@ def render_rays(ray_batch, network_fn, network_query_fn, N_samples, retraw=False
     dev = ray_batch.device
     opt = dict(N_samples=int(N_samples), N_importance=int(N_importance), lindisp=bool(lindisp),
                white_bkgd=bool(white_bkgd), perturb=float(perturb), raw_noise_std=float(raw_noise_std),
-               retraw=bool(retraw), precision=precision or _lib.default_precision(), seed=_seed(),
+               retraw=bool(retraw), precision=_lib.resolve_precision(precision, net_c, net_f), seed=_seed(),
                grad=torch.is_grad_enabled())
     if pytest:
         if perturb > 0.:

@@ -126,6 +126,12 @@ class NeRF(nn.Module):
         m._keep = ts
         return m
 
+    def tensor_core_shape(self):
+        """True for the one network shape the tcgen05 kernels are specialised for (the reference's default: 8 x 256, skip at
+        layer 4, view directions, multires 10 / 4).  Other shapes run on the fp32 CUDA-core kernels."""
+        return (self.D == 8 and self.W == 256 and list(self.skips) == [4] and bool(self.use_viewdirs)
+                and self.input_ch == 63 and self.input_ch_views == 27)
+
     def forward(self, x):
         """The reference's ``NeRF.forward`` (run_nerf_helpers.py:105-128) consumes pre-embedded features and
         is only ever reached through ``run_network`` (create_nerf.py:18-32).  Here the positional encoding

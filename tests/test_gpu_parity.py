@@ -156,6 +156,11 @@ def test_field_golden(lib, golden):
     nv.load_state_dict({k: T(v) for k, v in synth.mlp_state(4, use_viewdirs=False, input_ch_views=0).items()})
     raw = run_network(pts[:, None, :], None, nv.to(DEV), e10, None, precision="fp32")   # (no tensor-core plan for this shape)
     close(raw[:, 0, :], g["raw_noview"], 1e-5, "raw (no viewdirs)")
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")                              # (the one-time "running on the fp32 kernels" notice)
+        raw = run_network(pts[:, None, :], None, nv, e10, None)      # default precision adapts to the shape: fp32 kernels
+    close(raw[:, 0, :], g["raw_noview"], 1e-5, "raw (no viewdirs, default precision)")
 
 
 def test_raw2outputs_golden(lib, golden):

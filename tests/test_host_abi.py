@@ -266,3 +266,28 @@ def test_pipelined_slab_plans(which, name, ring_multiples):
         assert waited == {0, 1, 2, 3}, (name, st, waited)          # every barrier advances once per stage
         assert sorted(commits) == [0, 1], (name, st, commits)      # both accumulator-half barriers fire once
         assert mine[-1]["flags"] & F_STAGE_END                     # nothing is issued after the stage's last commit
+
+
+def test_default_precision_follows_the_network_shape():
+    """The default precision is the tensor-core path only for the network shape those kernels are specialised for; other
+    shapes (the reference's own default has no view directions) run on the fp32 CUDA-core kernels, announced once; an
+    explicit precision is never overridden."""
+    import types
+    import warnings
+    from scnerf_b200 import _lib
+    from scnerf_b200.nerfplusplus.ddp_model import NerfNet
+    from scnerf_b200.run_nerf_helpers import NeRF
+    std = NeRF(D=8, W=256, input_ch=63, output_ch=5, skips=[4], input_ch_views=27, use_viewdirs=True)
+    plain = NeRF(D=8, W=256, input_ch=63, output_ch=5, skips=[4], input_ch_views=0, use_viewdirs=False)
+    narrow = NeRF(D=8, W=128, input_ch=63, output_ch=5, skips=[4], input_ch_views=27, use_viewdirs=True)
+    _lib._warned_shapes.clear()
+    assert _lib.resolve_precision(None, std, std) == _lib.default_precision()
+    assert _lib.resolve_precision("bf16x3", plain) == "bf16x3"          # explicit: the library will refuse it loudly
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        assert _lib.resolve_precision(None, std, plain) == "fp32"
+        assert _lib.resolve_precision(None, narrow, None) == "fp32"
+        assert _lib.resolve_precision(None, plain) == "fp32"            # second time: no second warning
+    assert len(w) == 2 and "fp32 CUDA-core" in str(w[0].message)
+    args = types.SimpleNamespace(max_freq_log2=10, max_freq_log2_viewdirs=4, netdepth=8, netwidth=256, use_viewdirs=True)
+    assert NerfNet(args).precision == _lib.default_precision()
