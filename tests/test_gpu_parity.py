@@ -635,6 +635,35 @@ def test_render_c2mini_golden_bf16x3(lib, golden):
         close(ex["rgb0"], g[f"{tag}_rgb0"], 1e-4, f"{tag} rgb0", 1.0)
 
 
+@pytest.mark.parametrize("precision", ["fp32", "bf16x3"])
+def test_train_step_coarse_only(lib, precision):
+    """configs[0]'s shape as a TRAINING step (N_importance = 0: no hierarchical pass, no fine network; run_nerf.py:482-506
+    with `--N_importance 0`): loss, colours and every gradient against the oracle, through the autograd path and through
+    the fused one-call engine."""
+    from scnerf_b200.engine import TrainStep
+    N = 256
+    mods = build_modules(9, DEV)
+    kps, idx, target = synth.pixel_batch(9, N)
+    loss, rgb, grads = cuda_step(mods, kps, idx, target, 64, 0, precision=precision)
+    l32, rgb32, g32 = oracle_step(9, kps, idx, target, 64, 0, torch.float32)
+    _, _, g64 = oracle_step(9, kps, idx, target, 64, 0, torch.float64)
+    assert abs(loss - l32) <= 1e-4 * abs(l32)
+    close(rgb, rgb32, 1e-4, "rgb", 1.0)
+    assert not any(k.startswith("fine.") for k in grads)
+    for k in sorted(g64):
+        floor, mine = rel(g32[k], g64[k]), rel(grads[k], g64[k])
+        assert mine <= max(3.0 * floor, 1e-3), f"{k}: cuda-vs-f64 {mine:.2e}, fp32 oracle floor {floor:.2e}"
+    # the one-call engine on the same batch (its own random draws: compare statistics-free quantities only)
+    eng = TrainStep(mods["cam"], mods["coarse"], None, N, 64, 0, perturb=0., raw_noise_std=0., precision=precision)
+    le = eng.step_device(T(kps).to(DEV), T(idx).to(DEV), T(target).to(DEV))
+    torch.cuda.synchronize()
+    ld, _, gd = cuda_step(mods, kps, idx, target, 64, 0, precision=precision, perturb=0., std=0.)
+    assert abs(float(le) - ld) <= 2e-6 * abs(ld), (float(le), ld)
+    for k in ("coarse.0", "camera.extrinsics_noise"):
+        ref = gd["coarse.pts_linears.0.weight"] if k == "coarse.0" else gd[k]
+        assert rel(eng.grads.views[k].cpu().numpy(), ref) <= 2e-5, k
+
+
 def test_train_step_gradients_bf16x3(lib):
     """Whole step with the tensor-core forward AND backward (fused dgrad + wgrad kernels, split-bf16):
     same noise-floor criterion as the fp32 path (error vs fp64 oracle <= 3x the fp32 oracle's own
