@@ -569,17 +569,31 @@ inline int field_tc_bwd_impl(const scnerf_mlp& m, const scnerf_mlp& g, const flo
   wgrad::Args w{};
   w.num_tiles = T; w.P = P;
   {
-    // CTAs per job in proportion to the measured cycles per K=16 slot of each job (profiles/README.md, r1h):
-    // J0 issues 12 N=64 MMAs, J8 also reduces d(alpha_linear.weight), J9 has the narrowest slab
-    static const int weight[wgrad::NJOBS] = {1385, 1170, 1170, 1170, 1170, 1170, 1170, 1170, 1500, 1100};
+    // CTAs per job.  Round 1 set them in proportion to the measured cycles per K=16 slot of each job; round 2 re-balanced
+    // them on the per-job end times of the kernel's own timeline (tools/timeline_wgrad.py): on 148 SMs
+    // {16, 14 x 7, 20, 14} ends every job within 5 % (the feature job J8 also reduces d(alpha_linear.weight) and has the
+    // widest spread; J0 issues 12 N=64 MMAs per slot): 3.62 -> 3.38 ms per step (profiles/r2zz_wgrad_alloc*.txt).
+    static const int weight[wgrad::NJOBS] = {16, 14, 14, 14, 14, 14, 14, 14, 20, 14};
     static int ncta_env = -1;     // experiment knob: wgrad on fewer SMs (is it still HBM-bound?  profiles/README.md, round 2)
     if (ncta_env < 0) { const char* e = getenv("SCNERF_WGRAD_CTAS"); ncta_env = e ? atoi(e) : 0; }
     const int ncta = std::max(ncta_env > 0 ? std::min(ncta_env, device_sm_count()) : device_sm_count(), wgrad::NJOBS);
     int wsum = 0, used = 0, n[wgrad::NJOBS];
     for (int j = 0; j < wgrad::NJOBS; ++j) wsum += weight[j];
     for (int j = 0; j < wgrad::NJOBS; ++j) { n[j] = std::max(1, ncta * weight[j] / wsum); used += n[j]; }
-    for (int j = 0; used < ncta; j = (j + 1) % wgrad::NJOBS)     // leftovers to the heaviest jobs first
-      if (weight[j] >= 1385 || used + wgrad::NJOBS <= ncta) { ++n[j]; ++used; }
+    static const int order[wgrad::NJOBS] = {8, 0, 1, 2, 3, 4, 5, 6, 7, 9};     // leftovers (other SM counts): heaviest jobs first
+    for (int k = 0; used < ncta; k = (k + 1) % wgrad::NJOBS) { ++n[order[k]]; ++used; }
+    {   // experiment knob: explicit CTAs per job, "a,b,...,j" (10 numbers summing to at most the SM count)
+      static int alloc_env[wgrad::NJOBS] = {-1};
+      if (alloc_env[0] == -1) {
+        alloc_env[0] = 0;
+        if (const char* e = getenv("SCNERF_WGRAD_ALLOC")) {
+          int v[wgrad::NJOBS], k = 0, sum = 0;
+          for (const char* q = e; *q && k < wgrad::NJOBS; ++k) { v[k] = atoi(q); sum += v[k]; while (*q && *q != ',') ++q; if (*q == ',') ++q; }
+          if (k == wgrad::NJOBS && sum <= device_sm_count()) for (int j = 0; j < wgrad::NJOBS; ++j) alloc_env[j] = std::max(1, v[j]);
+        }
+      }
+      if (alloc_env[0] > 0 && ncta_env <= 0) for (int j = 0; j < wgrad::NJOBS; ++j) n[j] = alloc_env[j];
+    }
     w.cta0[0] = 0;
     for (int j = 0; j < wgrad::NJOBS; ++j) w.cta0[j + 1] = w.cta0[j] + n[j];
   }

@@ -31,7 +31,7 @@ nct = 148
 c = b[T * 8 * 4: T * 8 * 4 + nct * 4].reshape(nct, 4)
 g0 = c[:, 0].min()
 import numpy as np
-alloc = [18, 14, 14, 14, 14, 14, 14, 14, 19, 13]          # field_tc.cuh: CTAs per job on a 148-SM part
+alloc = [int(x) for x in os.environ.get("SCNERF_WGRAD_ALLOC", "16,14,14,14,14,14,14,14,20,14").split(",")]   # field_tc.cuh: CTAs per job on a 148-SM part
 print("per job: start_us  loop_end_us  end_us  sm_cycles (min..max over the job's CTAs)")
 o = 0
 for j, n in enumerate(alloc):
