@@ -608,6 +608,14 @@ __global__ void __launch_bounds__(320, 1) field_fwd_pipe_kernel(const __grid_con
   }
   tc::tc_fence_before();
   __syncthreads();
+#ifdef SCNERF_TIMELINE
+  // per-CTA end stamps behind the [tile][stage][16] block: how evenly does the static round-robin tile split end?
+  if (a.dbg != nullptr && tid == 0) {
+    unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    a.dbg[(size_t)a.dbg_tiles * NSTAGE * 16 + blockIdx.x * 2] = (long long)t;
+    a.dbg[(size_t)a.dbg_tiles * NSTAGE * 16 + blockIdx.x * 2 + 1] = tile_count;
+  }
+#endif
   if (warp == 1) tc::tmem_dealloc(tmem, 512);
 }
 

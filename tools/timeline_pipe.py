@@ -13,7 +13,7 @@ lib = _lib.load()
 mods = build_modules(0, "cuda:0")
 TRAIN = len(sys.argv) > 2 and sys.argv[2] == "train"     # training step: the fine-pass forward (image dumps on) stamps last
 T = 4
-buf = torch.zeros(T, 10, 16, dtype=torch.int64, device="cuda")
+buf = torch.zeros(T * 10 * 16 + 2 * 160, dtype=torch.int64, device="cuda")     # + per-CTA (end time, tiles) pairs
 if TRAIN:
     from scnerf_b200 import synth
     from scnerf_b200.engine import TrainStep
@@ -31,7 +31,10 @@ else:
     run_network(pts, vd, mods["fine"], None, None, precision=prec)
 torch.cuda.synchronize()
 lib.scnerf_debug_timeline(None, 0)
-b = buf.cpu().numpy()
+raw = buf.cpu().numpy()
+b = raw[:T * 10 * 16].reshape(T, 10, 16)
+ends = raw[T * 10 * 16:].reshape(-1, 2)
+ends = ends[ends[:, 0] > 0]
 stamps = np.delete(b, [11, 15], axis=2)      # slots 11 / 15 are cycle counts, not stamps
 t0 = stamps[stamps > 0].min()
 print(prec, "TRAIN" if TRAIN else "INFER", "stage: mma_a1 mma_a2 commit0 commit1 | epi_accf0 epi_a1 epi_accf1 epi_a2   (cycles from the first stamp)")
@@ -43,3 +46,9 @@ for t in range(1, 3):
               f" | epi0 quarters handed over at +{int(r[9] - r[4]):5d} +{int(r[10] - r[4]):5d}"
               f" | epi1 at +{int(r[13] - r[6]):5d} +{int(r[14] - r[6]):5d} | weight-ring waits h0 {int(b[t, s, 11]):5d} h1 {int(b[t, s, 15]):5d}")
     print(f"tile {t} total cycles: {b[t + 1, 0, 0] - b[t, 0, 0]}")
+if len(ends):
+    e = (ends[:, 0] - ends[:, 0].min()) / 1e3
+    for n in sorted(set(ends[:, 1])):
+        m = ends[:, 1] == n
+        print(f"CTAs with {int(n)} tiles: {int(m.sum()):3d}; end time relative to the first CTA to finish: min {e[m].min():7.1f}  mean {e[m].mean():7.1f}  max {e[m].max():7.1f} us")
+    print(f"all {len(e)} CTAs: last - first = {e.max():.1f} us, mean - first = {e.mean():.1f} us")
