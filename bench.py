@@ -356,8 +356,8 @@ class NerfppWorkload:
 
 
 # launch sites of the three tensor-core kernel classes (names as SCNERF_LAUNCH stringifies them)
-KCLASS = (("fwd", ("field_fwd_pipe_kernel", "field_fused_fwd_kernel")),
-          ("dgrad", ("field_dgrad_pipe_kernel", "field_fused_dgrad_kernel")),
+KCLASS = (("fwd", ("field_fwd_pipe_kernel",)),
+          ("dgrad", ("field_dgrad_pipe_kernel",)),
           ("wgrad", ("field_wgrad_kernel",)))
 
 
